@@ -1,0 +1,168 @@
+/*
+ * sdb200.h — C ABI of libsdb200.so, the sm_100a kernel library under the Stable Diffusion
+ * sampling path (CLIP -> [VAE encoder] -> DDPM/UNet loop with CFG -> VAE decoder).
+ *
+ * The reference (dawmro/pytorch_stable_diffusion) has no FFI layer: every arithmetic call is a
+ * torch.nn / torch.nn.functional call inside sd/*.py. Each entry point below names the reference
+ * call sites it replaces (paths relative to the reference checkout). Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked "host";
+ *   - activations are NHWC (tokens x channels) bf16 unless stated otherwise; weights are bf16,
+ *     K-major ([out][in], 3x3 convs packed as [out][ky][kx][in]); biases and norm affine
+ *     parameters are fp32;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous, allocates nothing,
+ *     never synchronises, and is legal under CUDA-graph stream capture;
+ *   - return 0 on success, negative on error (SDB_ERR_*); sdb_last_error() gives the text.
+ */
+#ifndef SDB200_H_
+#define SDB200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_ABI_VERSION 1
+
+#define SDB_OK 0
+#define SDB_ERR_ARG (-1)
+#define SDB_ERR_UNSUPPORTED (-2)
+#define SDB_ERR_CUDA (-3)
+#define SDB_ERR_DRIVER (-4)
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int sdb_abi_version(void);
+const char* sdb_last_error(void);
+/* Reads and clears the device watchdog word (non-zero = an mbarrier wait timed out inside a
+ * kernel: (site << 8) | kind). Synchronises the device; for tests and smoke runs only. */
+int sdb_read_fault(unsigned int* out_host);
+
+/* ---- tensor-core GEMM / implicit-GEMM convolution ---------------------------------------- */
+enum {
+  SDB_GEMM_LINEAR = 0,            /* out[M,Cout] = A[M,C0(+C1)] . W^T   (nn.Linear, 1x1 conv)   */
+  SDB_GEMM_CONV3X3_S1 = 1,        /* 3x3, stride 1, pad 1                                        */
+  SDB_GEMM_CONV3X3_S2 = 2,        /* 3x3, stride 2, pad 1   (sd/diffusion.py:553,561,569)        */
+  SDB_GEMM_CONV3X3_S2_PAD_RB = 3  /* 3x3, stride 2, pad right/bottom only (sd/encoder.py:120-122)*/
+};
+enum { SDB_ACT_NONE = 0, SDB_ACT_QUICK_GELU = 1, SDB_ACT_SILU = 2 };
+
+typedef struct sdb_gemm_args {
+  int kind;               /* SDB_GEMM_*                                                          */
+  const void* a0;         /* bf16 activations, source 0: [M, lda0] or NHWC [NB, HI, WI, C0]      */
+  const void* a1;         /* optional source 1 (channel concatenation without a copy), or NULL   */
+  const void* w;          /* bf16 weights [Cout, ldw], row = taps * (C0 + C1) values             */
+  const float* bias;      /* fp32 [Cout] (or [M] when bias_per_row), or NULL                     */
+  const void* residual;   /* bf16 [M, ldr] added after the activation, or NULL                   */
+  void* out;              /* bf16 (or fp32 when out_fp32) [M, ldo]                               */
+  float* workspace;       /* fp32 [nsplit, M, Cout] when nsplit > 1                              */
+  int M;                  /* rows (LINEAR only)                                                  */
+  int NB, HI, WI;         /* input batch / height / width (CONV only)                            */
+  int C0, C1;             /* channels of source 0 / 1                                            */
+  int Cout;
+  long long lda0, lda1;   /* row strides in elements for LINEAR (0 = dense)                      */
+  long long ldw;          /* weight row stride in elements (0 = dense)                           */
+  long long ldo, ldr;     /* output / residual row strides in elements (0 = Cout)                */
+  int out_fp32;
+  int bias_per_row;
+  int act;                /* SDB_ACT_*                                                           */
+  int block_n;            /* 0 = choose; else multiple of 16 in [16, 256]                        */
+  int nsplit;             /* split-K factor, 0/1 = none                                          */
+  int smem_budget;        /* bytes of shared memory for the pipeline, 0 = choose                 */
+} sdb_gemm_args;
+
+/* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,
+ * 545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112,121,129,235-339;
+ * sd/encoder.py:56-92; sd/clip.py:117,121. */
+int sdb_gemm_tc(const sdb_gemm_args* args, void* stream);
+
+/* ---- attention ----------------------------------------------------------------------------- */
+typedef struct sdb_attn_args {
+  const void* q;          /* bf16, token (n, s) head h at q + ((n*S + s) * ldq + h*d)            */
+  const void* k;          /* bf16, key (n, t) head h at k + ((n*Skv_pad + t) * ldk + h*d)        */
+  const void* vt;         /* bf16 V transposed: channel c of key (n, t) at vt + (c*NB + n)*Skv_pad + t */
+  void* out;              /* bf16 [NB*S, ldo], head h at column h*d                              */
+  int NB, heads, d;       /* d = head dim (multiple of 8, <= 160)                                */
+  int S;                  /* queries per sample                                                  */
+  int Skv;                /* valid keys per sample                                               */
+  int Skv_pad;            /* allocated keys per sample (multiple of 8, >= Skv)                   */
+  long long ldq, ldk, ldo;
+  int causal;             /* key t visible to query s iff t <= s (sd/attention.py:58-62)         */
+  float scale;            /* 1/sqrt(d) (sd/attention.py:66,223)                                  */
+} sdb_attn_args;
+
+/* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),
+ * :219-234 (cross). */
+int sdb_attention(const sdb_attn_args* args, void* stream);
+
+/* ---- normalisation (HBM-bound) ------------------------------------------------------------ */
+/* GroupNorm statistics over NHWC bf16 x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0):
+ * stats[n][g] = {sum, sum of squares} in fp64; stats must be zeroed by the caller
+ * (sdb_fill_zero). nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;
+ * sd/encoder.py:86. */
+int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, long long HW,
+                        int C0, int C1, int groups, void* stream);
+/* y = (x - mean) * rstd * gamma + beta, optionally followed by SiLU (F.silu: sd/diffusion.py:176,
+ * 202,738; sd/decoder.py:162,175,335); writes bf16 NHWC [NB, HW, C0 + C1]. */
+int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats, const float* gamma,
+                        const float* beta, void* out, int NB, long long HW, int C0, int C1,
+                        int groups, float eps, int silu, void* stream);
+/* nn.LayerNorm over the last axis (sd/diffusion.py:258,261,264; sd/clip.py:105,113,225).
+ * x bf16 [rows, C] -> out bf16 (or fp32 when out_fp32). */
+int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out, long long rows,
+                  int C, float eps, int out_fp32, void* stream);
+/* Row softmax of fp32 scores * scale -> bf16 probabilities (VAE attention, sd/attention.py:66-71). */
+int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols, float scale,
+                     void* stream);
+
+/* ---- layout / elementwise ------------------------------------------------------------------ */
+int sdb_fill_zero(void* ptr, long long bytes, void* stream);
+/* fp32 NCHW [NB, C, H, W] -> bf16 NHWC [NB*repeat, H, W, C], value * scale; `repeat` tiles the
+ * batch (latents.repeat(2,1,1,1), sd/pipeline.py:221). */
+int sdb_nchw_f32_to_nhwc_bf16(const float* x, void* out, int NB, int C, int H, int W, int repeat,
+                              float scale, void* stream);
+/* NHWC (bf16, or fp32 when in_fp32) -> fp32 NCHW. */
+int sdb_nhwc_to_nchw_f32(const void* x, float* out, int NB, int C, int H, int W, int in_fp32,
+                         void* stream);
+/* Nearest-neighbour x2 (F.interpolate sd/diffusion.py:430; nn.Upsample sd/decoder.py:269). */
+int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int W, int C, void* stream);
+/* Direct convolution for tiny channel counts (Cin <= 8 or Cout <= 8): k in {1, 3}, stride 1,
+ * pad (k-1)/2. x bf16 NHWC, w fp32 [Cout][k*k][Cin], out bf16 or fp32 NHWC.
+ * sd/diffusion.py:545; sd/decoder.py:235,239; sd/encoder.py:56,92. */
+int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, int NB, int H,
+                    int W, int Cin, int Cout, int ksize, int out_fp32, void* stream);
+/* y[r, n] = act_out( sum_k act_in(x[r, k]) * W[n, k] + bias[n] ), fp32 activations, bf16 weights.
+ * The time path: TimeEmbedding (sd/diffusion.py:64-76) and SiLU+linear_time (:184-187). */
+int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R, int K,
+                     int N, int act_in, int act_out, void* stream);
+/* Fused classifier-free guidance + DDPM ancestral step (sd/pipeline.py:228-237,
+ * sd/ddpm.py:102-139). eps: fp32 NHWC [2*NB (or NB when !do_cfg), H, W, C]; latents/noise: fp32
+ * NCHW [NB, C, H, W]; coef: device fp32 [steps][5] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt,
+ * sigma_t}; writes latents in place and the next UNet input (bf16 NHWC, batch tiled x2 when
+ * do_cfg) to next_in when non-NULL. */
+int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise, const float* coef,
+                      int step, float cfg_scale, int do_cfg, void* next_in, int NB, int C, int H,
+                      int W, void* stream);
+/* VAE_AttentionBlock tail as the reference computes it (sd/decoder.py:62-71): the (n, hw, c)
+ * attention output is re-viewed raw as (n, c, h, w) and added to the residual.
+ * y, res, out: bf16 NHWC [NB, HW, C]. out[n, p, c] = y_flat[n][c*HW + p] + res[n, p, c]. */
+int sdb_vae_attn_scramble_add(const void* y, const void* res, void* out, int NB, long long HW,
+                              int C, void* stream);
+/* VAE encoder tail (sd/encoder.py:127-152): moments fp32 NHWC [NB, H, W, 8] + noise fp32 NCHW
+ * [NB, 4, H, W] -> latents fp32 NCHW: (mean + exp(clamp(logvar,-30,20))^0.5 * noise) * 0.18215. */
+int sdb_vae_encode_tail(const float* moments, const float* noise, float* out, int NB, int H, int W,
+                        void* stream);
+/* DDPMSampler.add_noise (sd/ddpm.py:143-186): out = sa * x + sb * noise (fp32, any shape). */
+int sdb_axpby(const float* x, const float* y, float* out, float a, float b, long long n,
+              void* stream);
+/* Post-processing (sd/pipeline.py:253-259): fp32 NHWC in [-1,1] -> uint8 NHWC, rescale to
+ * [0,255], clamp, truncating cast. */
+int sdb_image_to_uint8(const float* x, unsigned char* out, long long n, void* stream);
+/* Pre-processing (sd/pipeline.py:162-173): uint8 HWC -> bf16 NHWC in [-1,1]. */
+int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, void* stream);
+/* CLIPEmbedding (sd/clip.py:58-63): out[b, t, :] = table[tokens[b, t]] + pos[t]; rows
+ * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out bf16 [NB, T_pad, D]. */
+int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,
+                   int T, int T_pad, int D, int vocab, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H_ */

@@ -1,0 +1,440 @@
+// Layout conversion, small direct convolutions, the time path, the fused CFG + DDPM step and the
+// pre/post-processing kernels. None of these is GEMM-shaped; they are sized for coalesced HBM
+// traffic (or are latency-bound at a few KiB, like the sampler step).
+#include "common.cuh"
+#include "host.h"
+#include "../../include/sdb200.h"
+
+namespace sdb {
+
+static inline int grid_for(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void fill_zero_kernel(uint4* p, long long n16, unsigned char* tail, int ntail) {
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < n16; i += step) p[i] = make_uint4(0, 0, 0, 0);
+  if (i0 < ntail) tail[i0] = 0;
+}
+
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                             int NB, int C, int H, int W, int repeat, float scale) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)NB * repeat * hw * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long p = (i / C) % hw;
+    const int n = (int)(i / (C * hw));
+    const int ns = n % NB;
+    out[i] = __float2bfloat16_rn(x[((long long)ns * C + c) * hw + p] * scale);
+  }
+}
+
+__global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ x, float* __restrict__ out, int NB,
+                                        int C, int H, int W, int in_fp32) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)NB * hw * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw;
+    const int c = (int)((i / hw) % C);
+    const int n = (int)(i / (hw * C));
+    const long long src = ((long long)n * hw + p) * C + c;
+    out[i] = in_fp32 ? reinterpret_cast<const float*>(x)[src]
+                     : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[src]);
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int NB, int H,
+                                  int W, int V) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = (long long)NB * Ho * Wo * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    long long r = i / V;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int n = (int)(r / Ho);
+    out[i] = __ldg(x + (((long long)n * H + (ho >> 1)) * W + (wo >> 1)) * V + v);
+  }
+}
+
+// Direct convolution, Cin <= 8: one thread = one output pixel x 8 output channels; the weights sit in
+// shared memory transposed to [k*k*Cin][Cout] so a warp reads consecutive words.
+template <int KS>
+__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, void* __restrict__ out, int NB,
+                                   int H, int W, int Cin, int Cout, int out_fp32) {
+  extern __shared__ float s_w[];  // [KS*KS*Cin][CoutPad]
+  const int CoutPad = (Cout + 7) & ~7;
+  const int K = KS * KS * Cin;
+  for (int i = threadIdx.x; i < K * CoutPad; i += blockDim.x) {
+    const int co = i % CoutPad, k = i / CoutPad;
+    s_w[i] = (co < Cout) ? w[(long long)co * K + k] : 0.f;
+  }
+  __syncthreads();
+  const int G = CoutPad >> 3;
+  const long long total = (long long)NB * H * W * G;
+  constexpr int PAD = (KS - 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int wo = (int)(r % W); r /= W;
+    const int ho = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      acc[j] = (bias != nullptr && co < Cout) ? bias[co] : 0.f;
+    }
+    for (int ky = 0; ky < KS; ++ky) {
+      const int hi = ho + ky - PAD;
+      if (hi < 0 || hi >= H) continue;
+      for (int kx = 0; kx < KS; ++kx) {
+        const int wi = wo + kx - PAD;
+        if (wi < 0 || wi >= W) continue;
+        const __nv_bfloat16* px = x + (((long long)n * H + hi) * W + wi) * Cin;
+        const float* wk = s_w + (long long)((ky * KS + kx) * Cin) * CoutPad + g * 8;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float a = __bfloat162float(px[ci]);
+          const float4 w0 = *reinterpret_cast<const float4*>(wk + ci * CoutPad);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + ci * CoutPad + 4);
+          acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
+          acc[4] += a * w1.x; acc[5] += a * w1.y; acc[6] += a * w1.z; acc[7] += a * w1.w;
+        }
+      }
+    }
+    const long long obase = (((long long)n * H + ho) * W + wo) * Cout + g * 8;
+    for (int j = 0; j < 8; ++j) {
+      if (g * 8 + j < Cout) {
+        if (out_fp32) reinterpret_cast<float*>(out)[obase + j] = acc[j];
+        else reinterpret_cast<__nv_bfloat16*>(out)[obase + j] = __float2bfloat16_rn(acc[j]);
+      }
+    }
+  }
+}
+
+// One warp per output element (r, n).
+__global__ void small_linear_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int R,
+                                    int K, int N, int act_in, int act_out) {
+  const long long gw = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)R * N) return;
+  const int n = (int)(gw % N);
+  const int r = (int)(gw / N);
+  const float* xr = x + (long long)r * K;
+  const __nv_bfloat16* wr = w + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float a = xr[k];
+    if (act_in == SDB_ACT_SILU) a = a / (1.0f + expf(-a));
+    acc += a * __bfloat162float(wr[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (bias) acc += bias[n];
+    if (act_out == SDB_ACT_SILU) acc = acc / (1.0f + expf(-acc));
+    out[(long long)r * N + n] = acc;
+  }
+}
+
+__global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* __restrict__ eps,
+                                     const float* __restrict__ noise, const float* __restrict__ coef,
+                                     int step, float cfg_scale, int do_cfg,
+                                     __nv_bfloat16* __restrict__ next_in, int NB, int C, int H, int W) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)NB * C * hw;
+  const float sb = coef[step * 5 + 0];   // sqrt(1 - abar_t)
+  const float sa = coef[step * 5 + 1];   // sqrt(abar_t)
+  const float c_x0 = coef[step * 5 + 2];
+  const float c_xt = coef[step * 5 + 3];
+  const float sigma = coef[step * 5 + 4];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw;
+    const int c = (int)((i / hw) % C);
+    const int n = (int)(i / (hw * C));
+    const long long e_idx = ((long long)n * hw + p) * C + c;
+    float e;
+    if (do_cfg) {
+      const float ec = eps[e_idx];
+      const float eu = eps[e_idx + (long long)NB * hw * C];
+      e = cfg_scale * (ec - eu) + eu;
+    } else {
+      e = eps[e_idx];
+    }
+    const float xt = latents[i];
+    const float x0 = (xt - sb * e) / sa;
+    float xn = c_x0 * x0 + c_xt * xt;
+    if (sigma != 0.f && noise != nullptr) xn += sigma * noise[i];
+    latents[i] = xn;
+    if (next_in != nullptr) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(xn);
+      next_in[e_idx] = b;
+      if (do_cfg) next_in[e_idx + (long long)NB * hw * C] = b;
+    }
+  }
+}
+
+// out[n][p][c] = y_flat[n][c*HW + p] + res[n][p][c]: a 32x32 shared-memory transpose of y viewed as
+// [C][HW].
+__global__ void vae_scramble_add_kernel(const __nv_bfloat16* __restrict__ y,
+                                        const __nv_bfloat16* __restrict__ res,
+                                        __nv_bfloat16* __restrict__ out, long long HW, int C) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const __nv_bfloat16* yn = y + (long long)n * HW * C;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const long long p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? __bfloat162float(yn[(long long)c * HW + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const long long p = p0 + j;
+    const int c = c0 + tx;
+    if (p < HW && c < C) {
+      const long long o = ((long long)n * HW + p) * C + c;
+      out[o] = __float2bfloat16_rn(tile[tx][j] + __bfloat162float(res[o]));
+    }
+  }
+}
+
+__global__ void vae_encode_tail_kernel(const float* __restrict__ moments, const float* __restrict__ noise,
+                                       float* __restrict__ out, int NB, int H, int W) {
+  const long long hw = (long long)H * W;
+  const long long total = (long long)NB * 4 * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw;
+    const int c = (int)((i / hw) % 4);
+    const int n = (int)(i / (hw * 4));
+    const float* m = moments + ((long long)n * hw + p) * 8;
+    const float mean = m[c];
+    float lv = m[4 + c];
+    lv = fminf(fmaxf(lv, -30.f), 20.f);
+    const float stdev = sqrtf(expf(lv));
+    out[i] = (mean + stdev * noise[i]) * 0.18215f;
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                             float* __restrict__ out, float a, float b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = a * x[i] + b * y[i];
+}
+
+__global__ void image_to_uint8_kernel(const float* __restrict__ x, unsigned char* __restrict__ out,
+                                      long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    // rescale (-1,1) -> (0,255) in the reference's operation order: x -= -1; x *= 255/2; x += 0
+    float v = x[i];
+    v -= -1.0f;
+    v *= 127.5f;
+    v += 0.0f;
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = (unsigned char)v;  // truncation, as torch's float -> uint8 cast
+  }
+}
+
+__global__ void uint8_to_image_kernel(const unsigned char* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                      long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = (float)x[i];
+    v -= 0.0f;
+    v *= (2.0f / 255.0f);
+    v += -1.0f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void clip_embed_kernel(const long long* __restrict__ tokens, const float* __restrict__ table,
+                                  const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int NB,
+                                  int T, int T_pad, int D, int vocab) {
+  const long long total = (long long)NB * T_pad * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const int t = (int)((i / D) % T_pad);
+    const int b = (int)(i / ((long long)D * T_pad));
+    float v = 0.f;
+    if (t < T) {
+      long long tok = tokens[(long long)b * T + t];
+      if (tok < 0) tok = 0;
+      if (tok >= vocab) tok = vocab - 1;
+      v = table[tok * D + d] + pos[(long long)t * D + d];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+#define SDB_STREAM ((cudaStream_t)stream)
+
+extern "C" int sdb_fill_zero(void* ptr, long long bytes, void* stream) {
+  if (!ptr || bytes < 0) { set_error("sdb_fill_zero: bad arguments"); return SDB_ERR_ARG; }
+  if (bytes == 0) return SDB_OK;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) {
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, SDB_STREAM);
+    if (e != cudaSuccess) { set_error("sdb_fill_zero: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
+    return SDB_OK;
+  }
+  const long long n16 = bytes / 16;
+  const int ntail = (int)(bytes % 16);
+  fill_zero_kernel<<<grid_for(n16 > 0 ? n16 : 1, 256), 256, 0, SDB_STREAM>>>(
+      (uint4*)ptr, n16, (unsigned char*)ptr + n16 * 16, ntail);
+  return check_launch("fill_zero_kernel");
+}
+
+extern "C" int sdb_nchw_f32_to_nhwc_bf16(const float* x, void* out, int NB, int C, int H, int W,
+                                         int repeat, float scale, void* stream) {
+  if (!x || !out || NB <= 0 || C <= 0 || H <= 0 || W <= 0 || repeat <= 0) {
+    set_error("sdb_nchw_f32_to_nhwc_bf16: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * repeat * C * H * W;
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
+      x, (__nv_bfloat16*)out, NB, C, H, W, repeat, scale);
+  return check_launch("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+extern "C" int sdb_nhwc_to_nchw_f32(const void* x, float* out, int NB, int C, int H, int W,
+                                    int in_fp32, void* stream) {
+  if (!x || !out || NB <= 0 || C <= 0 || H <= 0 || W <= 0) {
+    set_error("sdb_nhwc_to_nchw_f32: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * C * H * W;
+  nhwc_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(x, out, NB, C, H, W, in_fp32);
+  return check_launch("nhwc_to_nchw_f32_kernel");
+}
+
+extern "C" int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int W, int C, void* stream) {
+  if (!x || !out || NB <= 0 || H <= 0 || W <= 0 || C % 8 != 0) {
+    set_error("sdb_upsample2x_nhwc: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>((const uint4*)x, (uint4*)out, NB, H, W,
+                                                                  C / 8);
+  return check_launch("upsample2x_kernel");
+}
+
+extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, int NB,
+                               int H, int W, int Cin, int Cout, int ksize, int out_fp32, void* stream) {
+  if (!x || !w || !out || NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 ||
+      (ksize != 1 && ksize != 3)) {
+    set_error("sdb_conv_direct: bad arguments (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
+    return SDB_ERR_ARG;
+  }
+  const int CoutPad = (Cout + 7) & ~7;
+  const size_t smem = (size_t)ksize * ksize * Cin * CoutPad * sizeof(float);
+  if (smem > 160 * 1024) { set_error("sdb_conv_direct: weights too large"); return SDB_ERR_UNSUPPORTED; }
+  const long long total = (long long)NB * H * W * (CoutPad / 8);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(conv_direct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = true;
+  }
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (ksize == 1)
+    conv_direct_kernel<1><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>((const __nv_bfloat16*)x, w, bias, out,
+                                                                       NB, H, W, Cin, Cout, out_fp32);
+  else
+    conv_direct_kernel<3><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>((const __nv_bfloat16*)x, w, bias, out,
+                                                                       NB, H, W, Cin, Cout, out_fp32);
+  return check_launch("conv_direct_kernel");
+}
+
+extern "C" int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R,
+                                int K, int N, int act_in, int act_out, void* stream) {
+  if (!x || !w || !out || R <= 0 || K <= 0 || N <= 0) {
+    set_error("sdb_small_linear: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long warps = (long long)R * N;
+  const long long blocks = (warps + 7) / 8;
+  small_linear_kernel<<<(unsigned)blocks, 256, 0, SDB_STREAM>>>(x, (const __nv_bfloat16*)w, bias, out, R, K,
+                                                                N, act_in, act_out);
+  return check_launch("small_linear_kernel");
+}
+
+extern "C" int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise,
+                                 const float* coef, int step, float cfg_scale, int do_cfg,
+                                 void* next_in, int NB, int C, int H, int W, void* stream) {
+  if (!latents || !eps || !coef || step < 0 || NB <= 0 || C <= 0 || H <= 0 || W <= 0) {
+    set_error("sdb_cfg_ddpm_step: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * C * H * W;
+  cfg_ddpm_step_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
+      latents, eps, noise, coef, step, cfg_scale, do_cfg, (__nv_bfloat16*)next_in, NB, C, H, W);
+  return check_launch("cfg_ddpm_step_kernel");
+}
+
+extern "C" int sdb_vae_attn_scramble_add(const void* y, const void* res, void* out, int NB,
+                                         long long HW, int C, void* stream) {
+  if (!y || !res || !out || NB <= 0 || HW <= 0 || C <= 0) {
+    set_error("sdb_vae_attn_scramble_add: bad arguments"); return SDB_ERR_ARG;
+  }
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)NB);
+  vae_scramble_add_kernel<<<grid, dim3(32, 8), 0, SDB_STREAM>>>(
+      (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, HW, C);
+  return check_launch("vae_scramble_add_kernel");
+}
+
+extern "C" int sdb_vae_encode_tail(const float* moments, const float* noise, float* out, int NB, int H,
+                                   int W, void* stream) {
+  if (!moments || !noise || !out || NB <= 0 || H <= 0 || W <= 0) {
+    set_error("sdb_vae_encode_tail: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * 4 * H * W;
+  vae_encode_tail_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(moments, noise, out, NB, H, W);
+  return check_launch("vae_encode_tail_kernel");
+}
+
+extern "C" int sdb_axpby(const float* x, const float* y, float* out, float a, float b, long long n,
+                         void* stream) {
+  if (!x || !y || !out || n <= 0) { set_error("sdb_axpby: bad arguments"); return SDB_ERR_ARG; }
+  axpby_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, y, out, a, b, n);
+  return check_launch("axpby_kernel");
+}
+
+extern "C" int sdb_image_to_uint8(const float* x, unsigned char* out, long long n, void* stream) {
+  if (!x || !out || n <= 0) { set_error("sdb_image_to_uint8: bad arguments"); return SDB_ERR_ARG; }
+  image_to_uint8_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, out, n);
+  return check_launch("image_to_uint8_kernel");
+}
+
+extern "C" int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, void* stream) {
+  if (!x || !out || n <= 0) { set_error("sdb_uint8_to_image: bad arguments"); return SDB_ERR_ARG; }
+  uint8_to_image_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, (__nv_bfloat16*)out, n);
+  return check_launch("uint8_to_image_kernel");
+}
+
+extern "C" int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out,
+                              int NB, int T, int T_pad, int D, int vocab, void* stream) {
+  if (!tokens || !table || !pos || !out || NB <= 0 || T <= 0 || T_pad < T || D <= 0 || vocab <= 0) {
+    set_error("sdb_clip_embed: bad arguments"); return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * T_pad * D;
+  clip_embed_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(tokens, table, pos, (__nv_bfloat16*)out, NB,
+                                                                  T, T_pad, D, vocab);
+  return check_launch("clip_embed_kernel");
+}

@@ -1,0 +1,320 @@
+// HBM-bound normalisation kernels: GroupNorm (statistics + apply[+SiLU]), LayerNorm, row softmax.
+// All reductions are fp32 per thread and fp64 across threads/blocks; activations are bf16 NHWC.
+#include "common.cuh"
+#include "host.h"
+#include "../../include/sdb200.h"
+
+namespace sdb {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// Thread layout shared by stats and apply: V = (C0+C1)/8 16-byte vectors per pixel; a block holds
+// `lanes` pixels side by side, thread t -> (vector t % V, pixel lane t / V). Each thread keeps the
+// same 8 channels for its whole life, so per-channel state lives in registers.
+// grid = (chunks, NB); every block walks pixels [chunk*ppc, (chunk+1)*ppc).
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
+                                const __nv_bfloat16* __restrict__ x1, double* __restrict__ stats,
+                                long long HW, int C0, int C1, int groups, long long ppc, int V,
+                                int lanes) {
+  __shared__ float s_sum[64];
+  __shared__ float s_sq[64];
+  const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  for (int i = t; i < groups; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+  __syncthreads();
+  const int v = t % V;
+  const int pl = t / V;
+  const int V0 = C0 >> 3;
+  const int ctot = C0 + C1;
+  const int cpg = ctot / groups;
+  if (pl < lanes) {
+    const bool second = v >= V0;
+    const __nv_bfloat16* base = second ? x1 + (long long)n * HW * C1 + (long long)(v - V0) * 8
+                                       : x0 + (long long)n * HW * C0 + (long long)v * 8;
+    const long long stride = second ? C1 : C0;
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
+    const long long p_begin = (long long)blockIdx.x * ppc;
+    const long long p_end = min(HW, p_begin + ppc);
+    for (long long p = p_begin + pl; p < p_end; p += lanes) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * stride));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
+    }
+    const int c0 = v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      atomicAdd(&s_sum[g], sum[j]);
+      atomicAdd(&s_sq[g], sq[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < groups; i += blockDim.x) {
+    double* dst = stats + ((long long)n * groups + i) * 2;
+    atomicAdd(dst, (double)s_sum[i]);
+    atomicAdd(dst + 1, (double)s_sq[i]);
+  }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
+                                const __nv_bfloat16* __restrict__ x1,
+                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                long long HW, int C0, int C1, int groups, float eps, int silu,
+                                long long ppc, int V, int lanes) {
+  const int n = blockIdx.y;
+  const int t = threadIdx.x;
+  const int v = t % V;
+  const int pl = t / V;
+  if (pl >= lanes) return;
+  const int V0 = C0 >> 3;
+  const int ctot = C0 + C1;
+  const int cpg = ctot / groups;
+  const double cnt = (double)HW * cpg;
+  float sc[8], sh[8];
+  const int c0 = v * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    const double s = stats[((long long)n * groups + g) * 2];
+    const double ss = stats[((long long)n * groups + g) * 2 + 1];
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma[c], be = beta[c];
+    sc[j] = rstd * ga;
+    sh[j] = be - (float)mean * rstd * ga;
+  }
+  const bool second = v >= V0;
+  const __nv_bfloat16* base = second ? x1 + (long long)n * HW * C1 + (long long)(v - V0) * 8
+                                     : x0 + (long long)n * HW * C0 + (long long)v * 8;
+  const long long stride = second ? C1 : C0;
+  __nv_bfloat16* obase = out + (long long)n * HW * ctot + c0;
+  const long long p_begin = (long long)blockIdx.x * ppc;
+  const long long p_end = min(HW, p_begin + ppc);
+  for (long long p = p_begin + pl; p < p_end; p += lanes) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * stride));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = f[j] * sc[j] + sh[j];
+      if (silu) y = silu_f(y);
+      f[j] = y;
+    }
+    *reinterpret_cast<uint4*>(obase + p * ctot) = pack8(f);
+  }
+}
+
+// One warp per row; rows of up to 5*32*8 = 1280 channels are held in registers between the passes.
+constexpr int LN_MAX_VEC_PER_LANE = 5;
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, void* __restrict__ out,
+                                 long long rows, int C, float eps, int out_fp32) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int V = C >> 3;
+  const __nv_bfloat16* xr = x + row * C;
+  float f[LN_MAX_VEC_PER_LANE][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC_PER_LANE; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      unpack8(u, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC_PER_LANE; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_VEC_PER_LANE; ++i) {
+    const int v = lane + i * 32;
+    if (v < V) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        y[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
+      if (out_fp32) {
+        float* o = reinterpret_cast<float*>(out) + row * C + v * 8;
+        *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row * C + v * 8;
+        *reinterpret_cast<uint4*>(o) = pack8(y);
+      }
+    }
+  }
+}
+
+// One block per row, the row staged in shared memory (cols * 4 bytes).
+__global__ void softmax_rows_kernel(const float* __restrict__ scores, __nv_bfloat16* __restrict__ probs,
+                                    int cols, float scale_log2) {
+  extern __shared__ float s_row[];
+  __shared__ float s_red[32];
+  const long long row = blockIdx.x;
+  const float* src = scores + row * cols;
+  const int t = threadIdx.x, nt = blockDim.x;
+  float mx = -INFINITY;
+  for (int i = t; i < cols; i += nt) {
+    const float v = src[i] * scale_log2;
+    s_row[i] = v;
+    mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((t & 31) == 0) s_red[t >> 5] = mx;
+  __syncthreads();
+  if (t < 32) {
+    float v = (t < (nt >> 5)) ? s_red[t] : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (t == 0) s_red[0] = v;
+  }
+  __syncthreads();
+  mx = s_red[0];
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = t; i < cols; i += nt) {
+    const float e = exp2f(s_row[i] - mx);
+    s_row[i] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((t & 31) == 0) s_red[t >> 5] = sum;
+  __syncthreads();
+  if (t < 32) {
+    float v = (t < (nt >> 5)) ? s_red[t] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (t == 0) s_red[0] = v;
+  }
+  __syncthreads();
+  const float inv = 1.0f / s_red[0];
+  __nv_bfloat16* dst = probs + row * cols;
+  for (int i = t; i < cols; i += nt) dst[i] = __float2bfloat16_rn(s_row[i] * inv);
+}
+
+static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* threads,
+                       long long* ppc, int* chunks) {
+  if (ctot % 8 != 0) return -1;
+  *V = ctot / 8;
+  if (*V > 1024) return -1;
+  *lanes = 256 / *V;
+  if (*lanes < 1) *lanes = 1;
+  *threads = *V * *lanes;
+  // aim for ~4 resident blocks per SM across the batch
+  long long want = (148LL * 4 + NB - 1) / NB;
+  long long max_chunks = (HW + *lanes * 4 - 1) / (*lanes * 4);
+  if (want > max_chunks) want = max_chunks;
+  if (want < 1) want = 1;
+  *ppc = (HW + want - 1) / want;
+  *chunks = (int)((HW + *ppc - 1) / *ppc);
+  return 0;
+}
+
+}  // namespace sdb
+
+extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB,
+                                   long long HW, int C0, int C1, int groups, void* stream) {
+  using namespace sdb;
+  const int ctot = C0 + C1;
+  if (!x0 || !stats || NB <= 0 || HW <= 0 || groups <= 0 || groups > 64 || ctot % groups != 0 ||
+      C0 % 8 != 0 || C1 % 8 != 0 || (C1 > 0 && !x1)) {
+    set_error("sdb_groupnorm_stats: bad arguments (C0=%d C1=%d groups=%d)", C0, C1, groups);
+    return SDB_ERR_ARG;
+  }
+  int V, lanes, threads, chunks; long long ppc;
+  if (gn_geometry(NB, HW, ctot, &V, &lanes, &threads, &ppc, &chunks)) {
+    set_error("sdb_groupnorm_stats: unsupported channel count %d", ctot);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  gn_stats_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, stats, HW, C0, C1, groups, ppc, V, lanes);
+  return check_launch("gn_stats_kernel");
+}
+
+extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats,
+                                   const float* gamma, const float* beta, void* out, int NB,
+                                   long long HW, int C0, int C1, int groups, float eps, int silu,
+                                   void* stream) {
+  using namespace sdb;
+  const int ctot = C0 + C1;
+  if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 ||
+      ctot % groups != 0 || C0 % 8 != 0 || C1 % 8 != 0 || (C1 > 0 && !x1)) {
+    set_error("sdb_groupnorm_apply: bad arguments");
+    return SDB_ERR_ARG;
+  }
+  int V, lanes, threads, chunks; long long ppc;
+  if (gn_geometry(NB, HW, ctot, &V, &lanes, &threads, &ppc, &chunks)) {
+    set_error("sdb_groupnorm_apply: unsupported channel count %d", ctot);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  gn_apply_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, stats, gamma, beta, (__nv_bfloat16*)out, HW,
+      C0, C1, groups, eps, silu, ppc, V, lanes);
+  return check_launch("gn_apply_kernel");
+}
+
+extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out,
+                             long long rows, int C, float eps, int out_fp32, void* stream) {
+  using namespace sdb;
+  if (!x || !gamma || !beta || !out || rows <= 0 || C % 8 != 0 || C > LN_MAX_VEC_PER_LANE * 256) {
+    set_error("sdb_layernorm: bad arguments (C=%d)", C);
+    return SDB_ERR_ARG;
+  }
+  const int warps = 8;
+  const long long blocks = (rows + warps - 1) / warps;
+  layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, gamma, beta, out, rows, C, eps, out_fp32);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols,
+                                float scale, void* stream) {
+  using namespace sdb;
+  if (!scores || !probs || rows <= 0 || cols <= 0 || cols > 24576) {
+    set_error("sdb_softmax_rows: bad arguments");
+    return SDB_ERR_ARG;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    configured = true;
+  }
+  softmax_rows_kernel<<<(unsigned)rows, 256, cols * sizeof(float), (cudaStream_t)stream>>>(
+      scores, (__nv_bfloat16*)probs, cols, scale * 1.4426950408889634f);
+  return check_launch("softmax_rows_kernel");
+}

@@ -1,0 +1,285 @@
+"""Thin torch-tensor wrappers over the C ABI (include/sdb200.h).
+
+PyTorch is used for device memory and streams only; every function here launches one (or, for
+GroupNorm and split-K GEMMs, two) hand-written kernels on the current CUDA stream.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _ext
+from ._ext import AttnArgs, GemmArgs
+
+GEMM_LINEAR, GEMM_CONV3X3_S1, GEMM_CONV3X3_S2, GEMM_CONV3X3_S2_PAD_RB = 0, 1, 2, 3
+ACT_NONE, ACT_QUICK_GELU, ACT_SILU = 0, 1, 2
+NUM_SMS = 148
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _choose_block_n(cout):
+    if cout % 256 == 0:
+        return 256
+    if cout % 160 == 0:
+        return 160
+    if cout % 128 == 0:
+        return 128
+    if cout >= 256:
+        return 256
+    return ((cout + 15) // 16) * 16
+
+
+def _choose_split(m_tiles, cout, block_n, nkb):
+    """Split the reduction when the output tiles alone cannot fill the 148 SMs."""
+    tiles = m_tiles * ((cout + block_n - 1) // block_n)
+    if tiles >= NUM_SMS // 2 or nkb < 16:
+        return 1
+    return max(1, min(NUM_SMS // tiles, nkb // 8, 16))
+
+
+def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
+         out=None, out_fp32=False, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
+         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0):
+    """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
+    lib = _ext.lib()
+    _chk(a0, torch.bfloat16, "a0")
+    _chk(w, torch.bfloat16, "w")
+    args = GemmArgs()
+    args.kind = kind
+    args.a0, args.a1, args.w = _p(a0), _p(a1), _p(w)
+    args.bias = _p(_chk(bias, torch.float32, "bias")) if bias is not None else None
+    args.residual = _p(_chk(residual, torch.bfloat16, "residual")) if residual is not None else None
+    if kind == GEMM_LINEAR:
+        if M is None:
+            M = a0.shape[0] if a0.dim() == 2 else a0.numel() // a0.shape[-1]
+        if c0 is None:
+            c0 = a0.shape[-1]
+        args.M = M
+        rows = M
+        ntaps = 1
+        m_tiles = (M + 127) // 128
+    else:
+        nb, hi, wi = conv_dims
+        if c0 is None:
+            c0 = a0.shape[-1]
+        args.NB, args.HI, args.WI = nb, hi, wi
+        s2 = kind != GEMM_CONV3X3_S1
+        ho, wo = (hi // 2, wi // 2) if s2 else (hi, wi)
+        rows = nb * ho * wo
+        ntaps = 9
+        m_tiles = (rows + 127) // 128
+    args.C0, args.C1, args.Cout = c0, c1, cout
+    args.lda0, args.lda1, args.ldw, args.ldo, args.ldr = lda0, lda1, ldw, ldo, ldr
+    if out is None:
+        out = torch.empty((rows, cout), device=a0.device,
+                          dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    args.out = _p(out)
+    args.out_fp32 = 1 if out_fp32 else 0
+    args.bias_per_row = 1 if bias_per_row else 0
+    args.act = act
+    if block_n == 0:
+        block_n = _choose_block_n(cout)
+    args.block_n = block_n
+    nkb = ntaps * ((c0 + 63) // 64 + (c1 + 63) // 64)
+    if nsplit == 0:
+        nsplit = _choose_split(m_tiles, cout, block_n, nkb)
+    ws = None
+    if nsplit > 1:
+        ws = torch.empty((nsplit, rows, cout), device=a0.device, dtype=torch.float32)
+        args.workspace = _p(ws)
+    args.nsplit = nsplit
+    _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
+    return out
+
+
+def linear(x, w, bias=None, **kw):
+    """x: bf16 [M, K] (row stride may exceed K), w: bf16 [Cout, K]."""
+    lda = x.stride(0) if x.dim() == 2 and x.stride(0) != x.shape[1] else 0
+    return gemm(x, w, w.shape[0], kind=GEMM_LINEAR, bias=bias, M=x.shape[0], c0=x.shape[1],
+                lda0=lda, **kw)
+
+
+def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
+    """x: bf16 NHWC [N, H, W, C]; w: bf16 [Cout, 9*C] packed (ky, kx, c). Returns [N, Ho, Wo, Cout]."""
+    n, h, wd, c = x.shape
+    out = gemm(x, w, cout, kind=kind, bias=bias, conv_dims=(n, h, wd), c0=c, **kw)
+    s2 = kind != GEMM_CONV3X3_S1
+    return out.view(n, h // 2 if s2 else h, wd // 2 if s2 else wd, cout)
+
+
+def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False):
+    lib = _ext.lib()
+    a = AttnArgs()
+    a.q, a.k, a.vt, a.out = _p(_chk(q, torch.bfloat16, "q")), _p(_chk(k, torch.bfloat16, "k")), \
+        _p(_chk(vt, torch.bfloat16, "vt")), _p(_chk(out, torch.bfloat16, "out"))
+    a.NB, a.heads, a.d, a.S, a.Skv, a.Skv_pad = NB, heads, d, S, Skv, Skv_pad
+    a.ldq, a.ldk, a.ldo = ldq, ldk, ldo
+    a.causal = 1 if causal else 0
+    a.scale = 1.0 / math.sqrt(d)
+    _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")
+    return out
+
+
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
+    """GroupNorm (+SiLU) over NHWC bf16 x0 ++ x1 (channel concat); returns bf16 [N, H, W, C0+C1]."""
+    lib = _ext.lib()
+    _chk(x0, torch.bfloat16, "x0")
+    n = x0.shape[0]
+    c0 = x0.shape[-1]
+    hw = x0.numel() // (n * c0)
+    c1 = x1.shape[-1] if x1 is not None else 0
+    stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float64)
+    _ext.check(lib.sdb_fill_zero(_p(stats), stats.numel() * 8, _stream()), "sdb_fill_zero")
+    _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, _stream()),
+               "sdb_groupnorm_stats")
+    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
+                                       c0, c1, groups, float(eps), 1 if silu else 0, _stream()),
+               "sdb_groupnorm_apply")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False):
+    lib = _ext.lib()
+    _chk(x, torch.bfloat16, "x")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
+                                 1 if out_fp32 else 0, _stream()), "sdb_layernorm")
+    return out
+
+
+def softmax_rows(scores, scale):
+    lib = _ext.lib()
+    _chk(scores, torch.float32, "scores")
+    rows, cols = scores.shape
+    out = torch.empty((rows, cols), device=scores.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_softmax_rows(_p(scores), _p(out), rows, cols, float(scale), _stream()),
+               "sdb_softmax_rows")
+    return out
+
+
+def nchw_to_nhwc_bf16(x, repeat=1, scale=1.0):
+    lib = _ext.lib()
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n * repeat, h, w, c), device=x.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_nchw_f32_to_nhwc_bf16(_p(x), _p(out), n, c, h, w, repeat, float(scale), _stream()),
+               "sdb_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    lib = _ext.lib()
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    _ext.check(lib.sdb_nhwc_to_nchw_f32(_p(x), _p(out), n, c, h, w, 1 if x.dtype == torch.float32 else 0,
+                                        _stream()), "sdb_nhwc_to_nchw_f32")
+    return out
+
+
+def upsample2x(x):
+    lib = _ext.lib()
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_upsample2x_nhwc(_p(x), _p(out), n, h, w, c, _stream()), "sdb_upsample2x_nhwc")
+    return out
+
+
+def conv_direct(x, w, bias, cout, ksize, out_fp32=False):
+    """x bf16 NHWC with Cin <= 8; w fp32 [Cout, k*k, Cin]."""
+    lib = _ext.lib()
+    n, h, wd, cin = x.shape
+    out = torch.empty((n, h, wd, cout), device=x.device,
+                      dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _ext.check(lib.sdb_conv_direct(_p(x), _p(w), _p(bias), _p(out), n, h, wd, cin, cout, ksize,
+                                   1 if out_fp32 else 0, _stream()), "sdb_conv_direct")
+    return out
+
+
+def small_linear(x, w, bias, act_in=ACT_NONE, act_out=ACT_NONE):
+    lib = _ext.lib()
+    _chk(x, torch.float32, "x")
+    r, k = x.shape
+    n = w.shape[0]
+    out = torch.empty((r, n), device=x.device, dtype=torch.float32)
+    _ext.check(lib.sdb_small_linear(_p(x), _p(w), _p(bias), _p(out), r, k, n, act_in, act_out, _stream()),
+               "sdb_small_linear")
+    return out
+
+
+def cfg_ddpm_step(latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in):
+    lib = _ext.lib()
+    n, c, h, w = latents.shape
+    _ext.check(lib.sdb_cfg_ddpm_step(_p(latents), _p(eps), _p(noise), _p(coef), step, float(cfg_scale),
+                                     1 if do_cfg else 0, _p(next_in), n, c, h, w, _stream()),
+               "sdb_cfg_ddpm_step")
+    return latents
+
+
+def vae_attn_scramble_add(y, res):
+    lib = _ext.lib()
+    n = res.shape[0]
+    c = res.shape[-1]
+    hw = res.numel() // (n * c)
+    out = torch.empty_like(res)
+    _ext.check(lib.sdb_vae_attn_scramble_add(_p(y), _p(res), _p(out), n, hw, c, _stream()),
+               "sdb_vae_attn_scramble_add")
+    return out
+
+
+def vae_encode_tail(moments, noise):
+    lib = _ext.lib()
+    n, h, w, _ = moments.shape
+    out = torch.empty((n, 4, h, w), device=moments.device, dtype=torch.float32)
+    _ext.check(lib.sdb_vae_encode_tail(_p(moments), _p(noise.contiguous()), _p(out), n, h, w, _stream()),
+               "sdb_vae_encode_tail")
+    return out
+
+
+def axpby(x, y, a, b):
+    lib = _ext.lib()
+    out = torch.empty_like(x)
+    _ext.check(lib.sdb_axpby(_p(x), _p(y), _p(out), float(a), float(b), x.numel(), _stream()), "sdb_axpby")
+    return out
+
+
+def image_to_uint8(x):
+    lib = _ext.lib()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    _ext.check(lib.sdb_image_to_uint8(_p(x), _p(out), x.numel(), _stream()), "sdb_image_to_uint8")
+    return out
+
+
+def uint8_to_image(x):
+    lib = _ext.lib()
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_uint8_to_image(_p(x), _p(out), x.numel(), _stream()), "sdb_uint8_to_image")
+    return out
+
+
+def clip_embed(tokens, table, pos, t_pad):
+    lib = _ext.lib()
+    nb, t = tokens.shape
+    vocab, d = table.shape
+    out = torch.empty((nb, t_pad, d), device=tokens.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_clip_embed(_p(tokens), _p(table), _p(pos), _p(out), nb, t, t_pad, d, vocab, _stream()),
+               "sdb_clip_embed")
+    return out

@@ -1,0 +1,342 @@
+"""GPU parity of every kernel against plain fp32 PyTorch on the same (bf16-rounded) inputs.
+
+Tolerances: GEMM/conv/attention outputs are bf16 with fp32 accumulation -> 1e-2 of max|ref|
+(north_star tolerance); fp32-output and normalisation kernels are held tighter.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import report, setup_exact_fp32
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from pytorch_stable_diffusion_b200 import ops
+    return ops
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,K,N,block_n", [
+    (128, 64, 128, 128),      # one tile, one k-block
+    (256, 128, 64, 64),
+    (8192, 320, 960, 160),    # UNet self-attention in_proj @64x64
+    (2048, 1280, 320, 160),
+    (512, 2560, 1280, 256),
+    (154, 768, 320, 160),     # ragged M (context rows)
+    (300, 320, 1280, 0),
+])
+def test_linear_plain(M, K, N, block_n):
+    ops = _ops()
+    setup_exact_fp32()
+    a = rnd(M, K).bfloat16()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    out = ops.linear(a, w, block_n=block_n, nsplit=1)
+    report(f"linear {M}x{K}x{N}", out, a.float() @ w.float().t(), 1e-2)
+
+
+def test_linear_epilogue_bias_act_residual():
+    ops = _ops()
+    setup_exact_fp32()
+    M, K, N = 1000, 640, 640
+    a = rnd(M, K).bfloat16()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    b = rnd(N, seed=2)
+    r = rnd(M, N, seed=3).bfloat16()
+    ref = a.float() @ w.float().t() + b
+    out = ops.linear(a, w, bias=b)
+    report("linear+bias", out, ref, 1e-2)
+    out = ops.linear(a, w, bias=b, residual=r)
+    report("linear+bias+res", out, ref + r.float(), 1e-2)
+    out = ops.linear(a, w, bias=b, act=ops.ACT_QUICK_GELU, residual=r)
+    report("linear+bias+qgelu+res", out, ref * torch.sigmoid(1.702 * ref) + r.float(), 1e-2)
+    out = ops.linear(a, w, bias=b, out_fp32=True)
+    report("linear fp32 out", out, ref, 2e-3)
+
+
+def test_linear_small_n_fp32_and_row_bias():
+    ops = _ops()
+    setup_exact_fp32()
+    M, K = 4096, 320
+    a = rnd(M, K).bfloat16()
+    w = rnd(4, K, scale=K ** -0.5, seed=1).bfloat16()
+    b = rnd(4, seed=2)
+    out = ops.linear(a, w, bias=b, out_fp32=True)
+    report("linear N=4", out, a.float() @ w.float().t() + b, 2e-3)
+    # swapped-operand projection (V^T = Wv . X^T + bv): bias per output row
+    wv = rnd(512, K, scale=K ** -0.5, seed=4).bfloat16()
+    bv = rnd(512, seed=5)
+    out = ops.gemm(wv, a, M, kind=ops.GEMM_LINEAR, M=512, c0=K, bias=bv, bias_per_row=True)
+    report("linear swapped + row bias", out, wv.float() @ a.float().t() + bv[:, None], 1e-2)
+
+
+def test_linear_strided_and_dual_source_and_splitk():
+    ops = _ops()
+    setup_exact_fp32()
+    M, C0, C1, N = 512, 640, 320, 640
+    big = rnd(M, 2 * C0).bfloat16()
+    a0 = big[:, C0:]                      # strided view, lda = 2*C0
+    a1 = rnd(M, C1, seed=7).bfloat16()
+    w = rnd(N, C0 + C1, scale=(C0 + C1) ** -0.5, seed=1).bfloat16()
+    ref = torch.cat([a0.float(), a1.float()], 1) @ w.float().t()
+    out = ops.gemm(a0, w, N, kind=ops.GEMM_LINEAR, a1=a1, M=M, c0=C0, c1=C1, lda0=2 * C0, nsplit=1)
+    report("linear dual-source strided", out, ref, 1e-2)
+    out = ops.gemm(a0, w, N, kind=ops.GEMM_LINEAR, a1=a1, M=M, c0=C0, c1=C1, lda0=2 * C0, nsplit=3)
+    report("linear dual-source split-K 3", out, ref, 1e-2)
+    # strided output / weight views (K^T-style scores): out into a column slice
+    wide = torch.zeros(M, 2 * N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a1, w[:, :C1], N, kind=ops.GEMM_LINEAR, M=M, c0=C1, ldw=C0 + C1, out=wide[:, N:], ldo=2 * N,
+             nsplit=1)
+    report("linear ldw/ldo", wide[:, N:], a1.float() @ w[:, :C1].float().t(), 1e-2)
+    assert float(wide[:, :N].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------ conv
+def pack3x3(w):
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [
+    (1, 16, 16, 64, 64),
+    (2, 64, 64, 320, 320),
+    (2, 32, 32, 640, 640),
+    (2, 16, 16, 1280, 1280),
+    (2, 8, 8, 1280, 1280),
+    (3, 8, 8, 128, 128),       # odd batch with 2 images per tile
+    (2, 24, 24, 128, 256),     # 768^2 latent level
+    (2, 12, 12, 128, 128),
+    (1, 96, 96, 64, 128),
+    (2, 64, 64, 320, 4),       # UNet output conv (fp32 out handled below)
+])
+def test_conv3x3_s1(N, H, W, Cin, Cout):
+    ops = _ops()
+    setup_exact_fp32()
+    x = rnd(N, H, W, Cin).bfloat16()
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    out = ops.conv3x3(x, pack3x3(w), Cout, bias=b, nsplit=1, out_fp32=(Cout == 4))
+    report(f"conv3x3 s1 {N}x{H}x{W} {Cin}->{Cout}", out, ref, 1e-2 if Cout != 4 else 3e-3)
+
+
+def test_conv3x3_residual_dual_source_splitk():
+    ops = _ops()
+    setup_exact_fp32()
+    N, H, W, C0, C1, Cout = 2, 16, 16, 640, 320, 640
+    x0 = rnd(N, H, W, C0).bfloat16()
+    x1 = rnd(N, H, W, C1, seed=5).bfloat16()
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    r = rnd(N, H, W, Cout, seed=3).bfloat16()
+    xin = torch.cat([x0, x1], -1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, w.float(), b, padding=1).permute(0, 2, 3, 1) + r.float()
+    out = ops.conv3x3(x0, pack3x3(w), Cout, bias=b, a1=x1, c1=C1, residual=r.view(-1, Cout), nsplit=1)
+    report("conv3x3 dual-source + residual", out, ref, 1e-2)
+    out = ops.conv3x3(x0, pack3x3(w), Cout, bias=b, a1=x1, c1=C1, residual=r.view(-1, Cout), nsplit=4)
+    report("conv3x3 dual-source + residual split-K", out, ref, 1e-2)
+    out = ops.conv3x3(x0, pack3x3(w), Cout, bias=b, a1=x1, c1=C1, residual=r.view(-1, Cout))
+    report("conv3x3 dual-source + residual auto split", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout", [(2, 64, 64, 320, 320), (2, 16, 16, 1280, 1280), (1, 32, 32, 128, 128)])
+def test_conv3x3_s2(N, H, W, C, Cout):
+    ops = _ops()
+    setup_exact_fp32()
+    x = rnd(N, H, W, C).bfloat16()
+    w = rnd(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    xin = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xin, w.float(), b, stride=2, padding=1).permute(0, 2, 3, 1)
+    out = ops.conv3x3(x, pack3x3(w), Cout, bias=b, kind=ops.GEMM_CONV3X3_S2, nsplit=1)
+    report(f"conv3x3 s2 pad1 {H}x{W}", out, ref, 1e-2)
+    ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), b, stride=2).permute(0, 2, 3, 1)
+    out = ops.conv3x3(x, pack3x3(w), Cout, bias=b, kind=ops.GEMM_CONV3X3_S2_PAD_RB, nsplit=1)
+    report(f"conv3x3 s2 pad-rb {H}x{W}", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("Cin,Cout,k", [(4, 320, 3), (4, 4, 1), (3, 128, 3), (8, 8, 1), (4, 512, 3)])
+def test_conv_direct(Cin, Cout, k):
+    ops = _ops()
+    setup_exact_fp32()
+    N, H, W = 2, 32, 32
+    x = rnd(N, H, W, Cin).bfloat16()
+    w = rnd(Cout, Cin, k, k, scale=(k * k * Cin) ** -0.5, seed=1)
+    b = rnd(Cout, seed=2)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, b, padding=(k - 1) // 2).permute(0, 2, 3, 1)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous()
+    out = ops.conv_direct(x, wp, b, Cout, k, out_fp32=True)
+    report(f"conv_direct {Cin}->{Cout} k{k}", out, ref, 1e-4)
+    out = ops.conv_direct(x, wp, b, Cout, k)
+    report(f"conv_direct bf16 {Cin}->{Cout} k{k}", out, ref, 1e-2)
+
+
+# ------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("N,HW,C0,C1,eps,silu", [
+    (2, 4096, 320, 0, 1e-5, True), (2, 64, 1280, 1280, 1e-5, True), (2, 1024, 640, 320, 1e-5, True),
+    (2, 256, 1280, 0, 1e-6, False), (1, 16384, 128, 0, 1e-5, True), (2, 1024, 1280, 640, 1e-5, True),
+])
+def test_groupnorm(N, HW, C0, C1, eps, silu):
+    ops = _ops()
+    x0 = (rnd(N, HW, C0) * 2 + 0.5).bfloat16()
+    x1 = (rnd(N, HW, C1, seed=3) - 1.0).bfloat16() if C1 else None
+    C = C0 + C1
+    g = rnd(C, seed=4) + 1.0
+    b = rnd(C, seed=5)
+    out = ops.groupnorm(x0, g, b, x1=x1, eps=eps, silu=silu)
+    xc = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(xc.float().permute(0, 2, 1), 32, g, b, eps).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    report(f"groupnorm C={C0}+{C1} HW={HW}", out, ref, 6e-3)
+
+
+@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (512, 1280), (160, 768)])
+def test_layernorm(rows, C):
+    ops = _ops()
+    x = (rnd(rows, C) * 3 + 1).bfloat16()
+    g = rnd(C, seed=4) + 1.0
+    b = rnd(C, seed=5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    report(f"layernorm {rows}x{C}", ops.layernorm(x, g, b), ref, 6e-3)
+    report(f"layernorm fp32 {rows}x{C}", ops.layernorm(x, g, b, out_fp32=True), ref, 1e-5)
+
+
+def test_softmax_rows():
+    ops = _ops()
+    s = rnd(300, 4096) * 20
+    ref = torch.softmax(s / math.sqrt(512), -1)
+    report("softmax_rows", ops.softmax_rows(s, 1 / math.sqrt(512)), ref, 5e-3)
+
+
+# ------------------------------------------------------------------------------------ attention
+def ref_attention(q, k, v, causal):
+    # q: [N, h, S, d], k/v: [N, h, T, d] fp32
+    d = q.shape[-1]
+    w = q @ k.transpose(-1, -2)
+    if causal:
+        mask = torch.ones_like(w, dtype=torch.bool).triu(1)
+        w.masked_fill_(mask, -torch.inf)
+    w = w / math.sqrt(d)
+    return torch.softmax(w, -1) @ v
+
+
+@pytest.mark.parametrize("N,heads,d,S,Skv,causal,amp", [
+    (1, 1, 64, 128, 128, False, 1.0),
+    (2, 8, 40, 4096, 4096, False, 1.0),
+    (2, 8, 80, 1024, 1024, False, 1.0),
+    (2, 8, 160, 256, 256, False, 1.0),
+    (2, 8, 160, 64, 64, False, 1.0),
+    (2, 8, 40, 4096, 77, False, 1.0),     # cross-attention over the 77 CLIP tokens
+    (2, 8, 160, 64, 77, False, 1.0),
+    (2, 12, 64, 77, 77, True, 1.0),       # CLIP causal self-attention
+    (2, 8, 40, 1024, 1024, False, 6.0),   # peaky logits: exercises the lazy O rescale
+    (2, 8, 80, 576, 576, False, 1.0),     # 768^2 levels (ragged tiles)
+    (1, 8, 160, 144, 144, False, 1.0),
+])
+def test_attention(N, heads, d, S, Skv, causal, amp):
+    ops = _ops()
+    setup_exact_fp32()
+    C = heads * d
+    Skv_pad = (Skv + 7) // 8 * 8
+    q = (rnd(N * S, C) * amp).bfloat16()
+    k = (rnd(N, Skv_pad, C, seed=1) * amp).bfloat16()
+    v = rnd(N, Skv_pad, C, seed=2).bfloat16()
+    vt = v.permute(2, 0, 1).contiguous()          # [C, N, Skv_pad]
+    out = torch.empty(N * S, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k.view(N * Skv_pad, C), vt, out, NB=N, heads=heads, d=d, S=S, Skv=Skv,
+                  Skv_pad=Skv_pad, ldq=C, ldk=C, ldo=C, causal=causal)
+    qf = q.float().view(N, S, heads, d).transpose(1, 2)
+    kf = k.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
+    vf = v.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
+    ref = ref_attention(qf, kf, vf, causal).transpose(1, 2).reshape(N * S, C)
+    report(f"attention d={d} S={S} Skv={Skv} causal={causal}", out, ref, 1e-2)
+
+
+# ------------------------------------------------------------------------------------ elementwise
+def test_layout_and_upsample():
+    ops = _ops()
+    x = rnd(2, 4, 64, 64)
+    out = ops.nchw_to_nhwc_bf16(x, repeat=2, scale=0.5)
+    ref = (x * 0.5).repeat(2, 1, 1, 1).permute(0, 2, 3, 1)
+    report("nchw->nhwc repeat", out, ref.bfloat16().float(), 1e-6)
+    y = rnd(2, 16, 16, 64).bfloat16()
+    report("nhwc->nchw", ops.nhwc_to_nchw_f32(y), y.float().permute(0, 3, 1, 2), 0.0)
+    report("upsample2x", ops.upsample2x(y),
+           F.interpolate(y.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1), 0.0)
+
+
+def test_small_linear_time_path():
+    ops = _ops()
+    x = rnd(50, 320)
+    w = rnd(1280, 320, scale=320 ** -0.5, seed=1).bfloat16()
+    b = rnd(1280, seed=2)
+    ref = F.silu(x @ w.float().t() + b)
+    report("small_linear silu out", ops.small_linear(x, w, b, act_out=ops.ACT_SILU), ref, 1e-5)
+    ref2 = F.silu(x[:, :320]) @ w.float().t() + b
+    report("small_linear silu in", ops.small_linear(x, w, b, act_in=ops.ACT_SILU), ref2, 1e-5)
+
+
+def test_cfg_ddpm_step():
+    ops = _ops()
+    B, C, H, W = 3, 4, 64, 64
+    lat = rnd(B, C, H, W)
+    eps = rnd(2 * B, H, W, C, seed=1)
+    noise = rnd(B, C, H, W, seed=2)
+    coef = torch.tensor([[0.99, 0.125, 0.3, 0.8, 0.45], [0.01, 0.999, 0.9, 0.1, 0.0]], device=DEV)
+    e = eps.permute(0, 3, 1, 2)
+    for step in (0, 1):
+        sb, sa, c0, c1, sg = coef[step].tolist()
+        mo = 7.5 * (e[:B] - e[B:]) + e[B:]
+        x0 = (lat - sb * mo) / sa
+        ref = c0 * x0 + c1 * lat + sg * noise
+        got = lat.clone()
+        nxt = torch.empty(2 * B, H, W, C, device=DEV, dtype=torch.bfloat16)
+        ops.cfg_ddpm_step(got, eps, noise, coef, step, 7.5, True, nxt)
+        report(f"cfg_ddpm_step {step}", got, ref, 1e-6)
+        report("next_in", nxt, ref.repeat(2, 1, 1, 1).permute(0, 2, 3, 1).bfloat16().float(), 1e-6)
+
+
+def test_vae_scramble_tail_uint8_embed():
+    ops = _ops()
+    N, HW, C = 2, 1024, 512
+    y = rnd(N, HW, C).bfloat16()
+    r = rnd(N, HW, C, seed=1).bfloat16()
+    # reference semantics (sd/decoder.py:62-71): raw re-view of (n, hw, c) as (n, c, h, w), NCHW add
+    ref_nchw = y.float().reshape(N, C, HW) + r.float().permute(0, 2, 1)
+    report("vae scramble add", ops.vae_attn_scramble_add(y, r), ref_nchw.permute(0, 2, 1), 8e-3)
+    mom = rnd(2, 8, 8, 8) * 3
+    nz = rnd(2, 4, 8, 8, seed=3)
+    m = mom.permute(0, 3, 1, 2)
+    ref = (m[:, :4] + torch.clamp(m[:, 4:], -30, 20).exp().sqrt() * nz) * 0.18215
+    report("vae encode tail", ops.vae_encode_tail(mom, nz), ref, 1e-5)
+    img = rnd(1, 16, 16, 3) * 1.2
+    t = img.clone()
+    t -= -1
+    t *= 127.5
+    ref8 = t.clamp(0, 255).to(torch.uint8)
+    got8 = ops.image_to_uint8(img)
+    assert int((got8.int() - ref8.int()).abs().max()) <= 1
+    assert float((got8 != ref8).float().mean()) < 0.01
+    u8 = torch.randint(0, 256, (1, 16, 16, 3), device=DEV, dtype=torch.uint8)
+    f = u8.float()
+    f *= 2 / 255
+    f += -1
+    report("uint8->image", ops.uint8_to_image(u8), f.bfloat16().float(), 1e-6)
+    tok = torch.randint(0, 1000, (2, 77), device=DEV)
+    table = rnd(1000, 768)
+    pos = rnd(77, 768, seed=9)
+    e = ops.clip_embed(tok, table, pos, 80)
+    report("clip embed", e[:, :77], (table[tok] + pos).bfloat16().float(), 1e-6)
+    assert float(e[:, 77:].abs().max()) == 0.0
+    a, b = rnd(1000), rnd(1000, seed=4)
+    report("axpby", ops.axpby(a, b, 0.3, 0.7), 0.3 * a + 0.7 * b, 1e-6)
