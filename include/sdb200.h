@@ -133,13 +133,13 @@ int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out,
 int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R, int K,
                      int N, int act_in, int act_out, void* stream);
 /* Fused classifier-free guidance + DDPM ancestral step (sd/pipeline.py:228-237,
- * sd/ddpm.py:102-139). eps: fp32 NHWC [2*NB (or NB when !do_cfg), H, W, C]; latents/noise: fp32
+ * sd/ddpm.py:102-139). eps: fp32 NHWC (NCHW when eps_nchw) [2*NB (or NB when !do_cfg), H, W, C]; latents/noise: fp32
  * NCHW [NB, C, H, W]; coef: device fp32 [steps][5] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt,
  * sigma_t}; writes latents in place and the next UNet input (bf16 NHWC, batch tiled x2 when
  * do_cfg) to next_in when non-NULL. */
 int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise, const float* coef,
                       int step, float cfg_scale, int do_cfg, void* next_in, int NB, int C, int H,
-                      int W, void* stream);
+                      int W, int eps_nchw, void* stream);
 /* VAE_AttentionBlock tail as the reference computes it (sd/decoder.py:62-71): the (n, hw, c)
  * attention output is re-viewed raw as (n, c, h, w) and added to the residual.
  * y, res, out: bf16 NHWC [NB, HW, C]. out[n, p, c] = y_flat[n][c*HW + p] + res[n, p, c]. */

@@ -50,7 +50,7 @@ SIGNATURES = {
                         c_int, c_void_p],
     "sdb_small_linear": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_cfg_ddpm_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int,
-                          c_int, c_int, c_int, c_void_p],
+                          c_int, c_int, c_int, c_int, c_void_p],
     "sdb_vae_attn_scramble_add": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
     "sdb_vae_encode_tail": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sdb_axpby": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_ll, c_void_p],

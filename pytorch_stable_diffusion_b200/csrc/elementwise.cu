@@ -152,7 +152,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const __nv_bflo
 __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* __restrict__ eps,
                                      const float* __restrict__ noise, const float* __restrict__ coef,
                                      int step, float cfg_scale, int do_cfg,
-                                     __nv_bfloat16* __restrict__ next_in, int NB, int C, int H, int W) {
+                                     __nv_bfloat16* __restrict__ next_in, int NB, int C, int H, int W,
+                                     int eps_nchw) {
   const long long hw = (long long)H * W;
   const long long total = (long long)NB * C * hw;
   const float sb = coef[step * 5 + 0];   // sqrt(1 - abar_t)
@@ -165,14 +166,15 @@ __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* _
     const long long p = i % hw;
     const int c = (int)((i / hw) % C);
     const int n = (int)(i / (hw * C));
-    const long long e_idx = ((long long)n * hw + p) * C + c;
+    const long long e_idx = ((long long)n * hw + p) * C + c;   // NHWC position (next_in layout)
+    const long long s_idx = eps_nchw ? i : e_idx;
     float e;
     if (do_cfg) {
-      const float ec = eps[e_idx];
-      const float eu = eps[e_idx + (long long)NB * hw * C];
+      const float ec = eps[s_idx];
+      const float eu = eps[s_idx + (long long)NB * hw * C];
       e = cfg_scale * (ec - eu) + eu;
     } else {
-      e = eps[e_idx];
+      e = eps[s_idx];
     }
     const float xt = latents[i];
     const float x0 = (xt - sb * e) / sa;
@@ -378,13 +380,14 @@ extern "C" int sdb_small_linear(const float* x, const void* w, const float* bias
 
 extern "C" int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise,
                                  const float* coef, int step, float cfg_scale, int do_cfg,
-                                 void* next_in, int NB, int C, int H, int W, void* stream) {
+                                 void* next_in, int NB, int C, int H, int W, int eps_nchw,
+                                 void* stream) {
   if (!latents || !eps || !coef || step < 0 || NB <= 0 || C <= 0 || H <= 0 || W <= 0) {
     set_error("sdb_cfg_ddpm_step: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * C * H * W;
   cfg_ddpm_step_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
-      latents, eps, noise, coef, step, cfg_scale, do_cfg, (__nv_bfloat16*)next_in, NB, C, H, W);
+      latents, eps, noise, coef, step, cfg_scale, do_cfg, (__nv_bfloat16*)next_in, NB, C, H, W, eps_nchw);
   return check_launch("cfg_ddpm_step_kernel");
 }
 

@@ -52,6 +52,7 @@ struct GemmTcParams {
   int block_n;             // UMMA N (multiple of 16, <= 256)
   int tmem_cols;           // power of two >= max(32, round_up(block_n, 32))
   int stages;
+  int a_tx_bytes;           // bytes one A box delivers (bw*bh*bn rows of 128 B)
   int nsplit;              // split-K factor (gridDim.z)
   void* out;
   long long ldo;
@@ -133,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int cb = kb - tap * p.cblocks;
         uint8_t* a_dst = smem + s * stage_bytes;
         uint8_t* b_dst = a_dst + GEMM_A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_tx_bytes + b_stage_bytes));
         const bool second = cb >= p.cblocks0;
         const CUtensorMap* ma = second ? &p.map_a1 : &p.map_a0;
         const int c = (second ? (cb - p.cblocks0) : cb) * GEMM_BK;
@@ -430,6 +431,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
       if ((rc = make_tmap_bf16(&p.map_a0, a->a0, 5, dims, str, box, "conv-s2 A0"))) return rc;
     }
   }
+  p.a_tx_bytes = (p.a_rank == 2) ? GEMM_A_STAGE_BYTES : p.bw * p.bh * p.bn * 128;
   p.tiles_w = (p.WO + p.bw - 1) / p.bw;
   p.tiles_h = (p.HO + p.bh - 1) / p.bh;
   const int tiles_n = (p.NB + p.bn - 1) / p.bn;

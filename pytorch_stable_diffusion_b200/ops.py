@@ -225,11 +225,11 @@ def small_linear(x, w, bias, act_in=ACT_NONE, act_out=ACT_NONE):
     return out
 
 
-def cfg_ddpm_step(latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in):
+def cfg_ddpm_step(latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in, eps_nchw=False):
     lib = _ext.lib()
     n, c, h, w = latents.shape
     _ext.check(lib.sdb_cfg_ddpm_step(_p(latents), _p(eps), _p(noise), _p(coef), step, float(cfg_scale),
-                                     1 if do_cfg else 0, _p(next_in), n, c, h, w, _stream()),
+                                     1 if do_cfg else 0, _p(next_in), n, c, h, w, 1 if eps_nchw else 0, _stream()),
                "sdb_cfg_ddpm_step")
     return latents
 

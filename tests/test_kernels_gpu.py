@@ -331,7 +331,7 @@ def test_vae_scramble_tail_uint8_embed():
     f = u8.float()
     f *= 2 / 255
     f += -1
-    report("uint8->image", ops.uint8_to_image(u8), f.bfloat16().float(), 1e-6)
+    report("uint8->image", ops.uint8_to_image(u8), f, 4e-3)
     tok = torch.randint(0, 1000, (2, 77), device=DEV)
     table = rnd(1000, 768)
     pos = rnd(77, 768, seed=9)
