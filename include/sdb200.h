@@ -50,8 +50,9 @@ typedef struct sdb_gemm_args {
   const void* a1;         /* optional source 1 (channel concatenation without a copy), or NULL   */
   const void* w;          /* bf16 weights [Cout, ldw], row = taps * (C0 + C1) values             */
   const float* bias;      /* fp32 [Cout] (or [M] when bias_per_row), or NULL                     */
-  const void* residual;   /* bf16 [M, ldr] added after the activation, or NULL                   */
+  const void* residual;   /* bf16 (fp32 when res_fp32) [M, ldr] added after the activation, or NULL */
   void* out;              /* bf16 (or fp32 when out_fp32) [M, ldo]                               */
+  void* out2;             /* optional bf16 copy [M, ldo] written next to an fp32 `out`, or NULL  */
   float* workspace;       /* fp32 [nsplit, M, Cout] when nsplit > 1                              */
   int M;                  /* rows (LINEAR only)                                                  */
   int NB, HI, WI;         /* input batch / height / width (CONV only)                            */
@@ -61,6 +62,7 @@ typedef struct sdb_gemm_args {
   long long ldw;          /* weight row stride in elements (0 = dense)                           */
   long long ldo, ldr;     /* output / residual row strides in elements (0 = Cout)                */
   int out_fp32;
+  int res_fp32;
   int bias_per_row;
   int act;                /* SDB_ACT_*                                                           */
   int block_n;            /* 0 = choose; else multiple of 16 in [16, 256]                        */
@@ -77,12 +79,13 @@ int sdb_gemm_tc(const sdb_gemm_args* args, void* stream);
 typedef struct sdb_attn_args {
   const void* q;          /* bf16, token (n, s) head h at q + ((n*S + s) * ldq + h*d)            */
   const void* k;          /* bf16, key (n, t) head h at k + ((n*Skv_pad + t) * ldk + h*d)        */
-  const void* vt;         /* bf16 V transposed: channel c of key (n, t) at vt + (c*NB + n)*Skv_pad + t */
+  const void* vt;         /* bf16 V transposed: channel c of key (n, t) at vt + (c*NB + n)*vt_ld + t */
   void* out;              /* bf16 [NB*S, ldo], head h at column h*d                              */
   int NB, heads, d;       /* d = head dim (multiple of 8, <= 160)                                */
   int S;                  /* queries per sample                                                  */
   int Skv;                /* valid keys per sample                                               */
-  int Skv_pad;            /* allocated keys per sample (multiple of 8, >= Skv)                   */
+  int Skv_pad;            /* allocated key rows per sample in k (>= Skv)                         */
+  int vt_ld;              /* per-sample stride of vt in elements (multiple of 8; 0 = Skv_pad)    */
   long long ldq, ldk, ldo;
   int causal;             /* key t visible to query s iff t <= s (sd/attention.py:58-62)         */
   float scale;            /* 1/sqrt(d) (sd/attention.py:66,223)                                  */
@@ -93,21 +96,22 @@ typedef struct sdb_attn_args {
 int sdb_attention(const sdb_attn_args* args, void* stream);
 
 /* ---- normalisation (HBM-bound) ------------------------------------------------------------ */
-/* GroupNorm statistics over NHWC bf16 x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0):
+/* GroupNorm statistics over NHWC x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0), each bf16 or
+ * fp32 (x?_fp32):
  * stats[n][g] = {sum, sum of squares} in fp64; stats must be zeroed by the caller
  * (sdb_fill_zero). nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;
  * sd/encoder.py:86. */
 int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, long long HW,
-                        int C0, int C1, int groups, void* stream);
+                        int C0, int C1, int groups, int x0_fp32, int x1_fp32, void* stream);
 /* y = (x - mean) * rstd * gamma + beta, optionally followed by SiLU (F.silu: sd/diffusion.py:176,
  * 202,738; sd/decoder.py:162,175,335); writes bf16 NHWC [NB, HW, C0 + C1]. */
 int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats, const float* gamma,
                         const float* beta, void* out, int NB, long long HW, int C0, int C1,
-                        int groups, float eps, int silu, void* stream);
+                        int groups, float eps, int silu, int x0_fp32, int x1_fp32, void* stream);
 /* nn.LayerNorm over the last axis (sd/diffusion.py:258,261,264; sd/clip.py:105,113,225).
- * x bf16 [rows, C] -> out bf16 (or fp32 when out_fp32). */
+ * x bf16 (fp32 when in_fp32) [rows, C] -> out bf16 (or fp32 when out_fp32). */
 int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out, long long rows,
-                  int C, float eps, int out_fp32, void* stream);
+                  int C, float eps, int in_fp32, int out_fp32, void* stream);
 /* Row softmax of fp32 scores * scale -> bf16 probabilities (VAE attention, sd/attention.py:66-71). */
 int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols, float scale,
                      void* stream);
@@ -142,9 +146,12 @@ int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise, cons
                       int W, int eps_nchw, void* stream);
 /* VAE_AttentionBlock tail as the reference computes it (sd/decoder.py:62-71): the (n, hw, c)
  * attention output is re-viewed raw as (n, c, h, w) and added to the residual.
- * y, res, out: bf16 NHWC [NB, HW, C]. out[n, p, c] = y_flat[n][c*HW + p] + res[n, p, c]. */
-int sdb_vae_attn_scramble_add(const void* y, const void* res, void* out, int NB, long long HW,
-                              int C, void* stream);
+ * y bf16, res fp32, out fp32 (+ optional bf16 copy out2), all NHWC [NB, HW, C].
+ * out[n, p, c] = y_flat[n][c*HW + p] + res[n, p, c]. */
+int sdb_vae_attn_scramble_add(const void* y, const float* res, float* out, void* out2, int NB,
+                              long long HW, int C, void* stream);
+/* fp32 -> bf16 copy (bf16 shadow of an fp32 residual-stream tensor). */
+int sdb_f32_to_bf16(const float* x, void* out, long long n, void* stream);
 /* VAE encoder tail (sd/encoder.py:127-152): moments fp32 NHWC [NB, H, W, 8] + noise fp32 NCHW
  * [NB, 4, H, W] -> latents fp32 NCHW: (mean + exp(clamp(logvar,-30,20))^0.5 * noise) * 0.18215. */
 int sdb_vae_encode_tail(const float* moments, const float* noise, float* out, int NB, int H, int W,
@@ -158,7 +165,7 @@ int sdb_image_to_uint8(const float* x, unsigned char* out, long long n, void* st
 /* Pre-processing (sd/pipeline.py:162-173): uint8 HWC -> bf16 NHWC in [-1,1]. */
 int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, void* stream);
 /* CLIPEmbedding (sd/clip.py:58-63): out[b, t, :] = table[tokens[b, t]] + pos[t]; rows
- * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out bf16 [NB, T_pad, D]. */
+ * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out fp32 [NB, T_pad, D]. */
 int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,
                    int T, int T_pad, int D, int vocab, void* stream);
 

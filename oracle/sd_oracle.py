@@ -287,7 +287,7 @@ class OracleDDPM:
         return b_t ** 0.5, a_t ** 0.5, c_x0, c_xt, sigma
 
     def step(self, t, latents, model_output):                           # :102-139
-        sb, sa, c_x0, c_xt, sigma = self.coefficients(t)
+        sb, sa, c_x0, c_xt, sigma = (c.to(latents.device) for c in self.coefficients(t))
         x0 = (latents - sb * model_output) / sa
         prev = c_x0 * x0 + c_xt * latents
         if int(t) > 0:
@@ -295,7 +295,7 @@ class OracleDDPM:
         return prev
 
     def add_noise(self, x0, t):                                         # :143-186
-        a = self.alphas_cumprod[int(t)]
+        a = self.alphas_cumprod[int(t)].to(x0.device)
         return a ** 0.5 * x0 + (1 - a) ** 0.5 * self.noise_fn(x0.shape)
 
 
@@ -310,18 +310,21 @@ def get_time_embedding(timestep):
 
 def generate(weights, cond_tokens, uncond_tokens, *, seed=42, cfg_scale=7.5, n_inference_steps=50,
              do_cfg=True, input_image=None, strength=0.8, latent_hw=(64, 64), max_steps=None,
-             trace=None):
+             trace=None, device="cpu"):
     """pipeline.generate — sd/pipeline.py:72-262 for one image, token ids instead of a tokenizer.
 
     weights: {'clip','encoder','decoder','diffusion'} state_dicts. The noise stream is a CPU
     torch.Generator seeded with `seed`, drawn in the reference's order (:177 encoder noise,
     sd/ddpm.py:184 add_noise, :196 initial latents, sd/ddpm.py:131 per step).
+    `device` places the arithmetic (the noise is always drawn on the CPU and moved).
     `max_steps` stops the loop early (bounded CPU-baseline samples); `trace` (a list) receives
     (timestep, latents_in, unet_out) per step. Returns (uint8 HxWx3 image, final latents).
     """
     with torch.no_grad():
         gen = torch.Generator(device="cpu").manual_seed(seed)
-        randn = lambda shape: torch.randn(tuple(shape), generator=gen)
+        randn = lambda shape: torch.randn(tuple(shape), generator=gen).to(device)
+        cond_tokens = cond_tokens.to(device)
+        uncond_tokens = uncond_tokens.to(device) if uncond_tokens is not None else None
         if do_cfg:
             ctx = torch.cat([clip_forward(weights["clip"], cond_tokens.view(1, -1)),
                              clip_forward(weights["clip"], uncond_tokens.view(1, -1))])
@@ -331,7 +334,7 @@ def generate(weights, cond_tokens, uncond_tokens, *, seed=42, cfg_scale=7.5, n_i
         sampler.set_inference_timesteps(n_inference_steps)
         shape = (1, 4, latent_hw[0], latent_hw[1])
         if input_image is not None:
-            img = torch.tensor(np.asarray(input_image), dtype=torch.float32)
+            img = torch.tensor(np.asarray(input_image), dtype=torch.float32, device=device)
             img = (img * (2.0 / 255.0) - 1.0).unsqueeze(0).permute(0, 3, 1, 2)
             latents = vae_encoder_forward(weights["encoder"], img, randn(shape))
             sampler.set_strength(strength)
@@ -341,7 +344,7 @@ def generate(weights, cond_tokens, uncond_tokens, *, seed=42, cfg_scale=7.5, n_i
         for i, t in enumerate(sampler.timesteps):
             if max_steps is not None and i >= max_steps:
                 break
-            temb = get_time_embedding(int(t))
+            temb = get_time_embedding(int(t)).to(device)
             x = latents.repeat(2, 1, 1, 1) if do_cfg else latents
             out = diffusion_forward(weights["diffusion"], x, ctx, temb)
             if trace is not None:
@@ -352,7 +355,7 @@ def generate(weights, cond_tokens, uncond_tokens, *, seed=42, cfg_scale=7.5, n_i
             latents = sampler.step(t, latents, out)
         img = vae_decoder_forward(weights["decoder"], latents.clone())
         img = ((img + 1.0) * 127.5).clamp(0, 255).permute(0, 2, 3, 1)
-        return img.to(torch.uint8).numpy()[0], latents
+        return img.to("cpu", torch.uint8).numpy()[0], latents
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,10 +14,10 @@ c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlon
 class GemmArgs(ctypes.Structure):
     _fields_ = [
         ("kind", c_int), ("a0", c_void_p), ("a1", c_void_p), ("w", c_void_p), ("bias", c_void_p),
-        ("residual", c_void_p), ("out", c_void_p), ("workspace", c_void_p), ("M", c_int),
+        ("residual", c_void_p), ("out", c_void_p), ("out2", c_void_p), ("workspace", c_void_p), ("M", c_int),
         ("NB", c_int), ("HI", c_int), ("WI", c_int), ("C0", c_int), ("C1", c_int), ("Cout", c_int),
         ("lda0", c_ll), ("lda1", c_ll), ("ldw", c_ll), ("ldo", c_ll), ("ldr", c_ll),
-        ("out_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
+        ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
         ("nsplit", c_int), ("smem_budget", c_int),
     ]
 
@@ -25,7 +25,7 @@ class GemmArgs(ctypes.Structure):
 class AttnArgs(ctypes.Structure):
     _fields_ = [
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p), ("out", c_void_p), ("NB", c_int),
-        ("heads", c_int), ("d", c_int), ("S", c_int), ("Skv", c_int), ("Skv_pad", c_int),
+        ("heads", c_int), ("d", c_int), ("S", c_int), ("Skv", c_int), ("Skv_pad", c_int), ("vt_ld", c_int),
         ("ldq", c_ll), ("ldk", c_ll), ("ldo", c_ll), ("causal", c_int), ("scale", c_float),
     ]
 
@@ -37,10 +37,11 @@ SIGNATURES = {
     "sdb_read_fault": [ctypes.POINTER(ctypes.c_uint)],
     "sdb_gemm_tc": [ctypes.POINTER(GemmArgs), c_void_p],
     "sdb_attention": [ctypes.POINTER(AttnArgs), c_void_p],
-    "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_void_p],
+    "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p],
     "sdb_groupnorm_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll,
-                            c_int, c_int, c_int, c_float, c_int, c_void_p],
-    "sdb_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_void_p],
+                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p],
+    "sdb_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p],
     "sdb_softmax_rows": [c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p],
     "sdb_fill_zero": [c_void_p, c_ll, c_void_p],
     "sdb_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
@@ -51,7 +52,8 @@ SIGNATURES = {
     "sdb_small_linear": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_cfg_ddpm_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int,
                           c_int, c_int, c_int, c_int, c_void_p],
-    "sdb_vae_attn_scramble_add": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
+    "sdb_vae_attn_scramble_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
+    "sdb_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_vae_encode_tail": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sdb_axpby": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_ll, c_void_p],
     "sdb_image_to_uint8": [c_void_p, c_void_p, c_ll, c_void_p],

@@ -279,7 +279,11 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     set_error("sdb_attention: head dim %d unsupported (multiple of 8, <= 160)", a->d);
     return SDB_ERR_UNSUPPORTED;
   }
-  if (a->Skv_pad % 8 != 0) { set_error("sdb_attention: Skv_pad must be a multiple of 8"); return SDB_ERR_ARG; }
+  const int vt_ld = a->vt_ld ? a->vt_ld : a->Skv_pad;
+  if (vt_ld % 8 != 0 || vt_ld < a->Skv) {
+    set_error("sdb_attention: vt_ld (%d) must be a multiple of 8 and >= Skv", vt_ld);
+    return SDB_ERR_ARG;
+  }
   const long long ldq = a->ldq ? a->ldq : (long long)a->heads * a->d;
   const long long ldk = a->ldk ? a->ldk : (long long)a->heads * a->d;
   const long long ldo = a->ldo ? a->ldo : (long long)a->heads * a->d;
@@ -303,8 +307,8 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   }
   const int dv_pad = ((a->d + 15) / 16) * 16;
   {
-    uint64_t dims[3] = {(uint64_t)a->Skv_pad, (uint64_t)a->NB, (uint64_t)a->heads * a->d};
-    uint64_t str[2] = {(uint64_t)a->Skv_pad * 2, (uint64_t)a->Skv_pad * 2 * a->NB};
+    uint64_t dims[3] = {(uint64_t)vt_ld, (uint64_t)a->NB, (uint64_t)a->heads * a->d};
+    uint64_t str[2] = {(uint64_t)vt_ld * 2, (uint64_t)vt_ld * 2 * a->NB};
     uint32_t box[3] = {64, 1, (uint32_t)dv_pad};
     if ((rc = make_tmap_bf16(&p.map_vt, a->vt, 3, dims, str, box, "attention V^T"))) return rc;
   }

@@ -192,8 +192,8 @@ __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* _
 // out[n][p][c] = y_flat[n][c*HW + p] + res[n][p][c]: a 32x32 shared-memory transpose of y viewed as
 // [C][HW].
 __global__ void vae_scramble_add_kernel(const __nv_bfloat16* __restrict__ y,
-                                        const __nv_bfloat16* __restrict__ res,
-                                        __nv_bfloat16* __restrict__ out, long long HW, int C) {
+                                        const float* __restrict__ res, float* __restrict__ out,
+                                        __nv_bfloat16* __restrict__ out2, long long HW, int C) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -211,7 +211,9 @@ __global__ void vae_scramble_add_kernel(const __nv_bfloat16* __restrict__ y,
     const int c = c0 + tx;
     if (p < HW && c < C) {
       const long long o = ((long long)n * HW + p) * C + c;
-      out[o] = __float2bfloat16_rn(tile[tx][j] + __bfloat162float(res[o]));
+      const float v = tile[tx][j] + res[o];
+      out[o] = v;
+      if (out2 != nullptr) out2[o] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -232,6 +234,12 @@ __global__ void vae_encode_tail_kernel(const float* __restrict__ moments, const 
     const float stdev = sqrtf(expf(lv));
     out[i] = (mean + stdev * noise[i]) * 0.18215f;
   }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(x[i]);
 }
 
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -268,7 +276,7 @@ __global__ void uint8_to_image_kernel(const unsigned char* __restrict__ x, __nv_
 }
 
 __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const float* __restrict__ table,
-                                  const float* __restrict__ pos, __nv_bfloat16* __restrict__ out, int NB,
+                                  const float* __restrict__ pos, float* __restrict__ out, int NB,
                                   int T, int T_pad, int D, int vocab) {
   const long long total = (long long)NB * T_pad * D;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -283,7 +291,7 @@ __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const fl
       if (tok >= vocab) tok = vocab - 1;
       v = table[tok * D + d] + pos[(long long)t * D + d];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = v;
   }
 }
 
@@ -391,14 +399,14 @@ extern "C" int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* 
   return check_launch("cfg_ddpm_step_kernel");
 }
 
-extern "C" int sdb_vae_attn_scramble_add(const void* y, const void* res, void* out, int NB,
+extern "C" int sdb_vae_attn_scramble_add(const void* y, const float* res, float* out, void* out2, int NB,
                                          long long HW, int C, void* stream) {
   if (!y || !res || !out || NB <= 0 || HW <= 0 || C <= 0) {
     set_error("sdb_vae_attn_scramble_add: bad arguments"); return SDB_ERR_ARG;
   }
   dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)NB);
   vae_scramble_add_kernel<<<grid, dim3(32, 8), 0, SDB_STREAM>>>(
-      (const __nv_bfloat16*)y, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, HW, C);
+      (const __nv_bfloat16*)y, res, out, (__nv_bfloat16*)out2, HW, C);
   return check_launch("vae_scramble_add_kernel");
 }
 
@@ -410,6 +418,12 @@ extern "C" int sdb_vae_encode_tail(const float* moments, const float* noise, flo
   const long long total = (long long)NB * 4 * H * W;
   vae_encode_tail_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(moments, noise, out, NB, H, W);
   return check_launch("vae_encode_tail_kernel");
+}
+
+extern "C" int sdb_f32_to_bf16(const float* x, void* out, long long n, void* stream) {
+  if (!x || !out || n <= 0) { set_error("sdb_f32_to_bf16: bad arguments"); return SDB_ERR_ARG; }
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, (__nv_bfloat16*)out, n);
+  return check_launch("f32_to_bf16_kernel");
 }
 
 extern "C" int sdb_axpby(const float* x, const float* y, float* out, float a, float b, long long n,
@@ -437,7 +451,7 @@ extern "C" int sdb_clip_embed(const long long* tokens, const float* table, const
     set_error("sdb_clip_embed: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * T_pad * D;
-  clip_embed_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(tokens, table, pos, (__nv_bfloat16*)out, NB,
+  clip_embed_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(tokens, table, pos, (float*)out, NB,
                                                                   T, T_pad, D, vocab);
   return check_launch("clip_embed_kernel");
 }

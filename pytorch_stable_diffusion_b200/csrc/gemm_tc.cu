@@ -35,7 +35,7 @@ struct GemmTcParams {
   // output-pixel space and tiling
   int NB, HO, WO;          // output rows are (n, h, w), row index m = (n*HO + h)*WO + w
   int bw, bh, bn;          // tile box in (w, h, n); bw*bh*bn <= 128
-  int tiles_w, tiles_h;    // tiles along w and h (tiles along n = gridDim.y / (tiles_w*tiles_h))
+  int tiles_w, tiles_h;    // tiles along w and h (tiles along n = gridDim.x / (tiles_w*tiles_h))
   int a_rank;              // 2: plain [M, K] matrix; 5: NHWC conv addressing
   // reduction
   int C0, C1;              // channels from source 0 / source 1 (multiples of 64 when C1 > 0)
@@ -59,8 +59,10 @@ struct GemmTcParams {
   int out_fp32;
   const float* bias;
   int bias_mode;           // 0 none, 1 per column, 2 per row
-  const __nv_bfloat16* residual;
+  const void* residual;    // bf16, or fp32 when res_fp32
+  int res_fp32;
   long long ldr;
+  __nv_bfloat16* out2;     // optional bf16 copy of the output (same row stride), or nullptr
   int act;                 // 0 none, 1 quick-GELU, 2 SiLU
   float* workspace;        // [nsplit][M_total][N] fp32 when nsplit > 1
   long long m_total;
@@ -87,8 +89,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   // ---- tile coordinates
-  const int n_tile = blockIdx.x;
-  int mt = blockIdx.y;
+  const int n_tile = blockIdx.y;
+  int mt = blockIdx.x;
   const int tw_i = mt % p.tiles_w;
   mt /= p.tiles_w;
   const int th_i = mt % p.tiles_h;
@@ -228,8 +230,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
         }
-        if (p.residual != nullptr) {
-          const __nv_bfloat16* rp = p.residual + m * p.ldr + col0;
+        if (p.residual != nullptr && p.res_fp32) {
+          const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + col0;
+          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(rp + j));
+              x[j + 0] += u.x; x[j + 1] += u.y; x[j + 2] += u.z; x[j + 3] += u.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) x[j] += rp[j];
+          }
+        } else if (p.residual != nullptr) {
+          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + col0;
           if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -256,8 +271,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             for (int j = 0; j < 32; ++j)
               if (j < ncol) op[j] = x[j];
           }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + col0;
+        }
+        __nv_bfloat16* bp = p.out_fp32 ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
+        if (bp != nullptr) {
+          __nv_bfloat16* op = bp + m * p.ldo + col0;
           if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -288,8 +305,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int nsplit,
                                             long long m_total, int N, void* out, long long ldo,
                                             int out_fp32, const float* __restrict__ bias,
-                                            int bias_mode, const __nv_bfloat16* __restrict__ residual,
-                                            long long ldr, int act) {
+                                            int bias_mode, const void* __restrict__ residual,
+                                            int res_fp32, long long ldr, int act,
+                                            __nv_bfloat16* __restrict__ out2) {
   const long long total = m_total * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -300,9 +318,16 @@ __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int ns
     if (bias_mode == 1) acc += bias[n];
     else if (bias_mode == 2) acc += bias[m];
     acc = apply_act(acc, act);
-    if (residual) acc += __bfloat162float(residual[m * ldr + n]);
-    if (out_fp32) reinterpret_cast<float*>(out)[m * ldo + n] = acc;
-    else reinterpret_cast<__nv_bfloat16*>(out)[m * ldo + n] = __float2bfloat16_rn(acc);
+    if (residual) {
+      acc += res_fp32 ? reinterpret_cast<const float*>(residual)[m * ldr + n]
+                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[m * ldr + n]);
+    }
+    if (out_fp32) {
+      reinterpret_cast<float*>(out)[m * ldo + n] = acc;
+      if (out2) out2[m * ldo + n] = __float2bfloat16_rn(acc);
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(out)[m * ldo + n] = __float2bfloat16_rn(acc);
+    }
   }
 }
 
@@ -482,7 +507,10 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.out_fp32 = a->out_fp32;
   p.bias = a->bias;
   p.bias_mode = a->bias ? (a->bias_per_row ? 2 : 1) : 0;
-  p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+  p.residual = a->residual;
+  p.res_fp32 = a->res_fp32;
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2);
+  if (a->out2 && !a->out_fp32) { set_error("sdb_gemm_tc: out2 (bf16 copy) needs out_fp32"); return SDB_ERR_ARG; }
   p.ldr = a->ldr ? a->ldr : a->Cout;
   p.act = a->act;
   p.workspace = a->workspace;
@@ -498,8 +526,8 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
-  if (m_tiles > 65535) { set_error("sdb_gemm_tc: too many M tiles (%lld)", m_tiles); return SDB_ERR_UNSUPPORTED; }
-  dim3 grid((unsigned)n_tiles, (unsigned)m_tiles, (unsigned)nsplit);
+  if (m_tiles > 2147483647LL || n_tiles > 65535) { set_error("sdb_gemm_tc: grid too large"); return SDB_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)nsplit);
   gemm_tc_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
   if ((rc = check_launch("gemm_tc_kernel"))) return rc;
   if (nsplit > 1) {
@@ -508,7 +536,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     if (blocks > 148 * 8) blocks = 148 * 8;
     gemm_splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(
         p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias, p.bias_mode,
-        p.residual, p.ldr, p.act);
+        p.residual, p.res_fp32, p.ldr, p.act, p.out2);
     if ((rc = check_launch("gemm_splitk_finalize_kernel"))) return rc;
   }
   return SDB_OK;

@@ -17,14 +17,26 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return u;
 }
 
+// 8 consecutive channels of one pixel from a bf16 or fp32 tensor.
+__device__ __forceinline__ void load8(const void* base, long long elem_off, int is_fp32, float* f) {
+  if (is_fp32) {
+    const float* p = reinterpret_cast<const float*>(base) + elem_off;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
+    unpack8(u, f);
+  }
+}
+
 // Thread layout shared by stats and apply: V = (C0+C1)/8 16-byte vectors per pixel; a block holds
 // `lanes` pixels side by side, thread t -> (vector t % V, pixel lane t / V). Each thread keeps the
 // same 8 channels for its whole life, so per-channel state lives in registers.
 // grid = (chunks, NB); every block walks pixels [chunk*ppc, (chunk+1)*ppc).
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
-                                const __nv_bfloat16* __restrict__ x1, double* __restrict__ stats,
-                                long long HW, int C0, int C1, int groups, long long ppc, int V,
-                                int lanes) {
+__global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
+                                double* __restrict__ stats, long long HW, int C0, int C1, int groups,
+                                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
   __shared__ float s_sum[64];
   __shared__ float s_sq[64];
   const int n = blockIdx.y;
@@ -38,8 +50,10 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   const int cpg = ctot / groups;
   if (pl < lanes) {
     const bool second = v >= V0;
-    const __nv_bfloat16* base = second ? x1 + (long long)n * HW * C1 + (long long)(v - V0) * 8
-                                       : x0 + (long long)n * HW * C0 + (long long)v * 8;
+    const void* src = second ? x1 : x0;
+    const int src_fp32 = second ? x1_fp32 : x0_fp32;
+    const long long base = second ? (long long)n * HW * C1 + (long long)(v - V0) * 8
+                                  : (long long)n * HW * C0 + (long long)v * 8;
     const long long stride = second ? C1 : C0;
     float sum[8], sq[8];
 #pragma unroll
@@ -47,9 +61,8 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
     const long long p_begin = (long long)blockIdx.x * ppc;
     const long long p_end = min(HW, p_begin + ppc);
     for (long long p = p_begin + pl; p < p_end; p += lanes) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * stride));
       float f[8];
-      unpack8(u, f);
+      load8(src, base + p * stride, src_fp32, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
     }
@@ -69,12 +82,11 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0,
   }
 }
 
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
-                                const __nv_bfloat16* __restrict__ x1,
+__global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                 long long HW, int C0, int C1, int groups, float eps, int silu,
-                                long long ppc, int V, int lanes) {
+                                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int v = t % V;
@@ -101,16 +113,17 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
     sh[j] = be - (float)mean * rstd * ga;
   }
   const bool second = v >= V0;
-  const __nv_bfloat16* base = second ? x1 + (long long)n * HW * C1 + (long long)(v - V0) * 8
-                                     : x0 + (long long)n * HW * C0 + (long long)v * 8;
+  const void* src = second ? x1 : x0;
+  const int src_fp32 = second ? x1_fp32 : x0_fp32;
+  const long long base = second ? (long long)n * HW * C1 + (long long)(v - V0) * 8
+                                : (long long)n * HW * C0 + (long long)v * 8;
   const long long stride = second ? C1 : C0;
   __nv_bfloat16* obase = out + (long long)n * HW * ctot + c0;
   const long long p_begin = (long long)blockIdx.x * ppc;
   const long long p_end = min(HW, p_begin + ppc);
   for (long long p = p_begin + pl; p < p_end; p += lanes) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + p * stride));
     float f[8];
-    unpack8(u, f);
+    load8(src, base + p * stride, src_fp32, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = f[j] * sc[j] + sh[j];
@@ -123,22 +136,20 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0,
 
 // One warp per row; rows of up to 5*32*8 = 1280 channels are held in registers between the passes.
 constexpr int LN_MAX_VEC_PER_LANE = 5;
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+__global__ void layernorm_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, void* __restrict__ out,
-                                 long long rows, int C, float eps, int out_fp32) {
+                                 long long rows, int C, float eps, int in_fp32, int out_fp32) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int V = C >> 3;
-  const __nv_bfloat16* xr = x + row * C;
   float f[LN_MAX_VEC_PER_LANE][8];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < LN_MAX_VEC_PER_LANE; ++i) {
     const int v = lane + i * 32;
     if (v < V) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
-      unpack8(u, f[i]);
+      load8(x, row * C + v * 8, in_fp32, f[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += f[i][j];
     }
@@ -248,7 +259,8 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
 }  // namespace sdb
 
 extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB,
-                                   long long HW, int C0, int C1, int groups, void* stream) {
+                                   long long HW, int C0, int C1, int groups, int x0_fp32, int x1_fp32,
+                                   void* stream) {
   using namespace sdb;
   const int ctot = C0 + C1;
   if (!x0 || !stats || NB <= 0 || HW <= 0 || groups <= 0 || groups > 64 || ctot % groups != 0 ||
@@ -262,14 +274,14 @@ extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats
     return SDB_ERR_UNSUPPORTED;
   }
   gn_stats_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, stats, HW, C0, C1, groups, ppc, V, lanes);
+      x0, x1, stats, HW, C0, C1, groups, ppc, V, lanes, x0_fp32, x1_fp32);
   return check_launch("gn_stats_kernel");
 }
 
 extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats,
                                    const float* gamma, const float* beta, void* out, int NB,
                                    long long HW, int C0, int C1, int groups, float eps, int silu,
-                                   void* stream) {
+                                   int x0_fp32, int x1_fp32, void* stream) {
   using namespace sdb;
   const int ctot = C0 + C1;
   if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 ||
@@ -283,13 +295,13 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
     return SDB_ERR_UNSUPPORTED;
   }
   gn_apply_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, stats, gamma, beta, (__nv_bfloat16*)out, HW,
-      C0, C1, groups, eps, silu, ppc, V, lanes);
+      x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V, lanes,
+      x0_fp32, x1_fp32);
   return check_launch("gn_apply_kernel");
 }
 
 extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out,
-                             long long rows, int C, float eps, int out_fp32, void* stream) {
+                             long long rows, int C, float eps, int in_fp32, int out_fp32, void* stream) {
   using namespace sdb;
   if (!x || !gamma || !beta || !out || rows <= 0 || C % 8 != 0 || C > LN_MAX_VEC_PER_LANE * 256) {
     set_error("sdb_layernorm: bad arguments (C=%d)", C);
@@ -298,7 +310,7 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
   const int warps = 8;
   const long long blocks = (rows + warps - 1) / warps;
   layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, gamma, beta, out, rows, C, eps, out_fp32);
+      x, gamma, beta, out, rows, C, eps, in_fp32, out_fp32);
   return check_launch("layernorm_kernel");
 }
 

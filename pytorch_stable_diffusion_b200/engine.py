@@ -1,0 +1,473 @@
+"""Execution engine: packs module parameters into kernel-friendly bf16 device tensors and runs
+the four networks as sequences of C-ABI kernel launches over NHWC bf16 activations.
+
+Data layout in HBM
+  activations   bf16, NHWC ([N, H, W, C]; the (B, S, C) token view of the attention blocks is the
+                same memory), fp32 only for latents, UNet output (eps), VAE moments and images
+  conv weights  bf16 [Cout][ky][kx][Cin] (K-major rows of 9*Cin), linear weights bf16 [out][in]
+  attention     QK projection output [tokens, 2C]; V produced transposed [C, N, S] by a swapped GEMM
+  biases/affine fp32
+
+Nothing here computes on the host: every tensor op below is a kernel from libsdb200.so.
+"""
+import math
+from types import SimpleNamespace as NS
+
+import torch
+
+from . import ops
+
+CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
+
+
+# ------------------------------------------------------------------------------------------------
+# packing
+def _bf16(t, dev):
+    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32).contiguous()
+
+
+def pack_conv3x3(conv, dev):
+    w = conv.weight.detach()
+    cout = w.shape[0]
+    return _bf16(w.permute(0, 2, 3, 1).reshape(cout, -1), dev), _f32(conv.bias, dev)
+
+
+def pack_conv1x1(conv, dev):
+    w = conv.weight.detach()
+    return _bf16(w.reshape(w.shape[0], w.shape[1]), dev), _f32(conv.bias, dev)
+
+
+def pack_direct(conv, dev):
+    w = conv.weight.detach()
+    cout, cin, k, _ = w.shape
+    return NS(w=_f32(w.permute(0, 2, 3, 1).reshape(cout, k * k, cin), dev), b=_f32(conv.bias, dev),
+              cout=cout, k=k)
+
+
+def pack_linear(lin, dev):
+    return _bf16(lin.weight, dev), (_f32(lin.bias, dev) if lin.bias is not None else None)
+
+
+def pack_norm(norm, dev):
+    return _f32(norm.weight, dev), _f32(norm.bias, dev)
+
+
+def fingerprint(module):
+    """Cheap identity of a module's parameters (storage pointer + in-place version counter)."""
+    return tuple((p.data_ptr(), p._version, p.device.index if p.is_cuda else -1) for p in module.parameters())
+
+
+def pack_resblock(m, dev, time=True):
+    """UNET_ResidualBlock (sd/diffusion.py:111-143) or VAE_ResidualBlock (sd/decoder.py:103-133)."""
+    if time:
+        gn1, conv1, gn2, conv2 = m.groupnorm_feature, m.conv_feature, m.groupnorm_merged, m.conv_merged
+    else:
+        gn1, conv1, gn2, conv2 = m.groupnorm_1, m.conv_1, m.groupnorm_2, m.conv_2
+    pk = NS()
+    pk.gn1_w, pk.gn1_b = pack_norm(gn1, dev)
+    pk.conv1_w, pk.conv1_b = pack_conv3x3(conv1, dev)
+    pk.gn2_w, pk.gn2_b = pack_norm(gn2, dev)
+    pk.conv2_w, pk.conv2_b = pack_conv3x3(conv2, dev)
+    pk.cin, pk.cout = conv1.in_channels, conv1.out_channels
+    if isinstance(m.residual_layer, torch.nn.Conv2d):
+        pk.skip_w, pk.skip_b = pack_conv1x1(m.residual_layer, dev)
+    else:
+        pk.skip_w = pk.skip_b = None
+    if time:
+        pk.time_w, tb = pack_linear(m.linear_time, dev)
+        pk.time_b = (tb + pk.conv1_b).contiguous()   # conv bias folded into the time projection bias
+    return pk
+
+
+def pack_unet_attn(m, dev):
+    """UNET_AttentionBlock (sd/diffusion.py:243-269)."""
+    pk = NS()
+    c = m.conv_input.in_channels
+    pk.c, pk.heads = c, m.attention_1.n_heads
+    pk.gn_w, pk.gn_b = pack_norm(m.groupnorm, dev)
+    pk.cin_w, pk.cin_b = pack_conv1x1(m.conv_input, dev)
+    pk.ln1 = pack_norm(m.layernorm_1, dev)
+    w = m.attention_1.in_proj.weight.detach()
+    pk.wqk = _bf16(w[:2 * c], dev)
+    pk.wv = _bf16(w[2 * c:], dev)
+    b = m.attention_1.in_proj.bias
+    pk.bqk = _f32(b[:2 * c], dev) if b is not None else None
+    pk.bv = _f32(b[2 * c:], dev) if b is not None else None
+    pk.wo1, pk.bo1 = pack_linear(m.attention_1.out_proj, dev)
+    pk.ln2 = pack_norm(m.layernorm_2, dev)
+    pk.wq2, pk.bq2 = pack_linear(m.attention_2.q_proj, dev)
+    pk.wk2, pk.bk2 = pack_linear(m.attention_2.k_proj, dev)
+    pk.wv2, pk.bv2 = pack_linear(m.attention_2.v_proj, dev)
+    pk.wo2, pk.bo2 = pack_linear(m.attention_2.out_proj, dev)
+    pk.ln3 = pack_norm(m.layernorm_3, dev)
+    # the GEGLU gate half is dead in the reference (sd/diffusion.py:359-363): keep the first 4C rows only
+    pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev)
+    pk.bg1 = _f32(m.linear_geglu_1.bias[:4 * c], dev)
+    pk.wg2, pk.bg2 = pack_linear(m.linear_geglu_2, dev)
+    pk.cout_w, pk.cout_b = pack_conv1x1(m.conv_output, dev)
+    return pk
+
+
+def pack_self_attention(att, dev):
+    """SelfAttention (sd/attention.py:7-25) as used standalone by the VAE and CLIP."""
+    pk = NS()
+    c = att.in_proj.in_features
+    pk.c, pk.heads = c, att.n_heads
+    w = att.in_proj.weight.detach()
+    b = att.in_proj.bias
+    pk.wqk, pk.wv = _bf16(w[:2 * c], dev), _bf16(w[2 * c:], dev)
+    pk.bqk = _f32(b[:2 * c], dev) if b is not None else None
+    pk.bv = _f32(b[2 * c:], dev) if b is not None else None
+    pk.wo, pk.bo = pack_linear(att.out_proj, dev)
+    return pk
+
+
+# ------------------------------------------------------------------------------------------------
+# block runners (NHWC bf16 in / out)
+def run_resblock(pk, x, x1=None, bias1=None):
+    """conv2(silu(GN(conv1(silu(GN(x ++ x1))) + t))) + skip(x ++ x1).  bias1 = conv1 bias (+ time)."""
+    n, h, w, c0 = x.shape
+    c1 = x1.shape[-1] if x1 is not None else 0
+    a = ops.groupnorm(x, pk.gn1_w, pk.gn1_b, x1=x1, silu=True)
+    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b)
+    a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True)
+    if pk.skip_w is None:
+        res = x.view(-1, c0)
+    else:
+        res = ops.gemm(x.view(-1, c0), pk.skip_w, pk.cout, a1=x1.view(-1, c1) if x1 is not None else None,
+                       M=n * h * w, c0=c0, c1=c1, bias=pk.skip_b)
+    return ops.conv3x3(a2, pk.conv2_w, pk.cout, bias=pk.conv2_b, residual=res)
+
+
+def context_kv(pk, ctx_pad):
+    """Cross-attention K and V^T of one block from the padded context [N, CTX_PAD, 768] (bf16).
+    Constant over the denoising loop, so computed once per prompt (sd/attention.py:194-198)."""
+    n = ctx_pad.shape[0]
+    flat = ctx_pad.view(n * CTX_PAD, -1)
+    k = ops.linear(flat, pk.wk2, bias=pk.bk2)
+    vt = ops.gemm(pk.wv2, flat, n * CTX_PAD, M=pk.c, c0=flat.shape[1], bias=pk.bv2, bias_per_row=True)
+    return k, vt
+
+
+def run_unet_attn(pk, x, kv):
+    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381) on NHWC bf16."""
+    n, h, w, c = x.shape
+    s = h * w
+    m = n * s
+    d = c // pk.heads
+    xf = x.view(m, c)
+    a = ops.groupnorm(x, pk.gn_w, pk.gn_b, eps=1e-6, silu=False)
+    t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b)
+    # self-attention
+    l1 = ops.layernorm(t0, *pk.ln1)
+    qk = ops.linear(l1, pk.wqk, bias=pk.bqk)
+    vt = ops.gemm(pk.wv, l1, m, M=c, c0=c, bias=pk.bv, bias_per_row=True)
+    o = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
+    ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s,
+                  ldq=2 * c, ldk=2 * c, ldo=c)
+    t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0)
+    # cross-attention over the CLIP tokens
+    l2 = ops.layernorm(t1, *pk.ln2)
+    q = ops.linear(l2, pk.wq2, bias=pk.bq2)
+    k2, vt2 = kv
+    o2 = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
+    ops.attention(q, k2, vt2, o2, NB=n, heads=pk.heads, d=d, S=s, Skv=77, Skv_pad=CTX_PAD,
+                  ldq=c, ldk=c, ldo=c)
+    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1)
+    # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
+    l3 = ops.layernorm(t2, *pk.ln3)
+    g = ops.linear(l3, pk.wg1, bias=pk.bg1)
+    t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)
+    out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=xf)
+    return out.view(n, h, w, c)
+
+
+def run_vae_attn(pk, x):
+    """VAE_AttentionBlock.forward (sd/decoder.py:34-73): single-head d=C attention over h*w tokens,
+    no GroupNorm, output re-viewed raw as (n, c, h, w) before the residual add. d = 512 does not fit
+    one TMEM accumulator, so this runs as GEMM -> row softmax -> GEMM per sample."""
+    n, h, w, c = x.shape
+    s = h * w
+    m = n * s
+    xf = x.view(m, c)
+    qk = ops.linear(xf, pk.wqk, bias=pk.bqk)                                   # [m, 2c]
+    vt = ops.gemm(pk.wv, xf, m, M=c, c0=c, bias=pk.bv, bias_per_row=True)      # [c, m]
+    o = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(c // pk.heads)
+    for i in range(n):
+        q_i = qk[i * s:(i + 1) * s, :c]
+        k_i = qk[i * s:(i + 1) * s, c:]
+        scores = ops.gemm(q_i, k_i, s, M=s, c0=c, lda0=2 * c, ldw=2 * c, out_fp32=True, nsplit=1)
+        probs = ops.softmax_rows(scores, scale)
+        ops.gemm(probs, vt[:, i * s:(i + 1) * s], c, M=s, c0=s, ldw=m, out=o[i * s:(i + 1) * s], nsplit=1)
+    y = ops.linear(o, pk.wo, bias=pk.bo)
+    return ops.vae_attn_scramble_add(y.view(n, s, c), x.view(n, s, c)).view(n, h, w, c)
+
+
+def run_clip_layer(pk, x, n, t_pad):
+    """CLIPLayer.forward (sd/clip.py:123-176) on [n*t_pad, 768] bf16 rows (rows >= 77 are padding)."""
+    c = pk.att.c
+    d = c // pk.att.heads
+    l1 = ops.layernorm(x, *pk.ln1)
+    qk = ops.linear(l1, pk.att.wqk, bias=pk.att.bqk)
+    vt = ops.gemm(pk.att.wv, l1, n * t_pad, M=c, c0=c, bias=pk.att.bv, bias_per_row=True)
+    o = torch.empty_like(x)
+    ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.att.heads, d=d, S=t_pad, Skv=77, Skv_pad=t_pad,
+                  ldq=2 * c, ldk=2 * c, ldo=c, causal=True)
+    x = ops.linear(o, pk.att.wo, bias=pk.att.bo, residual=x)
+    l2 = ops.layernorm(x, *pk.ln2)
+    hdn = ops.linear(l2, pk.w1, bias=pk.b1, act=ops.ACT_QUICK_GELU)
+    return ops.linear(hdn, pk.w2, bias=pk.b2, residual=x)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole-network engines
+class UNetEngine:
+    """Diffusion (sd/diffusion.py:751-837) = TimeEmbedding + UNET + UNET_OutputLayer."""
+
+    def __init__(self, diffusion, dev):
+        from .diffusion import UNET_AttentionBlock, UNET_ResidualBlock, Upsample
+        self.dev = dev
+        te = diffusion.time_embedding
+        self.t1_w, self.t1_b = pack_linear(te.linear_1, dev)
+        self.t2_w, self.t2_b = pack_linear(te.linear_2, dev)
+        self.res_blocks = []
+
+        def pack_seq(seq):
+            prog = []
+            for layer in seq:
+                if isinstance(layer, UNET_ResidualBlock):
+                    pk = pack_resblock(layer, dev, time=True)
+                    self.res_blocks.append(pk)
+                    prog.append(("res", pk))
+                elif isinstance(layer, UNET_AttentionBlock):
+                    prog.append(("attn", pack_unet_attn(layer, dev)))
+                elif isinstance(layer, Upsample):
+                    w, b = pack_conv3x3(layer.conv, dev)
+                    prog.append(("up", NS(w=w, b=b, cout=layer.conv.out_channels)))
+                elif isinstance(layer, torch.nn.Conv2d):
+                    if layer.in_channels <= 8:
+                        prog.append(("direct", pack_direct(layer, dev)))
+                    else:
+                        w, b = pack_conv3x3(layer, dev)
+                        kind = ops.GEMM_CONV3X3_S2 if layer.stride[0] == 2 else ops.GEMM_CONV3X3_S1
+                        prog.append(("conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind)))
+                else:
+                    raise TypeError(f"unexpected layer {type(layer)}")
+            return prog
+
+        u = diffusion.unet
+        self.encoders = [pack_seq(s) for s in u.encoders]
+        self.bottleneck = pack_seq(u.bottleneck)
+        self.decoders = [pack_seq(s) for s in u.decoders]
+        self.attn_blocks = [pk for prog in self.encoders + [self.bottleneck] + self.decoders
+                            for kind, pk in prog if kind == "attn"]
+        # all linear_time projections as one [sum(Cout), 1280] matrix
+        offs, off = [], 0
+        for pk in self.res_blocks:
+            offs.append(off)
+            off += pk.cout
+        self.time_offsets, self.time_total = offs, off
+        self.time_w = torch.cat([pk.time_w for pk in self.res_blocks], 0).contiguous()
+        self.time_b = torch.cat([pk.time_b for pk in self.res_blocks], 0).contiguous()
+        for pk, o in zip(self.res_blocks, offs):
+            pk.time_off = o
+            pk.time_w = None
+        fin = diffusion.final
+        self.fin_gn = pack_norm(fin.groupnorm, dev)
+        self.fin_w, self.fin_b = pack_conv3x3(fin.conv, dev)
+        self.fin_cout = fin.conv.out_channels
+
+    def time_vectors(self, time):
+        """time fp32 [R, 320] -> fp32 [R, sum(Cout)]: per-ResBlock conv_feature bias + linear_time(
+        silu(TimeEmbedding(time))) (sd/diffusion.py:64-76,184-194). Batch-independent."""
+        h1 = ops.small_linear(time, self.t1_w, self.t1_b, act_out=ops.ACT_SILU)
+        temb = ops.small_linear(h1, self.t2_w, self.t2_b)
+        return ops.small_linear(temb, self.time_w, self.time_b, act_in=ops.ACT_SILU)
+
+    def context_kv(self, context):
+        """context fp32/bf16 [N, 77, 768] -> per-attention-block (K, V^T)."""
+        n, t, dc = context.shape
+        ctx = torch.zeros((n, CTX_PAD, dc), device=self.dev, dtype=torch.bfloat16)
+        ctx[:, :t] = context.to(device=self.dev, dtype=torch.bfloat16)
+        return [context_kv(pk, ctx) for pk in self.attn_blocks]
+
+    def _run_seq(self, prog, x, x1, tvec, kv_iter):
+        for kind, pk in prog:
+            if kind == "res":
+                x = run_resblock(pk, x, x1, tvec[pk.time_off:pk.time_off + pk.cout])
+                x1 = None
+            elif kind == "attn":
+                x = run_unet_attn(pk, x, next(kv_iter))
+            elif kind == "up":
+                x = ops.conv3x3(ops.upsample2x(x), pk.w, pk.cout, bias=pk.b)
+            elif kind == "conv":
+                x = ops.conv3x3(x, pk.w, pk.cout, bias=pk.b, kind=pk.kind)
+            elif kind == "direct":
+                x = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k)
+        return x
+
+    def forward_nhwc(self, x, tvec, kvs):
+        """x bf16 [N, h, w, 4]; tvec fp32 [sum(Cout)] (one row of time_vectors); returns eps fp32
+        NHWC [N, h, w, 4]. UNET.forward sd/diffusion.py:628-676 without materialising torch.cat."""
+        kv_iter = iter(kvs)
+        skips = []
+        for prog in self.encoders:
+            x = self._run_seq(prog, x, None, tvec, kv_iter)
+            skips.append(x)
+        x = self._run_seq(self.bottleneck, x, None, tvec, kv_iter)
+        for prog in self.decoders:
+            x = self._run_seq(prog, x, skips.pop(), tvec, kv_iter)
+        a = ops.groupnorm(x, *self.fin_gn, silu=True)
+        return ops.conv3x3(a, self.fin_w, self.fin_cout, bias=self.fin_b, out_fp32=True)
+
+
+def _pack_vae_sequential(seq, dev, pad_rb):
+    from .decoder import VAE_AttentionBlock, VAE_ResidualBlock
+    prog = []
+    for layer in seq:
+        if isinstance(layer, VAE_ResidualBlock):
+            prog.append(("res", pack_resblock(layer, dev, time=False)))
+        elif isinstance(layer, VAE_AttentionBlock):
+            prog.append(("attn", pack_self_attention(layer.attention, dev)))
+        elif isinstance(layer, torch.nn.Conv2d):
+            if layer.in_channels <= 8:
+                prog.append(("direct", pack_direct(layer, dev)))
+            elif layer.kernel_size[0] == 1:
+                w, b = pack_conv1x1(layer, dev)
+                prog.append(("conv1", NS(w=w, b=b, cout=layer.out_channels)))
+            else:
+                w, b = pack_conv3x3(layer, dev)
+                kind = ops.GEMM_CONV3X3_S1
+                if layer.stride[0] == 2:
+                    kind = ops.GEMM_CONV3X3_S2_PAD_RB if pad_rb else ops.GEMM_CONV3X3_S2
+                prog.append(("conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind)))
+        elif isinstance(layer, torch.nn.Upsample):
+            prog.append(("up", None))
+        elif isinstance(layer, torch.nn.GroupNorm):
+            prog.append(("gn", pack_norm(layer, dev)))
+        elif isinstance(layer, torch.nn.SiLU):
+            prog.append(("silu", None))
+        else:
+            raise TypeError(f"unexpected layer {type(layer)}")
+    # GroupNorm followed by SiLU is one kernel
+    fused = []
+    i = 0
+    while i < len(prog):
+        if prog[i][0] == "gn" and i + 1 < len(prog) and prog[i + 1][0] == "silu":
+            fused.append(("gn_silu", prog[i][1]))
+            i += 2
+        else:
+            fused.append(prog[i])
+            i += 1
+    return fused
+
+
+def _run_vae_sequential(prog, x, last_fp32):
+    for idx, (kind, pk) in enumerate(prog):
+        last = idx == len(prog) - 1
+        fp32 = last and last_fp32
+        if kind == "res":
+            x = run_resblock(pk, x)
+        elif kind == "attn":
+            x = run_vae_attn(pk, x)
+        elif kind == "direct":
+            x = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=fp32)
+        elif kind == "conv1":
+            n, h, w, c = x.shape
+            x = ops.linear(x.view(-1, c), pk.w, bias=pk.b, out_fp32=fp32).view(n, h, w, pk.cout)
+        elif kind == "conv":
+            x = ops.conv3x3(x, pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=fp32)
+        elif kind == "up":
+            x = ops.upsample2x(x)
+        elif kind == "gn_silu":
+            x = ops.groupnorm(x, *pk, silu=True)
+        elif kind == "gn":
+            x = ops.groupnorm(x, *pk, silu=False)
+        else:
+            raise RuntimeError(f"VAE program entry {kind} has no kernel")
+    return x
+
+
+class VAEDecoderEngine:
+    """VAE_Decoder (sd/decoder.py:192-374)."""
+
+    def __init__(self, decoder, dev):
+        self.dev = dev
+        self.prog = _pack_vae_sequential(decoder, dev, pad_rb=False)
+
+    def forward_nhwc(self, latents):
+        """latents fp32 NCHW [B, 4, h, w] -> image fp32 NHWC [B, 8h, 8w, 3] (x / 0.18215 first)."""
+        x = ops.nchw_to_nhwc_bf16(latents, scale=1.0 / 0.18215)
+        return _run_vae_sequential(self.prog, x, last_fp32=True)
+
+
+class VAEEncoderEngine:
+    """VAE_Encoder (sd/encoder.py:8-155)."""
+
+    def __init__(self, encoder, dev):
+        self.dev = dev
+        self.prog = _pack_vae_sequential(encoder, dev, pad_rb=True)
+
+    def forward_from_nhwc(self, x, noise):
+        """x bf16 NHWC [B, H, W, 3]; noise fp32 NCHW [B, 4, H/8, W/8] -> latents fp32 NCHW."""
+        moments = _run_vae_sequential(self.prog, x, last_fp32=True)
+        return ops.vae_encode_tail(moments, noise)
+
+
+class CLIPEngine:
+    """CLIP (sd/clip.py:179-261)."""
+
+    def __init__(self, clip, dev):
+        self.dev = dev
+        self.table = _f32(clip.embedding.token_embedding.weight, dev)
+        self.pos = _f32(clip.embedding.position_embedding, dev)
+        self.layers = []
+        for layer in clip.layers:
+            pk = NS()
+            pk.ln1 = pack_norm(layer.layernorm_1, dev)
+            pk.att = pack_self_attention(layer.attention, dev)
+            pk.ln2 = pack_norm(layer.layernorm_2, dev)
+            pk.w1, pk.b1 = pack_linear(layer.linear_1, dev)
+            pk.w2, pk.b2 = pack_linear(layer.linear_2, dev)
+            self.layers.append(pk)
+        self.ln = pack_norm(clip.layernorm, dev)
+
+    def forward(self, tokens):
+        """tokens int64 [B, 77] -> fp32 [B, 77, 768]."""
+        n, t = tokens.shape
+        t_pad = (t + 7) // 8 * 8
+        x = ops.clip_embed(tokens.to(self.dev).contiguous(), self.table, self.pos, t_pad)
+        d = x.shape[-1]
+        x = x.view(n * t_pad, d)
+        for pk in self.layers:
+            x = run_clip_layer(pk, x, n, t_pad)
+        out = ops.layernorm(x, *self.ln, out_fp32=True)
+        return out.view(n, t_pad, d)[:, :t].contiguous()
+
+
+class EngineCache:
+    """Mixin: lazily built, parameter-fingerprinted engine for a top-level nn.Module."""
+
+    _engine_cls = None
+
+    def _engine(self):
+        params = list(self.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"{type(self).__name__} runs on hand-written CUDA kernels only; move it to a CUDA device "
+                "(there is no CPU fallback)")
+        fp = fingerprint(self)
+        cached = self.__dict__.get("_sdb_engine")
+        if cached is None or cached[0] != fp:
+            cached = (fp, type(self)._engine_cls(self, dev))
+            self.__dict__["_sdb_engine"] = cached
+        return cached[1]
+
+    def invalidate_packed(self):
+        self.__dict__.pop("_sdb_engine", None)

@@ -53,7 +53,7 @@ def _choose_split(m_tiles, cout, block_n, nkb):
 
 
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
-         out=None, out_fp32=False, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
+         out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
          lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
     lib = _ext.lib()
@@ -63,7 +63,11 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.kind = kind
     args.a0, args.a1, args.w = _p(a0), _p(a1), _p(w)
     args.bias = _p(_chk(bias, torch.float32, "bias")) if bias is not None else None
-    args.residual = _p(_chk(residual, torch.bfloat16, "residual")) if residual is not None else None
+    if residual is not None:
+        if residual.dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("residual must be bf16 or fp32")
+        args.residual = _p(residual)
+        args.res_fp32 = 1 if residual.dtype == torch.float32 else 0
     if kind == GEMM_LINEAR:
         if M is None:
             M = a0.shape[0] if a0.dim() == 2 else a0.numel() // a0.shape[-1]
@@ -90,6 +94,9 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
                           dtype=torch.float32 if out_fp32 else torch.bfloat16)
     args.out = _p(out)
     args.out_fp32 = 1 if out_fp32 else 0
+    if out2 is True:
+        out2 = torch.empty(out.shape, device=out.device, dtype=torch.bfloat16)
+    args.out2 = _p(out2)
     args.bias_per_row = 1 if bias_per_row else 0
     args.act = act
     if block_n == 0:
@@ -104,7 +111,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         args.workspace = _p(ws)
     args.nsplit = nsplit
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
-    return out
+    return (out, out2) if out2 is not None else out
 
 
 def linear(x, w, bias=None, **kw):
@@ -119,15 +126,18 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
     n, h, wd, c = x.shape
     out = gemm(x, w, cout, kind=kind, bias=bias, conv_dims=(n, h, wd), c0=c, **kw)
     s2 = kind != GEMM_CONV3X3_S1
-    return out.view(n, h // 2 if s2 else h, wd // 2 if s2 else wd, cout)
+    shape = (n, h // 2 if s2 else h, wd // 2 if s2 else wd, cout)
+    if isinstance(out, tuple):
+        return out[0].view(shape), out[1].view(shape)
+    return out.view(shape)
 
 
-def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False):
+def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0):
     lib = _ext.lib()
     a = AttnArgs()
     a.q, a.k, a.vt, a.out = _p(_chk(q, torch.bfloat16, "q")), _p(_chk(k, torch.bfloat16, "k")), \
         _p(_chk(vt, torch.bfloat16, "vt")), _p(_chk(out, torch.bfloat16, "out"))
-    a.NB, a.heads, a.d, a.S, a.Skv, a.Skv_pad = NB, heads, d, S, Skv, Skv_pad
+    a.NB, a.heads, a.d, a.S, a.Skv, a.Skv_pad, a.vt_ld = NB, heads, d, S, Skv, Skv_pad, vt_ld
     a.ldq, a.ldk, a.ldo = ldq, ldk, ldo
     a.causal = 1 if causal else 0
     a.scale = 1.0 / math.sqrt(d)
@@ -136,32 +146,34 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
 
 
 def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
-    """GroupNorm (+SiLU) over NHWC bf16 x0 ++ x1 (channel concat); returns bf16 [N, H, W, C0+C1]."""
+    """GroupNorm (+SiLU) over NHWC x0 ++ x1 (channel concat; each bf16 or fp32); returns bf16
+    [N, H, W, C0+C1]."""
     lib = _ext.lib()
-    _chk(x0, torch.bfloat16, "x0")
+    f0 = 1 if x0.dtype == torch.float32 else 0
+    f1 = 1 if (x1 is not None and x1.dtype == torch.float32) else 0
     n = x0.shape[0]
     c0 = x0.shape[-1]
     hw = x0.numel() // (n * c0)
     c1 = x1.shape[-1] if x1 is not None else 0
     stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float64)
     _ext.check(lib.sdb_fill_zero(_p(stats), stats.numel() * 8, _stream()), "sdb_fill_zero")
-    _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, _stream()),
+    _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
                "sdb_groupnorm_stats")
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
     _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
-                                       c0, c1, groups, float(eps), 1 if silu else 0, _stream()),
+                                       c0, c1, groups, float(eps), 1 if silu else 0, f0, f1, _stream()),
                "sdb_groupnorm_apply")
     return out
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False):
     lib = _ext.lib()
-    _chk(x, torch.bfloat16, "x")
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
     _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
-                                 1 if out_fp32 else 0, _stream()), "sdb_layernorm")
+                                 1 if x.dtype == torch.float32 else 0, 1 if out_fp32 else 0, _stream()),
+               "sdb_layernorm")
     return out
 
 
@@ -235,13 +247,24 @@ def cfg_ddpm_step(latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in, e
 
 
 def vae_attn_scramble_add(y, res):
+    """y bf16, res fp32 [N, HW, C] -> (fp32, bf16) outputs."""
     lib = _ext.lib()
+    _chk(res, torch.float32, "res")
     n = res.shape[0]
     c = res.shape[-1]
     hw = res.numel() // (n * c)
     out = torch.empty_like(res)
-    _ext.check(lib.sdb_vae_attn_scramble_add(_p(y), _p(res), _p(out), n, hw, c, _stream()),
+    out2 = torch.empty(res.shape, device=res.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_vae_attn_scramble_add(_p(y), _p(res), _p(out), _p(out2), n, hw, c, _stream()),
                "sdb_vae_attn_scramble_add")
+    return out, out2
+
+
+def f32_to_bf16(x):
+    lib = _ext.lib()
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _ext.check(lib.sdb_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "sdb_f32_to_bf16")
     return out
 
 
@@ -279,7 +302,7 @@ def clip_embed(tokens, table, pos, t_pad):
     lib = _ext.lib()
     nb, t = tokens.shape
     vocab, d = table.shape
-    out = torch.empty((nb, t_pad, d), device=tokens.device, dtype=torch.bfloat16)
+    out = torch.empty((nb, t_pad, d), device=tokens.device, dtype=torch.float32)
     _ext.check(lib.sdb_clip_embed(_p(tokens), _p(table), _p(pos), _p(out), nb, t, t_pad, d, vocab, _stream()),
                "sdb_clip_embed")
     return out

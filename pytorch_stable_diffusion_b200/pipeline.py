@@ -1,0 +1,278 @@
+"""pipeline.generate() with the reference's signature (sd/pipeline.py:13-27), running CLIP, the
+optional VAE encoder, the classifier-free-guidance DDPM loop and the VAE decoder on hand-written
+sm_100a kernels. The whole denoising loop (n_steps x [UNet + fused CFG/DDPM step]) is captured
+once in a CUDA graph and replayed.
+
+Extensions are keyword-only and default to the reference's behaviour (one 512x512 image, RNG drawn
+from torch.Generator(device)): batch_size, height/width, per-sample seeds, injected noise,
+return_all, use_cuda_graph, trace.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .ddpm import DDPMSampler
+
+WIDTH = 512
+HEIGHT = 512
+LATENTS_WIDTH = WIDTH // 8
+LATENTS_HEIGHT = HEIGHT // 8
+
+_GRAPH_CACHE = {}
+
+
+def rescale(x, old_range, new_range, clamp=False):
+    """In-place affine range map, optional clamp (sd/pipeline.py:265-307)."""
+    old_min, old_max = old_range
+    new_min, new_max = new_range
+    x -= old_min
+    x *= (new_max - new_min) / (old_max - old_min)
+    x += new_min
+    if clamp:
+        x = x.clamp(new_min, new_max)
+    return x
+
+
+def get_time_embedding(timestep):
+    """(1, 320) sinusoidal embedding, cosine half first (sd/pipeline.py:310-349)."""
+    freqs = torch.pow(10000, -torch.arange(start=0, end=160, dtype=torch.float32) / 160)
+    x = torch.tensor([timestep], dtype=torch.float32)[:, None] * freqs[None]
+    return torch.cat([torch.cos(x), torch.sin(x)], dim=-1)
+
+
+def _encode_prompts(clip, tokenizer, prompts, device):
+    ids = [tokenizer.batch_encode_plus([p], padding="max_length", max_length=77).input_ids[0] for p in prompts]
+    uniq = {}
+    for row in ids:
+        uniq.setdefault(tuple(row), None)
+    keys = list(uniq)
+    tokens = torch.tensor(keys, dtype=torch.long, device=device)
+    ctx = clip(tokens)                                   # (U, 77, 768) fp32
+    index = [keys.index(tuple(row)) for row in ids]
+    return ctx[index]
+
+
+def _draw(shape, generator, seeds, device):
+    """One noise tensor of `shape` = (B, ...). With per-sample seeds each sample owns a CPU
+    generator (its stream equals an independent batch-1 reference run on CPU)."""
+    if seeds is None:
+        return torch.randn(shape, generator=generator, device=device)
+    parts = [torch.randn((1,) + tuple(shape[1:]), generator=g) for g in seeds]
+    return torch.cat(parts, 0).to(device)
+
+
+class _Loop:
+    """Static buffers + captured CUDA graph of one denoising-loop configuration."""
+
+    def __init__(self, eng, B, h, w, n_steps, do_cfg, cfg_scale, device):
+        self.eng, self.B, self.n_steps, self.do_cfg, self.cfg_scale = eng, B, n_steps, do_cfg, cfg_scale
+        N = 2 * B if do_cfg else B
+        self.latents = torch.zeros((B, 4, h, w), device=device, dtype=torch.float32)
+        self.x_in = torch.zeros((N, h, w, 4), device=device, dtype=torch.bfloat16)
+        self.noise = torch.zeros((n_steps, B, 4, h, w), device=device, dtype=torch.float32)
+        self.coef = torch.zeros((n_steps, 5), device=device, dtype=torch.float32)
+        self.tvecs = torch.zeros((n_steps, eng.time_total), device=device, dtype=torch.float32)
+        self.kvs = None
+        self.graph = None
+
+    def set_inputs(self, latents, noise, coef, tvecs, kvs):
+        self.latents.copy_(latents)
+        self.noise.copy_(noise)
+        self.coef.copy_(coef)
+        self.tvecs.copy_(tvecs)
+        if self.kvs is None:
+            self.kvs = [(k.clone(), v.clone()) for k, v in kvs]
+        else:
+            for (dk, dv), (k, v) in zip(self.kvs, kvs):
+                dk.copy_(k)
+                dv.copy_(v)
+        self.x_in.copy_(ops.nchw_to_nhwc_bf16(self.latents, repeat=2 if self.do_cfg else 1))
+
+    def run_steps(self, trace=None, timesteps=None):
+        for i in range(self.n_steps):
+            eps = self.eng.forward_nhwc(self.x_in, self.tvecs[i], self.kvs)
+            if trace is not None:
+                trace.append((int(timesteps[i]), self.latents.clone(), ops.nhwc_to_nchw_f32(eps)))
+            ops.cfg_ddpm_step(self.latents, eps, self.noise[i], self.coef, i, self.cfg_scale, self.do_cfg,
+                              self.x_in)
+
+    def capture(self):
+        # one eager UNet evaluation first: lazy CUDA/module initialisation must not happen under capture
+        self.eng.forward_nhwc(self.x_in, self.tvecs[0], self.kvs)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_steps()
+        self.graph = g
+
+    def replay(self):
+        self.graph.replay()
+
+
+def generate(
+    prompt,
+    uncond_prompt=None,
+    input_image=None,
+    strength=0.8,
+    do_cfg=True,
+    cfg_scale=7.5,
+    sampler_name="ddpm",
+    n_inference_steps=50,
+    models={},
+    seed=None,
+    device=None,
+    idle_device=None,
+    tokenizer=None,
+    *,
+    batch_size=1,
+    height=None,
+    width=None,
+    seeds=None,
+    noise=None,
+    use_cuda_graph=True,
+    return_all=False,
+    trace=None,
+):
+    """Text-to-image / image-to-image sampling; returns a uint8 (H, W, 3) array like the reference
+    (sd/pipeline.py:72-262), or (B, H, W, 3) with return_all=True.
+
+    noise: optional dict of injected fp32 tensors {'latents' | ('encoder', 'add'), 'steps'} replacing
+    every torch.randn draw (parity runs against the CPU oracle). trace: optional list receiving
+    (timestep, latents_in, unet_output) per step (forces eager execution).
+    """
+    with torch.no_grad():
+        if not 0 < strength <= 1:
+            raise ValueError(f"Strength must be between 0 and 1, got {strength}")
+        if sampler_name != "ddpm":
+            raise ValueError(f"Sampler {sampler_name} not found")
+        if idle_device:
+            to_idle = lambda x: x.to(idle_device)
+        else:
+            to_idle = lambda x: x
+        if device is None:
+            device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("this build runs on hand-written CUDA kernels for sm_100a only; "
+                               f"device={device} is not supported (no CPU fallback)")
+        H = HEIGHT if height is None else height
+        W = WIDTH if width is None else width
+        if H % 64 or W % 64:
+            raise ValueError("height and width must be multiples of 64")
+        lh, lw = H // 8, W // 8
+        B = batch_size
+
+        generator = torch.Generator(device=device)
+        if seed is None:
+            generator.seed()
+        else:
+            generator.manual_seed(seed)
+        sample_gens = None
+        if seeds is not None:
+            if len(seeds) != B:
+                raise ValueError("seeds must have batch_size entries")
+            sample_gens = [torch.Generator(device="cpu").manual_seed(int(s)) for s in seeds]
+
+        # ---- CLIP (sd/pipeline.py:101-134)
+        clip = models["clip"]
+        clip.to(device)
+        prompts = list(prompt) if isinstance(prompt, (list, tuple)) else [prompt] * B
+        if len(prompts) != B:
+            raise ValueError("a list-valued prompt must have batch_size entries")
+        if do_cfg:
+            unconds = (list(uncond_prompt) if isinstance(uncond_prompt, (list, tuple))
+                       else [uncond_prompt if uncond_prompt is not None else ""] * B)
+            context = torch.cat([_encode_prompts(clip, tokenizer, prompts, device),
+                                 _encode_prompts(clip, tokenizer, unconds, device)])
+        else:
+            context = _encode_prompts(clip, tokenizer, prompts, device)
+        to_idle(clip)
+
+        sampler = DDPMSampler(generator)
+        sampler.set_inference_timesteps(n_inference_steps)
+        latents_shape = (B, 4, lh, lw)
+
+        # ---- initial latents (sd/pipeline.py:149-196)
+        if input_image:
+            encoder = models["encoder"]
+            encoder.to(device)
+            img = np.array(input_image.resize((W, H)))
+            img_u8 = torch.tensor(img, dtype=torch.uint8, device=device).unsqueeze(0)
+            x = ops.uint8_to_image(img_u8.contiguous())              # bf16 NHWC in [-1, 1]
+            if B > 1:
+                x = x.expand(B, -1, -1, -1).contiguous()
+            enc_noise = noise["encoder"].to(device) if noise is not None else _draw(
+                latents_shape, generator, sample_gens, device)
+            latents = encoder._engine().forward_from_nhwc(x, enc_noise.to(torch.float32).contiguous())
+            sampler.set_strength(strength=strength)
+            t0 = int(sampler.timesteps[0])
+            add = noise["add"].to(device) if noise is not None else _draw(
+                latents_shape, generator, sample_gens, device)
+            a = sampler.alphas_cumprod[t0]
+            latents = ops.axpby(latents, add.to(torch.float32).contiguous(), float(a ** 0.5),
+                                float((1 - a) ** 0.5))
+            to_idle(encoder)
+        else:
+            latents = noise["latents"].to(device) if noise is not None else _draw(
+                latents_shape, generator, sample_gens, device)
+        latents = latents.to(torch.float32).contiguous()
+
+        # ---- per-step constants: noise, DDPM coefficients, time embeddings
+        timesteps = sampler.timesteps
+        n_steps = len(timesteps)
+        if noise is not None:
+            step_noise = noise["steps"].to(device=device, dtype=torch.float32, non_blocking=True)
+        else:
+            draws = [_draw(latents_shape, generator, sample_gens, device) if int(t) > 0
+                     else torch.zeros(latents_shape, device=device) for t in timesteps]
+            step_noise = torch.stack(draws)
+        if step_noise.shape[0] < n_steps:   # the last step (t = 0) draws nothing
+            pad = torch.zeros((n_steps - step_noise.shape[0],) + tuple(latents_shape), device=device)
+            step_noise = torch.cat([step_noise, pad])
+        coef = sampler.coefficient_table(device)
+        temb = torch.cat([get_time_embedding(int(t)) for t in timesteps]).to(device)
+
+        diffusion = models["diffusion"]
+        diffusion.to(device)
+        decoder = models["decoder"]
+        decoder.to(device)
+        images = sample_on_device(diffusion, decoder, context, latents, step_noise, coef, temb,
+                                  do_cfg=do_cfg, cfg_scale=cfg_scale, use_cuda_graph=use_cuda_graph,
+                                  trace=trace, timesteps=timesteps)
+        to_idle(diffusion)
+        to_idle(decoder)
+        images = images.to("cpu").numpy()
+        return images if return_all else images[0]
+
+
+def sample_on_device(diffusion, decoder, context, latents, step_noise, coef, temb, *, do_cfg=True,
+                     cfg_scale=7.5, use_cuda_graph=True, trace=None, timesteps=None):
+    """Device-resident core of generate(): everything is already in HBM.
+
+    context fp32 [N, 77, 768] (N = 2B with CFG: conditional rows first), latents fp32 [B, 4, h, w],
+    step_noise fp32 [steps, B, 4, h, w], coef fp32 [steps, 5] (DDPMSampler.coefficient_table),
+    temb fp32 [steps, 320] (get_time_embedding rows). Runs the denoising loop (sd/pipeline.py:205-237)
+    as one CUDA graph and decodes (sd/pipeline.py:243-259). Returns uint8 NHWC [B, 8h, 8w, 3] on device.
+    """
+    device = latents.device
+    B, _, lh, lw = latents.shape
+    n_steps = step_noise.shape[0]
+    eng = diffusion._engine()
+    tvecs = eng.time_vectors(temb)
+    kvs = eng.context_kv(context)
+    key = (id(eng), B, lh, lw, n_steps, bool(do_cfg), float(cfg_scale), device.index)
+    loop = _GRAPH_CACHE.get(key)
+    if loop is None:
+        loop = _Loop(eng, B, lh, lw, n_steps, bool(do_cfg), float(cfg_scale), device)
+        _GRAPH_CACHE.clear()          # one resident configuration; graphs pin their memory pool
+        _GRAPH_CACHE[key] = loop
+    loop.set_inputs(latents, step_noise, coef, tvecs, kvs)
+    if trace is not None or not use_cuda_graph:
+        loop.run_steps(trace=trace, timesteps=timesteps)
+    else:
+        if loop.graph is None:
+            loop.capture()
+            loop.set_inputs(latents, step_noise, coef, tvecs, kvs)
+        loop.replay()
+    images = decoder.decode_nhwc(loop.latents)           # fp32 NHWC in ~[-1, 1]
+    return ops.image_to_uint8(images)
