@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Headline benchmark: 512x512 txt2img images/s (50-step DDPM, CFG 7.5) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch: CLIP x2 -> 50 x (UNet with CFG pair + fused
+CFG/DDPM step, replayed from one CUDA graph) -> VAE decode -> uint8, for B images per GPU
+(BASELINE.json configs[1]: B = 8 on one B200). Multi-GPU = independent seeds per rank, no data-path
+collective (weak scaling: B per GPU is fixed).
+
+  value     images/s with every input resident in HBM when the timed region starts
+  e2e       the same through pipeline.generate() (prompt strings in, host uint8 images out)
+  roofline  gemm_tc_kernel (implicit-GEMM conv + linear, the dominant kernel): algorithmic FLOPs of
+            its launches in one UNet evaluation / their CUDA-event durations, against the measured
+            sustained bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference algorithm (oracle/sd_oracle.py) on the host cores, on a
+            bounded sample extrapolated to one 50-step image
+
+--impl reference times that CPU path alone (the reference is pure Python over PyTorch CPU kernels; its
+checkout does not travel to the GPU box, so the arm runs the oracle restatement of it).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "512x512 txt2img images/s (50-step DDPM, CFG 7.5)"
+UNIT = "images/s"
+N_STEPS = 50
+CFG = 7.5
+H = W = 512
+UNET_GFLOP_PER_IMAGE_STEP = 1498.25     # SURVEY.md §8d, algorithmic, CFG pair, 64x64 latent
+VAE_GFLOP_PER_IMAGE = 2514.52
+CLIP_GFLOP_PER_PROMPT = 13.30
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": d.get("bf16_tflops_sustained", 1390.6), "tflops_burst": d.get("bf16_tflops", 1654.9),
+                "hbm_gbs": d.get("hbm_gbs", 6546.9), "source": "MEASURED_PEAKS.json (sustained bf16)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_sample(weights, torch, sd_oracle, n_unet=1):
+    """One bounded sample of config 1 on the host: CLIP x2, n_unet UNet evaluations (CFG pair, 64x64
+    latent), VAE decode of one 64x64 latent. Returns seconds per phase."""
+    from pytorch_stable_diffusion_b200.synthetic import canonical_tokens
+    cond, uncond = canonical_tokens()
+    g = torch.Generator().manual_seed(42)
+    lat = torch.randn(1, 4, H // 8, W // 8, generator=g)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ctx = torch.cat([sd_oracle.clip_forward(weights["clip"], cond.view(1, -1)),
+                         sd_oracle.clip_forward(weights["clip"], uncond.view(1, -1))])
+        t1 = time.perf_counter()
+        for i in range(n_unet):
+            out = sd_oracle.diffusion_forward(weights["diffusion"], lat.repeat(2, 1, 1, 1), ctx,
+                                              sd_oracle.get_time_embedding(980 - 20 * i))
+        t2 = time.perf_counter()
+        img = sd_oracle.vae_decoder_forward(weights["decoder"], lat.clone())
+        t3 = time.perf_counter()
+    assert torch.isfinite(out).all() and torch.isfinite(img).all()
+    return {"clip_s": t1 - t0, "unet_s": (t2 - t1) / n_unet, "decode_s": t3 - t2}
+
+
+def cpu_images_per_s(s):
+    return 1.0 / (s["clip_s"] + N_STEPS * s["unet_s"] + s["decode_s"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sd_oracle
+    from pytorch_stable_diffusion_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    models = synthetic.build_models("cpu", which=("decoder", "diffusion", "clip"))
+    weights = synthetic.state_dicts(models)
+    for _ in range(args.warmup):
+        cpu_sample(weights, torch, sd_oracle, 1)
+    samples = [cpu_sample(weights, torch, sd_oracle, 1) for _ in range(args.steps)]
+    mean = {k: sum(s[k] for s in samples) / len(samples) for k in samples[0]}
+    v = cpu_images_per_s(mean)
+    sample = ("per step: CLIP x2 + 1 UNet evaluation (CFG pair, 64x64 latent) + VAE decode of one image, fp32 "
+              "on the host; images/s = 1 / (clip + 50*unet + decode)")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (mean["clip_s"] + mean["unet_s"] + mean["decode_s"]),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[0]: SD1.5-arch random-init txt2img 512x512, batch 1, 50 DDPM steps, "
+                                   "CFG 7.5, CPU (oracle port of the reference algorithm)",
+                       "torch_threads": torch.get_num_threads()},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "seconds": mean},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="one eager UNet evaluation + decode (short command for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3 and not args.profile_only:
+        print("bench.py: raising --warmup to 3 (timing rule)", file=sys.stderr)
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; "
+                         "use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from pytorch_stable_diffusion_b200 import _ext, ops, pipeline, synthetic
+    from pytorch_stable_diffusion_b200.ddpm import DDPMSampler
+    peaks = load_peaks()
+    B = args.batch
+    lh, lw = H // 8, W // 8
+
+    t_build = time.perf_counter()
+    models = synthetic.build_models("cpu")
+    cpu_weights = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
+        cpu_weights = synthetic.state_dicts({k: models[k] for k in ("clip", "diffusion", "decoder")})
+        cpu_weights = {k: {n: t.clone() for n, t in sd.items()} for k, sd in cpu_weights.items()}
+    for m in models.values():
+        m.to(dev)
+    t_build = time.perf_counter() - t_build
+
+    # ---- device-resident inputs of one step (seeds are disjoint across ranks)
+    cond, uncond = synthetic.canonical_tokens()
+    tokens = torch.stack([cond, uncond]).to(dev)
+    seeds = [42 + rank * B + i for i in range(B)]
+    gens = [torch.Generator().manual_seed(s) for s in seeds]
+    latents = torch.cat([torch.randn((1, 4, lh, lw), generator=g) for g in gens]).to(dev)
+    sampler = DDPMSampler(torch.Generator())
+    sampler.set_inference_timesteps(N_STEPS)
+    step_noise = torch.stack([
+        torch.cat([torch.randn((1, 4, lh, lw), generator=g) for g in gens]) if int(t) > 0
+        else torch.zeros((B, 4, lh, lw)) for t in sampler.timesteps]).to(dev)
+    coef = sampler.coefficient_table(dev)
+    temb = torch.cat([pipeline.get_time_embedding(int(t)) for t in sampler.timesteps]).to(dev)
+    idx = torch.tensor([0] * B + [1] * B, device=dev)
+
+    def step_device():
+        ctx = models["clip"](tokens)                   # (2, 77, 768): cond, uncond
+        context = ctx[idx]                             # (2B, 77, 768), conditional rows first
+        return pipeline.sample_on_device(models["diffusion"], models["decoder"], context, latents, step_noise,
+                                         coef, temb, do_cfg=True, cfg_scale=CFG)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.profile_only:
+        with torch.no_grad():
+            eng = models["diffusion"]._engine()
+            ctx = models["clip"](tokens)[idx]
+            kvs = eng.context_kv(ctx)
+            tv = eng.time_vectors(temb)
+            x = ops.nchw_to_nhwc_bf16(latents, repeat=2)
+            eng.forward_nhwc(x, tv[0], kvs)
+            models["decoder"].decode_nhwc(latents[:1])
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_only": True, "fault": _ext.read_fault()}))
+        return 0
+
+    with torch.no_grad():
+        # ---- warm-up (first call captures the CUDA graph of the 50-step loop)
+        n_before_capture = _ext.launch_count()
+        t_cap = time.perf_counter()
+        img = step_device()
+        torch.cuda.synchronize()
+        t_cap = time.perf_counter() - t_cap
+        loop = next(iter(pipeline._GRAPH_CACHE.values()))
+        for _ in range(args.warmup - 1):
+            img = step_device()
+        barrier()
+
+        # ---- timed region: K steps, inputs already in HBM
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        clocks = ClockSampler(vis.split(",")[local] if vis else local)
+        clocks.start()
+        n0 = _ext.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            img = step_device()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        eager_launches = _ext.launch_count() - n0
+        clk = clocks.stop()
+        graph_launches = loop.graph_launches
+        gpu_launches = eager_launches + args.steps * graph_launches
+        tms = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        value = world * B * args.steps / (ms / 1e3)
+
+        # ---- phase split on the device (graph replay alone, decode alone), rank 0 only, not the headline
+        def timed(fn, reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        loop_ms = timed(loop.replay, 2)
+        dec_ms = timed(lambda: models["decoder"].decode_nhwc(loop.latents), 3)
+        clip_ms = timed(lambda: models["clip"](tokens), 3)
+
+        # ---- end to end through the public API: prompt strings in, host uint8 images out
+        e2e = None
+        if not args.no_e2e:
+            tok = synthetic.StubTokenizer()
+            kw = dict(models=models, batch_size=B, n_inference_steps=N_STEPS, cfg_scale=CFG, device=dev,
+                      tokenizer=tok, return_all=True)
+            out = pipeline.generate("a", "b", seed=1000 + rank, **kw)     # warm (same graph)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            reps = max(1, min(args.steps, 3))
+            for i in range(reps):
+                out = pipeline.generate("a", "b", seed=2000 + rank * 100 + i, **kw)
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            assert out.shape == (B, H, W, 3) and out.dtype.name == "uint8"
+            e2e = {"value": world * B * reps / (float(t.item()) / 1e3), "unit": UNIT,
+                   "h2d_bytes_per_step": 2 * 77 * 8 + N_STEPS * 5 * 4 + N_STEPS * 320 * 4,
+                   "d2h_bytes_per_step": B * H * W * 3, "steps": reps,
+                   "note": "pipeline.generate(prompt, uncond_prompt, batch_size=B, seed=...): tokens, DDPM "
+                           "coefficient table and time embeddings copied H2D, device RNG, uint8 images copied D2H"}
+
+        # ---- roofline pass: one eager UNet evaluation + one decode with per-launch CUDA events
+        roof, breakdown = None, None
+        if rank == 0:
+            eng = models["diffusion"]._engine()
+            ops.PROFILER = ops.LaunchProfiler()
+            eng.forward_nhwc(loop.x_in, loop.tvecs[0], loop.kvs)        # warm
+            ops.PROFILER = ops.LaunchProfiler()
+            ta = torch.cuda.Event(enable_timing=True)
+            tb = torch.cuda.Event(enable_timing=True)
+            ta.record()
+            eng.forward_nhwc(loop.x_in, loop.tvecs[0], loop.kvs)
+            tb.record()
+            summ = ops.PROFILER.summary()
+            ops.PROFILER = None
+            unet_eager_ms = ta.elapsed_time(tb)
+            gemm_ms = sum(v["ms"] for k, v in summ.items() if k.startswith("gemm_tc"))
+            gemm_fl = sum(v["flops"] for k, v in summ.items() if k.startswith("gemm_tc"))
+            gemm_n = sum(v["launches"] for k, v in summ.items() if k.startswith("gemm_tc"))
+            achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (implicit-GEMM conv3x3 + linear/1x1)",
+                    "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "launches_per_unet_eval": gemm_n, "flops_per_launch_avg": gemm_fl / max(1, gemm_n),
+                    "us_per_launch_avg": 1e3 * gemm_ms / max(1, gemm_n)}
+            breakdown = {k: {"launches": v["launches"], "ms": round(v["ms"], 3),
+                             "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
+                             "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
+                         for k, v in sorted(summ.items())}
+            breakdown["unet_eval_eager_ms"] = round(unet_eager_ms, 3)
+
+    fault = _ext.read_fault()
+    if fault:
+        raise SystemExit(f"bench.py: device watchdog fault 0x{fault:x}")
+
+    # ---- CPU baseline beside it (rank 0, N = 1): the oracle port on the host cores
+    cpu = None
+    if cpu_weights is not None:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import sd_oracle
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        s = cpu_sample(cpu_weights, torch, sd_oracle, 2)
+        cpu = {"value": cpu_images_per_s(s), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "CLIP x2 + 2 UNet evaluations (CFG pair, 64x64 latent) + 1 VAE decode, fp32 oracle "
+                         "port on the host; images/s = 1 / (clip + 50*unet + decode)",
+               "seconds": {k: round(v, 3) for k, v in s.items()}}
+
+    if rank == 0:
+        unet_ms = loop_ms / N_STEPS
+        alg_tflop_img = (N_STEPS * UNET_GFLOP_PER_IMAGE_STEP + VAE_GFLOP_PER_IMAGE) / 1e3
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: SD1.5-arch random-init txt2img 512x512 (4x64x64 latent), "
+                                   f"batch {B} per GPU, 50 DDPM steps, CFG 7.5, CUDA-graph-captured loop",
+                       "batch_per_gpu": B, "global_batch": B * world, "n_inference_steps": N_STEPS,
+                       "cfg_scale": CFG, "parallelism": f"seed-sharded x{world}, no collective",
+                       "l2": "inputs larger than L2: 1.7 GB of bf16 weights streamed per UNet evaluation"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roof, "cpu_baseline": cpu,
+            "detail": {"unet_step_ms": unet_ms, "loop_ms": loop_ms, "vae_decode_ms": dec_ms, "clip_ms": clip_ms,
+                       "graph_capture_s": t_cap, "model_build_s": t_build,
+                       "launches_per_graph": graph_launches,
+                       "unet_tensor_frac_of_sustained_peak":
+                           B * UNET_GFLOP_PER_IMAGE_STEP / 1e3 / (unet_ms * 1e-3) / peaks["tflops"],
+                       "whole_job_tensor_frac_of_sustained_peak":
+                           value / world * alg_tflop_img / peaks["tflops"],
+                       "kernels": breakdown},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,6 +31,9 @@ extern "C" {
 /* ---- runtime ------------------------------------------------------------------------------ */
 int sdb_abi_version(void);
 const char* sdb_last_error(void);
+/* Number of kernels this library has launched in this process (a launch recorded during CUDA-graph
+ * capture counts once, at capture time). */
+unsigned long long sdb_launch_count(void);
 /* Reads and clears the device watchdog word (non-zero = an mbarrier wait timed out inside a
  * kernel: (site << 8) | kind). Synchronises the device; for tests and smoke runs only. */
 int sdb_read_fault(unsigned int* out_host);
@@ -118,20 +121,20 @@ int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols,
 
 /* ---- layout / elementwise ------------------------------------------------------------------ */
 int sdb_fill_zero(void* ptr, long long bytes, void* stream);
-/* fp32 NCHW [NB, C, H, W] -> bf16 NHWC [NB*repeat, H, W, C], value * scale; `repeat` tiles the
- * batch (latents.repeat(2,1,1,1), sd/pipeline.py:221). */
-int sdb_nchw_f32_to_nhwc_bf16(const float* x, void* out, int NB, int C, int H, int W, int repeat,
-                              float scale, void* stream);
+/* fp32 NCHW [NB, C, H, W] -> NHWC [NB*repeat, H, W, C] in bf16 (fp32 when out_fp32), value * scale;
+ * `repeat` tiles the batch (latents.repeat(2,1,1,1), sd/pipeline.py:221). */
+int sdb_nchw_f32_to_nhwc(const float* x, void* out, int NB, int C, int H, int W, int repeat,
+                         float scale, int out_fp32, void* stream);
 /* NHWC (bf16, or fp32 when in_fp32) -> fp32 NCHW. */
 int sdb_nhwc_to_nchw_f32(const void* x, float* out, int NB, int C, int H, int W, int in_fp32,
                          void* stream);
 /* Nearest-neighbour x2 (F.interpolate sd/diffusion.py:430; nn.Upsample sd/decoder.py:269). */
 int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int W, int C, void* stream);
 /* Direct convolution for tiny channel counts (Cin <= 8 or Cout <= 8): k in {1, 3}, stride 1,
- * pad (k-1)/2. x bf16 NHWC, w fp32 [Cout][k*k][Cin], out bf16 or fp32 NHWC.
- * sd/diffusion.py:545; sd/decoder.py:235,239; sd/encoder.py:56,92. */
-int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, int NB, int H,
-                    int W, int Cin, int Cout, int ksize, int out_fp32, void* stream);
+ * pad (k-1)/2. x bf16 NHWC, w fp32 [Cout][k*k][Cin], out bf16 or fp32 NHWC; out2 = optional bf16
+ * copy next to an fp32 out (or NULL). sd/diffusion.py:545; sd/decoder.py:235,239; sd/encoder.py:56,92. */
+int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2, int NB,
+                    int H, int W, int Cin, int Cout, int ksize, int out_fp32, void* stream);
 /* y[r, n] = act_out( sum_k act_in(x[r, k]) * W[n, k] + bias[n] ), fp32 activations, bf16 weights.
  * The time path: TimeEmbedding (sd/diffusion.py:64-76) and SiLU+linear_time (:184-187). */
 int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R, int K,

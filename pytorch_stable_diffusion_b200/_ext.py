@@ -34,6 +34,7 @@ class AttnArgs(ctypes.Structure):
 SIGNATURES = {
     "sdb_abi_version": [],
     "sdb_last_error": [],
+    "sdb_launch_count": [],
     "sdb_read_fault": [ctypes.POINTER(ctypes.c_uint)],
     "sdb_gemm_tc": [ctypes.POINTER(GemmArgs), c_void_p],
     "sdb_attention": [ctypes.POINTER(AttnArgs), c_void_p],
@@ -44,11 +45,11 @@ SIGNATURES = {
     "sdb_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p],
     "sdb_softmax_rows": [c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p],
     "sdb_fill_zero": [c_void_p, c_ll, c_void_p],
-    "sdb_nchw_f32_to_nhwc_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "sdb_nchw_f32_to_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "sdb_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_upsample2x_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "sdb_conv_direct": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                        c_int, c_void_p],
+    "sdb_conv_direct": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                        c_int, c_int, c_void_p],
     "sdb_small_linear": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_cfg_ddpm_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int,
                           c_int, c_int, c_int, c_int, c_void_p],
@@ -60,7 +61,7 @@ SIGNATURES = {
     "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"sdb_last_error": ctypes.c_char_p}
+_RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong}
 
 _lib = None
 
@@ -92,6 +93,10 @@ def check(rc, what):
         if rc in (-1, -2):
             raise ValueError(f"{what}: {msg} (rc={rc})")
         raise SdbError(f"{what}: {msg} (rc={rc})")
+
+
+def launch_count():
+    return int(lib().sdb_launch_count())
 
 
 def read_fault():

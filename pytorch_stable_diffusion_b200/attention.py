@@ -38,15 +38,15 @@ class SelfAttention(nn.Module, _Packed):
         _require_cuda(x, "SelfAttention")
         pk = self._packed(engine.pack_self_attention)
         b, s, e = x.shape
-        if s % 8 != 0 or self.d_head > 160:
-            raise ValueError("SelfAttention kernel path needs S % 8 == 0 and d_head <= 160; "
-                             "pad the sequence (CLIP) or use the block-level VAE path")
+        if self.d_head > 160:
+            raise ValueError("SelfAttention kernel path needs d_head <= 160; the d=512 VAE attention "
+                             "runs through VAE_AttentionBlock")
         xb = x.to(torch.bfloat16).contiguous().view(b * s, e)
         qk = ops.linear(xb, pk.wqk, bias=pk.bqk)
-        vt = ops.gemm(pk.wv, xb, b * s, M=e, c0=e, bias=pk.bv, bias_per_row=True)
+        vt, vt_ld = engine.project_vt(pk.wv, pk.bv, xb, b, s)
         o = torch.empty_like(xb)
         ops.attention(qk, qk[:, e:], vt, o, NB=b, heads=self.n_heads, d=self.d_head, S=s, Skv=s,
-                      Skv_pad=s, ldq=2 * e, ldk=2 * e, ldo=e, causal=causal_mask)
+                      Skv_pad=s, vt_ld=vt_ld, ldq=2 * e, ldk=2 * e, ldo=e, causal=causal_mask)
         out = ops.linear(o, pk.wo, bias=pk.bo, out_fp32=True)
         return out.view(b, s, e)
 

@@ -45,10 +45,10 @@ class CLIPLayer(nn.Module):
         pk.w2, pk.b2 = engine.pack_linear(self.linear_2, dev)
         n, t, d = x.shape
         t_pad = (t + 7) // 8 * 8
-        xb = torch.zeros((n, t_pad, d), device=dev, dtype=torch.bfloat16)
-        xb[:, :t] = x.to(torch.bfloat16)
-        y = engine.run_clip_layer(pk, xb.view(n * t_pad, d), n, t_pad)
-        return y.view(n, t_pad, d)[:, :t].float()
+        xp = torch.zeros((n, t_pad, d), device=dev, dtype=torch.float32)
+        xp[:, :t] = x
+        y = engine.run_clip_layer(pk, xp.view(n * t_pad, d), n, t_pad)
+        return y.view(n, t_pad, d)[:, :t].contiguous()
 
 
 class CLIP(nn.Module, engine.EngineCache):

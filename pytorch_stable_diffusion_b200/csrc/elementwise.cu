@@ -22,8 +22,9 @@ __global__ void fill_zero_kernel(uint4* p, long long n16, unsigned char* tail, i
   if (i0 < ntail) tail[i0] = 0;
 }
 
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                             int NB, int C, int H, int W, int repeat, float scale) {
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, void* __restrict__ out,
+                                             int NB, int C, int H, int W, int repeat, float scale,
+                                             int out_fp32) {
   const long long hw = (long long)H * W;
   const long long total = (long long)NB * repeat * hw * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -32,7 +33,9 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
     const long long p = (i / C) % hw;
     const int n = (int)(i / (C * hw));
     const int ns = n % NB;
-    out[i] = __float2bfloat16_rn(x[((long long)ns * C + c) * hw + p] * scale);
+    const float v = x[((long long)ns * C + c) * hw + p] * scale;
+    if (out_fp32) reinterpret_cast<float*>(out)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -70,8 +73,9 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 // shared memory transposed to [k*k*Cin][Cout] so a warp reads consecutive words.
 template <int KS>
 __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
-                                   const float* __restrict__ bias, void* __restrict__ out, int NB,
-                                   int H, int W, int Cin, int Cout, int out_fp32) {
+                                   const float* __restrict__ bias, void* __restrict__ out,
+                                   __nv_bfloat16* __restrict__ out2, int NB, int H, int W, int Cin,
+                                   int Cout, int out_fp32) {
   extern __shared__ float s_w[];  // [KS*KS*Cin][CoutPad]
   const int CoutPad = (Cout + 7) & ~7;
   const int K = KS * KS * Cin;
@@ -116,8 +120,12 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const fl
     const long long obase = (((long long)n * H + ho) * W + wo) * Cout + g * 8;
     for (int j = 0; j < 8; ++j) {
       if (g * 8 + j < Cout) {
-        if (out_fp32) reinterpret_cast<float*>(out)[obase + j] = acc[j];
-        else reinterpret_cast<__nv_bfloat16*>(out)[obase + j] = __float2bfloat16_rn(acc[j]);
+        if (out_fp32) {
+          reinterpret_cast<float*>(out)[obase + j] = acc[j];
+          if (out2 != nullptr) out2[obase + j] = __float2bfloat16_rn(acc[j]);
+        } else {
+          reinterpret_cast<__nv_bfloat16*>(out)[obase + j] = __float2bfloat16_rn(acc[j]);
+        }
       }
     }
   }
@@ -315,14 +323,14 @@ extern "C" int sdb_fill_zero(void* ptr, long long bytes, void* stream) {
   return check_launch("fill_zero_kernel");
 }
 
-extern "C" int sdb_nchw_f32_to_nhwc_bf16(const float* x, void* out, int NB, int C, int H, int W,
-                                         int repeat, float scale, void* stream) {
+extern "C" int sdb_nchw_f32_to_nhwc(const float* x, void* out, int NB, int C, int H, int W,
+                                    int repeat, float scale, int out_fp32, void* stream) {
   if (!x || !out || NB <= 0 || C <= 0 || H <= 0 || W <= 0 || repeat <= 0) {
-    set_error("sdb_nchw_f32_to_nhwc_bf16: bad arguments"); return SDB_ERR_ARG;
+    set_error("sdb_nchw_f32_to_nhwc: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * repeat * C * H * W;
   nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
-      x, (__nv_bfloat16*)out, NB, C, H, W, repeat, scale);
+      x, out, NB, C, H, W, repeat, scale, out_fp32);
   return check_launch("nchw_f32_to_nhwc_bf16_kernel");
 }
 
@@ -346,10 +354,11 @@ extern "C" int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int 
   return check_launch("upsample2x_kernel");
 }
 
-extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, int NB,
-                               int H, int W, int Cin, int Cout, int ksize, int out_fp32, void* stream) {
+extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2,
+                               int NB, int H, int W, int Cin, int Cout, int ksize, int out_fp32,
+                               void* stream) {
   if (!x || !w || !out || NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 ||
-      (ksize != 1 && ksize != 3)) {
+      (ksize != 1 && ksize != 3) || (out2 && !out_fp32)) {
     set_error("sdb_conv_direct: bad arguments (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
     return SDB_ERR_ARG;
   }
@@ -366,11 +375,11 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (ksize == 1)
-    conv_direct_kernel<1><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>((const __nv_bfloat16*)x, w, bias, out,
-                                                                       NB, H, W, Cin, Cout, out_fp32);
+    conv_direct_kernel<1><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
+        (const __nv_bfloat16*)x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32);
   else
-    conv_direct_kernel<3><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>((const __nv_bfloat16*)x, w, bias, out,
-                                                                       NB, H, W, Cin, Cout, out_fp32);
+    conv_direct_kernel<3><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
+        (const __nv_bfloat16*)x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32);
   return check_launch("conv_direct_kernel");
 }
 

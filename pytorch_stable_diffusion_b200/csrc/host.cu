@@ -15,7 +15,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -88,6 +91,10 @@ extern "C" {
 const char* sdb_last_error(void) { return sdb::g_err; }
 
 int sdb_abi_version(void) { return SDB_ABI_VERSION; }
+
+// Kernels launched by this library in this process so far (launches recorded into a CUDA graph
+// count once, at capture).
+unsigned long long sdb_launch_count(void) { return sdb::g_launches; }
 
 // Reads and clears the device fault word (mbarrier watchdog). Synchronises the device.
 int sdb_read_fault(unsigned int* out) {

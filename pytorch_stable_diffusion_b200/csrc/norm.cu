@@ -37,17 +37,18 @@ __device__ __forceinline__ void load8(const void* base, long long elem_off, int 
 __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                 double* __restrict__ stats, long long HW, int C0, int C1, int groups,
                                 long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
-  __shared__ float s_sum[64];
-  __shared__ float s_sq[64];
+  // per-thread partial sums, [lanes][ctot] each for sum and sum of squares; reduced per group in a
+  // fixed order so that a block's contribution does not depend on thread scheduling
+  extern __shared__ float s_part[];
   const int n = blockIdx.y;
   const int t = threadIdx.x;
-  for (int i = t; i < groups; i += blockDim.x) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
-  __syncthreads();
   const int v = t % V;
   const int pl = t / V;
   const int V0 = C0 >> 3;
   const int ctot = C0 + C1;
   const int cpg = ctot / groups;
+  float* s_sum = s_part;
+  float* s_sq = s_part + lanes * ctot;
   if (pl < lanes) {
     const bool second = v >= V0;
     const void* src = second ? x1 : x0;
@@ -66,19 +67,22 @@ __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sum[j] += f[j]; sq[j] += f[j] * f[j]; }
     }
-    const int c0 = v * 8;
+    float* ds = s_sum + pl * ctot + v * 8;
+    float* dq = s_sq + pl * ctot + v * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      atomicAdd(&s_sum[g], sum[j]);
-      atomicAdd(&s_sq[g], sq[j]);
-    }
+    for (int j = 0; j < 8; ++j) { ds[j] = sum[j]; dq[j] = sq[j]; }
   }
   __syncthreads();
-  for (int i = t; i < groups; i += blockDim.x) {
-    double* dst = stats + ((long long)n * groups + i) * 2;
-    atomicAdd(dst, (double)s_sum[i]);
-    atomicAdd(dst + 1, (double)s_sq[i]);
+  for (int g = t; g < groups; g += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      const float* ps = s_sum + l * ctot + g * cpg;
+      const float* pq = s_sq + l * ctot + g * cpg;
+      for (int c = 0; c < cpg; ++c) { a += (double)ps[c]; b += (double)pq[c]; }
+    }
+    double* dst = stats + ((long long)n * groups + g) * 2;
+    atomicAdd(dst, a);
+    atomicAdd(dst + 1, b);
   }
 }
 
@@ -273,7 +277,12 @@ extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats
     set_error("sdb_groupnorm_stats: unsupported channel count %d", ctot);
     return SDB_ERR_UNSUPPORTED;
   }
-  gn_stats_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
+  const size_t smem = (size_t)2 * lanes * ctot * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("sdb_groupnorm_stats: %d channels need %zu bytes of shared memory", ctot, smem);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  gn_stats_kernel<<<dim3(chunks, NB), threads, smem, (cudaStream_t)stream>>>(
       x0, x1, stats, HW, C0, C1, groups, ppc, V, lanes, x0_fp32, x1_fp32);
   return check_launch("gn_stats_kernel");
 }

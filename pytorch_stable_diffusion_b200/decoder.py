@@ -19,8 +19,8 @@ class VAE_AttentionBlock(nn.Module, _Packed):
         attention output re-viewed raw as (n, c, h, w) before the residual add)."""
         _require_cuda(x, "VAE_AttentionBlock")
         pk = self._packed(lambda m, dev: engine.pack_self_attention(m.attention, dev))
-        xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
-        return ops.nhwc_to_nchw_f32(engine.run_vae_attn(pk, xn))
+        xn = engine.Stream(ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True))
+        return ops.nhwc_to_nchw_f32(engine.run_vae_attn(pk, xn).f)
 
 
 class VAE_ResidualBlock(nn.Module, _Packed):
@@ -39,8 +39,8 @@ class VAE_ResidualBlock(nn.Module, _Packed):
         """sd/decoder.py:135-189."""
         _require_cuda(x, "VAE_ResidualBlock")
         pk = self._packed(lambda m, dev: engine.pack_resblock(m, dev, time=False))
-        xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
-        return ops.nhwc_to_nchw_f32(engine.run_resblock(pk, xn))
+        xn = engine.Stream(ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True))
+        return ops.nhwc_to_nchw_f32(engine.run_resblock(pk, xn).f)
 
 
 class VAE_Decoder(nn.Sequential, engine.EngineCache):

@@ -45,8 +45,8 @@ class UNET_ResidualBlock(nn.Module, _Packed):
         pk = self._packed(lambda m, dev: engine.pack_resblock(m, dev, time=True))
         tvec = ops.small_linear(time.to(torch.float32).contiguous(), pk.time_w, pk.time_b,
                                 act_in=ops.ACT_SILU).view(-1)
-        x = ops.nchw_to_nhwc_bf16(feature.to(torch.float32))
-        return ops.nhwc_to_nchw_f32(engine.run_resblock(pk, x, None, tvec))
+        x = engine.Stream(ops.nchw_to_nhwc(feature.to(torch.float32), out_fp32=True))
+        return ops.nhwc_to_nchw_f32(engine.run_resblock(pk, x, None, tvec).f)
 
 
 class UNET_AttentionBlock(nn.Module, _Packed):
@@ -72,8 +72,8 @@ class UNET_AttentionBlock(nn.Module, _Packed):
         ctx = torch.zeros((n, engine.CTX_PAD, dc), device=x.device, dtype=torch.bfloat16)
         ctx[:, :t] = context.to(torch.bfloat16)
         kv = engine.context_kv(pk, ctx)
-        xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
-        return ops.nhwc_to_nchw_f32(engine.run_unet_attn(pk, xn, kv))
+        xn = engine.Stream(ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True))
+        return ops.nhwc_to_nchw_f32(engine.run_unet_attn(pk, xn, kv).f)
 
 
 class Upsample(nn.Module, _Packed):
@@ -86,7 +86,7 @@ class Upsample(nn.Module, _Packed):
         _require_cuda(x, "Upsample")
         w, b = self._packed(lambda m, dev: engine.pack_conv3x3(m.conv, dev))
         xn = ops.upsample2x(ops.nchw_to_nhwc_bf16(x.to(torch.float32)))
-        return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, self.conv.out_channels, bias=b))
+        return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, self.conv.out_channels, bias=b, out_fp32=True))
 
 
 class SwitchSequential(nn.Sequential):
@@ -113,10 +113,10 @@ def _conv2d_kernel(conv, x):
     xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
     if conv.in_channels <= 8:
         pk = engine.pack_direct(conv, dev)
-        return ops.nhwc_to_nchw_f32(ops.conv_direct(xn, pk.w, pk.b, pk.cout, pk.k))
+        return ops.nhwc_to_nchw_f32(ops.conv_direct(xn, pk.w, pk.b, pk.cout, pk.k, out_fp32=True))
     w, b = engine.pack_conv3x3(conv, dev)
     kind = ops.GEMM_CONV3X3_S2 if conv.stride[0] == 2 else ops.GEMM_CONV3X3_S1
-    return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, conv.out_channels, bias=b, kind=kind))
+    return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, conv.out_channels, bias=b, kind=kind, out_fp32=True))
 
 
 class UNET(nn.Module):
@@ -181,7 +181,7 @@ class UNET_OutputLayer(nn.Module, _Packed):
         _require_cuda(x, "UNET_OutputLayer")
         gn, (w, b) = self._packed(lambda m, dev: (engine.pack_norm(m.groupnorm, dev),
                                                    engine.pack_conv3x3(m.conv, dev)))
-        xn = ops.groupnorm(ops.nchw_to_nhwc_bf16(x.to(torch.float32)), *gn, silu=True)
+        xn = ops.groupnorm(ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True), *gn, silu=True)
         return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, self.conv.out_channels, bias=b, out_fp32=True))
 
 

@@ -127,20 +127,74 @@ def pack_self_attention(att, dev):
 
 
 # ------------------------------------------------------------------------------------------------
-# block runners (NHWC bf16 in / out)
-def run_resblock(pk, x, x1=None, bias1=None):
-    """conv2(silu(GN(conv1(silu(GN(x ++ x1))) + t))) + skip(x ++ x1).  bias1 = conv1 bias (+ time)."""
+# residual stream
+class Stream:
+    """A residual-stream activation: fp32 NHWC master `f` plus an optional bf16 shadow `b`.
+
+    Everything that is added to again later (block inputs/outputs, the token stream inside an
+    attention block, UNet skips) stays fp32 so that rounding does not accumulate along the ~60
+    residual additions of a UNet evaluation; the bf16 shadow exists only where a tensor-core kernel
+    reads the stream directly as its A operand (skip 1x1 convs, down/up-sampling convs, conv_output,
+    the VAE attention projections). Branch tensors (GroupNorm/LayerNorm outputs, conv hidden, Q/K/V,
+    attention outputs) are bf16."""
+    __slots__ = ("f", "b")
+
+    def __init__(self, f, b=None):
+        self.f, self.b = f, b
+
+    @property
+    def shape(self):
+        return self.f.shape
+
+    def bf16(self):
+        if self.b is None:
+            self.b = ops.f32_to_bf16(self.f)
+        return self.b
+
+
+def _stream(out, shape):
+    """(fp32, bf16) pair or a lone fp32 tensor from a kernel wrapper -> Stream viewed as `shape`."""
+    if isinstance(out, tuple):
+        return Stream(out[0].view(shape), out[1].view(shape))
+    return Stream(out.view(shape))
+
+
+# ------------------------------------------------------------------------------------------------
+# block runners (Stream in / Stream out)
+def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
+    """conv2(silu(GN(conv1(silu(GN(x ++ x1))) + t))) + skip(x ++ x1).  bias1 = conv1 bias (+ time).
+    UNET_ResidualBlock (sd/diffusion.py:145-209) / VAE_ResidualBlock (sd/decoder.py:135-189)."""
     n, h, w, c0 = x.shape
     c1 = x1.shape[-1] if x1 is not None else 0
-    a = ops.groupnorm(x, pk.gn1_w, pk.gn1_b, x1=x1, silu=True)
+    a = ops.groupnorm(x.f, pk.gn1_w, pk.gn1_b, x1=x1.f if x1 is not None else None, silu=True)
     hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b)
     a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True)
     if pk.skip_w is None:
-        res = x.view(-1, c0)
+        res = x.f.view(-1, c0)
     else:
-        res = ops.gemm(x.view(-1, c0), pk.skip_w, pk.cout, a1=x1.view(-1, c1) if x1 is not None else None,
-                       M=n * h * w, c0=c0, c1=c1, bias=pk.skip_b)
-    return ops.conv3x3(a2, pk.conv2_w, pk.cout, bias=pk.conv2_b, residual=res)
+        res = ops.gemm(x.bf16().view(-1, c0), pk.skip_w, pk.cout,
+                       a1=x1.bf16().view(-1, c1) if x1 is not None else None,
+                       M=n * h * w, c0=c0, c1=c1, bias=pk.skip_b, out_fp32=True)
+    out = ops.conv3x3(a2, pk.conv2_w, pk.cout, bias=pk.conv2_b, residual=res, out_fp32=True,
+                      out2=True if want_b16 else None)
+    if isinstance(out, tuple):
+        return Stream(out[0], out[1])
+    return Stream(out)
+
+
+def project_vt(w, bias, x, n, s):
+    """V^T = Wv . X^T + bv for the attention kernel: [C, n, s_pad] bf16 with the per-sample key stride
+    padded to a multiple of 8 elements (TMA needs 16-byte strides). Returns (vt, s_pad). The common
+    case (s % 8 == 0) is one swapped-operand GEMM over all n*s tokens."""
+    c = w.shape[0]
+    if s % 8 == 0:
+        return ops.gemm(w, x, n * s, M=c, c0=x.shape[1], bias=bias, bias_per_row=True), s
+    s_pad = (s + 7) // 8 * 8
+    vt = ops.zeros((c, n, s_pad), torch.bfloat16, x.device)
+    for i in range(n):
+        ops.gemm(w, x[i * s:(i + 1) * s], s, M=c, c0=x.shape[1], bias=bias, bias_per_row=True,
+                 out=vt[:, i], ldo=n * s_pad)
+    return vt, s_pad
 
 
 def context_kv(pk, ctx_pad):
@@ -153,50 +207,51 @@ def context_kv(pk, ctx_pad):
     return k, vt
 
 
-def run_unet_attn(pk, x, kv):
-    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381) on NHWC bf16."""
+def run_unet_attn(pk, x, kv, want_b16=False):
+    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is fp32."""
     n, h, w, c = x.shape
     s = h * w
     m = n * s
     d = c // pk.heads
-    xf = x.view(m, c)
-    a = ops.groupnorm(x, pk.gn_w, pk.gn_b, eps=1e-6, silu=False)
-    t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b)
+    dev = x.f.device
+    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False)
+    t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=True)
     # self-attention
     l1 = ops.layernorm(t0, *pk.ln1)
     qk = ops.linear(l1, pk.wqk, bias=pk.bqk)
-    vt = ops.gemm(pk.wv, l1, m, M=c, c0=c, bias=pk.bv, bias_per_row=True)
-    o = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
-    ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s,
+    vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
+    o = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
+    ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
                   ldq=2 * c, ldk=2 * c, ldo=c)
-    t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0)
+    t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
     # cross-attention over the CLIP tokens
     l2 = ops.layernorm(t1, *pk.ln2)
     q = ops.linear(l2, pk.wq2, bias=pk.bq2)
     k2, vt2 = kv
-    o2 = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
+    o2 = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
     ops.attention(q, k2, vt2, o2, NB=n, heads=pk.heads, d=d, S=s, Skv=77, Skv_pad=CTX_PAD,
                   ldq=c, ldk=c, ldo=c)
-    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1)
+    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True)
     # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
     l3 = ops.layernorm(t2, *pk.ln3)
     g = ops.linear(l3, pk.wg1, bias=pk.bg1)
-    t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)
-    out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=xf)
-    return out.view(n, h, w, c)
+    t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)          # only conv_output reads it: bf16
+    out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=x.f.view(m, c), out_fp32=True,
+                     out2=True if want_b16 else None)
+    return _stream(out, (n, h, w, c))
 
 
-def run_vae_attn(pk, x):
+def run_vae_attn(pk, x, want_b16=False):
     """VAE_AttentionBlock.forward (sd/decoder.py:34-73): single-head d=C attention over h*w tokens,
     no GroupNorm, output re-viewed raw as (n, c, h, w) before the residual add. d = 512 does not fit
     one TMEM accumulator, so this runs as GEMM -> row softmax -> GEMM per sample."""
     n, h, w, c = x.shape
     s = h * w
     m = n * s
-    xf = x.view(m, c)
+    xf = x.bf16().view(m, c)
     qk = ops.linear(xf, pk.wqk, bias=pk.bqk)                                   # [m, 2c]
     vt = ops.gemm(pk.wv, xf, m, M=c, c0=c, bias=pk.bv, bias_per_row=True)      # [c, m]
-    o = torch.empty((m, c), device=x.device, dtype=torch.bfloat16)
+    o = torch.empty((m, c), device=xf.device, dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(c // pk.heads)
     for i in range(n):
         q_i = qk[i * s:(i + 1) * s, :c]
@@ -205,23 +260,31 @@ def run_vae_attn(pk, x):
         probs = ops.softmax_rows(scores, scale)
         ops.gemm(probs, vt[:, i * s:(i + 1) * s], c, M=s, c0=s, ldw=m, out=o[i * s:(i + 1) * s], nsplit=1)
     y = ops.linear(o, pk.wo, bias=pk.bo)
-    return ops.vae_attn_scramble_add(y.view(n, s, c), x.view(n, s, c)).view(n, h, w, c)
+    f, b = ops.vae_attn_scramble_add(y.view(n, s, c), x.f.view(n, s, c))
+    return Stream(f.view(n, h, w, c), b.view(n, h, w, c))
 
 
 def run_clip_layer(pk, x, n, t_pad):
-    """CLIPLayer.forward (sd/clip.py:123-176) on [n*t_pad, 768] bf16 rows (rows >= 77 are padding)."""
+    """CLIPLayer.forward (sd/clip.py:123-176) on fp32 [n*t_pad, 768] rows (rows >= 77 are padding)."""
     c = pk.att.c
     d = c // pk.att.heads
     l1 = ops.layernorm(x, *pk.ln1)
     qk = ops.linear(l1, pk.att.wqk, bias=pk.att.bqk)
     vt = ops.gemm(pk.att.wv, l1, n * t_pad, M=c, c0=c, bias=pk.att.bv, bias_per_row=True)
-    o = torch.empty_like(x)
+    o = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.att.heads, d=d, S=t_pad, Skv=77, Skv_pad=t_pad,
                   ldq=2 * c, ldk=2 * c, ldo=c, causal=True)
-    x = ops.linear(o, pk.att.wo, bias=pk.att.bo, residual=x)
+    x = ops.linear(o, pk.att.wo, bias=pk.att.bo, residual=x, out_fp32=True)
     l2 = ops.layernorm(x, *pk.ln2)
     hdn = ops.linear(l2, pk.w1, bias=pk.b1, act=ops.ACT_QUICK_GELU)
-    return ops.linear(hdn, pk.w2, bias=pk.b2, residual=x)
+    return ops.linear(hdn, pk.w2, bias=pk.b2, residual=x, out_fp32=True)
+
+
+def _reads_bf16(kind, pk):
+    """Does program entry (kind, pk) read its stream input as a bf16 tensor-core operand?"""
+    if kind == "res":
+        return pk.skip_w is not None
+    return kind in ("up", "conv", "conv1", "attn_vae", "direct")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -243,19 +306,19 @@ class UNetEngine:
                 if isinstance(layer, UNET_ResidualBlock):
                     pk = pack_resblock(layer, dev, time=True)
                     self.res_blocks.append(pk)
-                    prog.append(("res", pk))
+                    prog.append(["res", pk, False])
                 elif isinstance(layer, UNET_AttentionBlock):
-                    prog.append(("attn", pack_unet_attn(layer, dev)))
+                    prog.append(["attn", pack_unet_attn(layer, dev), False])
                 elif isinstance(layer, Upsample):
                     w, b = pack_conv3x3(layer.conv, dev)
-                    prog.append(("up", NS(w=w, b=b, cout=layer.conv.out_channels)))
+                    prog.append(["up", NS(w=w, b=b, cout=layer.conv.out_channels), False])
                 elif isinstance(layer, torch.nn.Conv2d):
                     if layer.in_channels <= 8:
-                        prog.append(("direct", pack_direct(layer, dev)))
+                        prog.append(["direct", pack_direct(layer, dev), False])
                     else:
                         w, b = pack_conv3x3(layer, dev)
                         kind = ops.GEMM_CONV3X3_S2 if layer.stride[0] == 2 else ops.GEMM_CONV3X3_S1
-                        prog.append(("conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind)))
+                        prog.append(["conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind), False])
                 else:
                     raise TypeError(f"unexpected layer {type(layer)}")
             return prog
@@ -264,8 +327,13 @@ class UNetEngine:
         self.encoders = [pack_seq(s) for s in u.encoders]
         self.bottleneck = pack_seq(u.bottleneck)
         self.decoders = [pack_seq(s) for s in u.decoders]
-        self.attn_blocks = [pk for prog in self.encoders + [self.bottleneck] + self.decoders
-                            for kind, pk in prog if kind == "attn"]
+        # third field of every entry: does a later tensor-core kernel read this output directly?
+        flat = [e for prog in self.encoders + [self.bottleneck] + self.decoders for e in prog]
+        for cur, nxt in zip(flat, flat[1:]):
+            cur[2] = _reads_bf16(nxt[0], nxt[1])
+        for prog in self.encoders:        # skips feed the decoders' 1x1 skip convs (sd/diffusion.py:671)
+            prog[-1][2] = True
+        self.attn_blocks = [pk for kind, pk, _ in flat if kind == "attn"]
         # all linear_time projections as one [sum(Cout), 1280] matrix
         offs, off = [], 0
         for pk in self.res_blocks:
@@ -297,18 +365,23 @@ class UNetEngine:
         return [context_kv(pk, ctx) for pk in self.attn_blocks]
 
     def _run_seq(self, prog, x, x1, tvec, kv_iter):
-        for kind, pk in prog:
+        for kind, pk, want in prog:
             if kind == "res":
-                x = run_resblock(pk, x, x1, tvec[pk.time_off:pk.time_off + pk.cout])
+                x = run_resblock(pk, x, x1, tvec[pk.time_off:pk.time_off + pk.cout], want_b16=want)
                 x1 = None
             elif kind == "attn":
-                x = run_unet_attn(pk, x, next(kv_iter))
+                x = run_unet_attn(pk, x, next(kv_iter), want_b16=want)
             elif kind == "up":
-                x = ops.conv3x3(ops.upsample2x(x), pk.w, pk.cout, bias=pk.b)
+                o = ops.conv3x3(ops.upsample2x(x.bf16()), pk.w, pk.cout, bias=pk.b, out_fp32=True,
+                                out2=True if want else None)
+                x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "conv":
-                x = ops.conv3x3(x, pk.w, pk.cout, bias=pk.b, kind=pk.kind)
+                o = ops.conv3x3(x.bf16(), pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True,
+                                out2=True if want else None)
+                x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "direct":
-                x = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k)
+                o = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=want)
+                x = Stream(*o) if isinstance(o, tuple) else Stream(o)
         return x
 
     def forward_nhwc(self, x, tvec, kvs):
@@ -322,7 +395,7 @@ class UNetEngine:
         x = self._run_seq(self.bottleneck, x, None, tvec, kv_iter)
         for prog in self.decoders:
             x = self._run_seq(prog, x, skips.pop(), tvec, kv_iter)
-        a = ops.groupnorm(x, *self.fin_gn, silu=True)
+        a = ops.groupnorm(x.f, *self.fin_gn, silu=True)
         return ops.conv3x3(a, self.fin_w, self.fin_cout, bias=self.fin_b, out_fp32=True)
 
 
@@ -331,27 +404,27 @@ def _pack_vae_sequential(seq, dev, pad_rb):
     prog = []
     for layer in seq:
         if isinstance(layer, VAE_ResidualBlock):
-            prog.append(("res", pack_resblock(layer, dev, time=False)))
+            prog.append(["res", pack_resblock(layer, dev, time=False), False])
         elif isinstance(layer, VAE_AttentionBlock):
-            prog.append(("attn", pack_self_attention(layer.attention, dev)))
+            prog.append(["attn_vae", pack_self_attention(layer.attention, dev), False])
         elif isinstance(layer, torch.nn.Conv2d):
             if layer.in_channels <= 8:
-                prog.append(("direct", pack_direct(layer, dev)))
+                prog.append(["direct", pack_direct(layer, dev), False])
             elif layer.kernel_size[0] == 1:
                 w, b = pack_conv1x1(layer, dev)
-                prog.append(("conv1", NS(w=w, b=b, cout=layer.out_channels)))
+                prog.append(["conv1", NS(w=w, b=b, cout=layer.out_channels), False])
             else:
                 w, b = pack_conv3x3(layer, dev)
                 kind = ops.GEMM_CONV3X3_S1
                 if layer.stride[0] == 2:
                     kind = ops.GEMM_CONV3X3_S2_PAD_RB if pad_rb else ops.GEMM_CONV3X3_S2
-                prog.append(("conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind)))
+                prog.append(["conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind), False])
         elif isinstance(layer, torch.nn.Upsample):
-            prog.append(("up", None))
+            prog.append(["up", None, False])
         elif isinstance(layer, torch.nn.GroupNorm):
-            prog.append(("gn", pack_norm(layer, dev)))
+            prog.append(["gn", pack_norm(layer, dev), False])
         elif isinstance(layer, torch.nn.SiLU):
-            prog.append(("silu", None))
+            prog.append(["silu", None, False])
         else:
             raise TypeError(f"unexpected layer {type(layer)}")
     # GroupNorm followed by SiLU is one kernel
@@ -359,38 +432,45 @@ def _pack_vae_sequential(seq, dev, pad_rb):
     i = 0
     while i < len(prog):
         if prog[i][0] == "gn" and i + 1 < len(prog) and prog[i + 1][0] == "silu":
-            fused.append(("gn_silu", prog[i][1]))
+            fused.append(["gn_silu", prog[i][1], False])
             i += 2
         else:
             fused.append(prog[i])
             i += 1
+    for cur, nxt in zip(fused, fused[1:]):
+        cur[2] = _reads_bf16(nxt[0], nxt[1])
     return fused
 
 
-def _run_vae_sequential(prog, x, last_fp32):
-    for idx, (kind, pk) in enumerate(prog):
-        last = idx == len(prog) - 1
-        fp32 = last and last_fp32
+def _run_vae_sequential(prog, x):
+    """x: bf16 NHWC tensor (network input). Returns the last entry's fp32 NHWC output."""
+    for kind, pk, want in prog:
+        o2 = True if want else None
         if kind == "res":
-            x = run_resblock(pk, x)
-        elif kind == "attn":
+            x = run_resblock(pk, x, want_b16=want)
+        elif kind == "attn_vae":
             x = run_vae_attn(pk, x)
         elif kind == "direct":
-            x = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=fp32)
+            src = x.bf16() if isinstance(x, Stream) else x
+            o = ops.conv_direct(src, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=True)
+            x = Stream(*o)
         elif kind == "conv1":
             n, h, w, c = x.shape
-            x = ops.linear(x.view(-1, c), pk.w, bias=pk.b, out_fp32=fp32).view(n, h, w, pk.cout)
+            o = ops.linear(x.bf16().view(-1, c), pk.w, bias=pk.b, out_fp32=True, out2=o2)
+            x = _stream(o, (n, h, w, pk.cout))
         elif kind == "conv":
-            x = ops.conv3x3(x, pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=fp32)
+            src = x.bf16() if isinstance(x, Stream) else x
+            o = ops.conv3x3(src, pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True, out2=o2)
+            x = Stream(*o) if isinstance(o, tuple) else Stream(o)
         elif kind == "up":
-            x = ops.upsample2x(x)
+            x = ops.upsample2x(x.bf16())        # bf16 tensor: the next entry is a conv reading it
         elif kind == "gn_silu":
-            x = ops.groupnorm(x, *pk, silu=True)
+            x = ops.groupnorm(x.f, *pk, silu=True)
         elif kind == "gn":
-            x = ops.groupnorm(x, *pk, silu=False)
+            x = ops.groupnorm(x.f, *pk, silu=False)
         else:
             raise RuntimeError(f"VAE program entry {kind} has no kernel")
-    return x
+    return x.f if isinstance(x, Stream) else x
 
 
 class VAEDecoderEngine:
@@ -403,7 +483,7 @@ class VAEDecoderEngine:
     def forward_nhwc(self, latents):
         """latents fp32 NCHW [B, 4, h, w] -> image fp32 NHWC [B, 8h, 8w, 3] (x / 0.18215 first)."""
         x = ops.nchw_to_nhwc_bf16(latents, scale=1.0 / 0.18215)
-        return _run_vae_sequential(self.prog, x, last_fp32=True)
+        return _run_vae_sequential(self.prog, x)
 
 
 class VAEEncoderEngine:
@@ -415,7 +495,7 @@ class VAEEncoderEngine:
 
     def forward_from_nhwc(self, x, noise):
         """x bf16 NHWC [B, H, W, 3]; noise fp32 NCHW [B, 4, H/8, W/8] -> latents fp32 NCHW."""
-        moments = _run_vae_sequential(self.prog, x, last_fp32=True)
+        moments = _run_vae_sequential(self.prog, x)
         return ops.vae_encode_tail(moments, noise)
 
 

@@ -20,6 +20,44 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class LaunchProfiler:
+    """Brackets every C-ABI kernel call with CUDA events on the launching stream and records its
+    algorithmic work (bench.py's roofline pass; eager execution only, never under graph capture)."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self, name, flops=0.0, nbytes=0.0):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.records.append([name, float(flops), float(nbytes), e0, e1])
+        return e1
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILER = None
+
+
+def _prof(name, flops=0.0, nbytes=0.0):
+    return PROFILER.begin(name, flops, nbytes) if PROFILER is not None else None
+
+
+def _prof_end(ev):
+    if ev is not None:
+        ev.record()
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -110,7 +148,10 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         ws = torch.empty((nsplit, rows, cout), device=a0.device, dtype=torch.float32)
         args.workspace = _p(ws)
     args.nsplit = nsplit
+    ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
+               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size())
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
+    _prof_end(ev)
     return (out, out2) if out2 is not None else out
 
 
@@ -141,7 +182,10 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
     a.ldq, a.ldk, a.ldo = ldq, ldk, ldo
     a.causal = 1 if causal else 0
     a.scale = 1.0 / math.sqrt(d)
+    ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
+               2.0 * NB * heads * d * (2 * S + 2 * Skv))
     _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")
+    _prof_end(ev)
     return out
 
 
@@ -156,6 +200,9 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
     hw = x0.numel() // (n * c0)
     c1 = x1.shape[-1] if x1 is not None else 0
     stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float64)
+    nel0, nel1 = n * hw * c0, n * hw * c1
+    in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
+    ev = _prof("groupnorm", 0.0, 2.0 * in_bytes + 2.0 * (nel0 + nel1))
     _ext.check(lib.sdb_fill_zero(_p(stats), stats.numel() * 8, _stream()), "sdb_fill_zero")
     _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
                "sdb_groupnorm_stats")
@@ -163,6 +210,7 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
     _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
                                        c0, c1, groups, float(eps), 1 if silu else 0, f0, f1, _stream()),
                "sdb_groupnorm_apply")
+    _prof_end(ev)
     return out
 
 
@@ -171,9 +219,11 @@ def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False):
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    ev = _prof("layernorm", 0.0, x.numel() * x.element_size() + out.numel() * out.element_size())
     _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
                                  1 if x.dtype == torch.float32 else 0, 1 if out_fp32 else 0, _stream()),
                "sdb_layernorm")
+    _prof_end(ev)
     return out
 
 
@@ -187,15 +237,20 @@ def softmax_rows(scores, scale):
     return out
 
 
-def nchw_to_nhwc_bf16(x, repeat=1, scale=1.0):
+def nchw_to_nhwc(x, repeat=1, scale=1.0, out_fp32=False):
     lib = _ext.lib()
     _chk(x, torch.float32, "x")
     x = x.contiguous()
     n, c, h, w = x.shape
-    out = torch.empty((n * repeat, h, w, c), device=x.device, dtype=torch.bfloat16)
-    _ext.check(lib.sdb_nchw_f32_to_nhwc_bf16(_p(x), _p(out), n, c, h, w, repeat, float(scale), _stream()),
-               "sdb_nchw_f32_to_nhwc_bf16")
+    out = torch.empty((n * repeat, h, w, c), device=x.device,
+                      dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _ext.check(lib.sdb_nchw_f32_to_nhwc(_p(x), _p(out), n, c, h, w, repeat, float(scale),
+                                        1 if out_fp32 else 0, _stream()), "sdb_nchw_f32_to_nhwc")
     return out
+
+
+def nchw_to_nhwc_bf16(x, repeat=1, scale=1.0):
+    return nchw_to_nhwc(x, repeat, scale, False)
 
 
 def nhwc_to_nchw_f32(x):
@@ -215,15 +270,17 @@ def upsample2x(x):
     return out
 
 
-def conv_direct(x, w, bias, cout, ksize, out_fp32=False):
-    """x bf16 NHWC with Cin <= 8; w fp32 [Cout, k*k, Cin]."""
+def conv_direct(x, w, bias, cout, ksize, out_fp32=False, out2=False):
+    """x bf16 NHWC with Cin <= 8; w fp32 [Cout, k*k, Cin]. out2=True also returns a bf16 copy of an
+    fp32 output."""
     lib = _ext.lib()
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device,
                       dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    _ext.check(lib.sdb_conv_direct(_p(x), _p(w), _p(bias), _p(out), n, h, wd, cin, cout, ksize,
+    o2 = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bfloat16) if out2 else None
+    _ext.check(lib.sdb_conv_direct(_p(x), _p(w), _p(bias), _p(out), _p(o2), n, h, wd, cin, cout, ksize,
                                    1 if out_fp32 else 0, _stream()), "sdb_conv_direct")
-    return out
+    return (out, o2) if out2 else out
 
 
 def small_linear(x, w, bias, act_in=ACT_NONE, act_out=ACT_NONE):
@@ -258,6 +315,13 @@ def vae_attn_scramble_add(y, res):
     _ext.check(lib.sdb_vae_attn_scramble_add(_p(y), _p(res), _p(out), _p(out2), n, hw, c, _stream()),
                "sdb_vae_attn_scramble_add")
     return out, out2
+
+
+def zeros(shape, dtype, device):
+    lib = _ext.lib()
+    out = torch.empty(shape, device=device, dtype=dtype)
+    _ext.check(lib.sdb_fill_zero(_p(out), out.numel() * out.element_size(), _stream()), "sdb_fill_zero")
+    return out
 
 
 def f32_to_bf16(x):

@@ -10,7 +10,7 @@ return_all, use_cuda_graph, trace.
 import numpy as np
 import torch
 
-from . import ops
+from . import _ext, ops
 from .ddpm import DDPMSampler
 
 WIDTH = 512
@@ -74,6 +74,7 @@ class _Loop:
         self.tvecs = torch.zeros((n_steps, eng.time_total), device=device, dtype=torch.float32)
         self.kvs = None
         self.graph = None
+        self.graph_launches = 0
 
     def set_inputs(self, latents, noise, coef, tvecs, kvs):
         self.latents.copy_(latents)
@@ -101,8 +102,10 @@ class _Loop:
         self.eng.forward_nhwc(self.x_in, self.tvecs[0], self.kvs)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = _ext.launch_count()
         with torch.cuda.graph(g):
             self.run_steps()
+        self.graph_launches = _ext.launch_count() - n0     # kernels replayed by every graph launch
         self.graph = g
 
     def replay(self):
