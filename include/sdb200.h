@@ -71,12 +71,17 @@ typedef struct sdb_gemm_args {
   int block_n;            /* 0 = choose; else multiple of 16 in [16, 256]                        */
   int nsplit;             /* split-K factor, 0/1 = none                                          */
   int smem_budget;        /* bytes of shared memory for the pipeline, 0 = choose                 */
+  int cta_pair;           /* 0 = choose; 1 = one CTA per tile (128 rows); 2 = CTA pairs (256 rows) */
 } sdb_gemm_args;
 
 /* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,
  * 545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112,121,129,235-339;
  * sd/encoder.py:56-92; sd/clip.py:117,121. */
 int sdb_gemm_tc(const sdb_gemm_args* args, void* stream);
+
+/* Debug aid: on >= 0 switches a per-tile SM-clock timeline of CTA 0 on (1) / off (0) and clears it;
+ * on < 0 copies the 64 x 8 stamps to out_host (see csrc/gemm_tc.cu). Synchronises. */
+int sdb_debug_gemm_trace(int on, long long* out_host);
 
 /* ---- attention ----------------------------------------------------------------------------- */
 typedef struct sdb_attn_args {

@@ -18,7 +18,7 @@ class GemmArgs(ctypes.Structure):
         ("NB", c_int), ("HI", c_int), ("WI", c_int), ("C0", c_int), ("C1", c_int), ("Cout", c_int),
         ("lda0", c_ll), ("lda1", c_ll), ("ldw", c_ll), ("ldo", c_ll), ("ldr", c_ll),
         ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
-        ("nsplit", c_int), ("smem_budget", c_int),
+        ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int),
     ]
 
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "sdb_launch_count": [],
     "sdb_read_fault": [ctypes.POINTER(ctypes.c_uint)],
     "sdb_gemm_tc": [ctypes.POINTER(GemmArgs), c_void_p],
+    "sdb_debug_gemm_trace": [c_int, ctypes.POINTER(ctypes.c_longlong)],
     "sdb_attention": [ctypes.POINTER(AttnArgs), c_void_p],
     "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
                             c_void_p],

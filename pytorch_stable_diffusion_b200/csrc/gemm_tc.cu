@@ -24,9 +24,11 @@ namespace sdb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_WARPS = 8;                          // two per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KiB
+constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;          // one 32x32 fp32 chunk per epilogue warp
 
 struct GemmTcParams {
   CUtensorMap map_a0;
@@ -35,7 +37,9 @@ struct GemmTcParams {
   // output-pixel space and tiling
   int NB, HO, WO;          // output rows are (n, h, w), row index m = (n*HO + h)*WO + w
   int bw, bh, bn;          // tile box in (w, h, n); bw*bh*bn <= 128
-  int tiles_w, tiles_h;    // tiles along w and h (tiles along n = gridDim.x / (tiles_w*tiles_h))
+  int tiles_w, tiles_h;    // tiles along w and h
+  int m_tiles, n_tiles;    // tiles along the row space / the output channels
+  int total_tiles;         // m_tiles * n_tiles * nsplit
   int a_rank;              // 2: plain [M, K] matrix; 5: NHWC conv addressing
   // reduction
   int C0, C1;              // channels from source 0 / source 1 (multiples of 64 when C1 > 0)
@@ -50,10 +54,12 @@ struct GemmTcParams {
   // epilogue
   int N;                   // valid output columns (Cout)
   int block_n;             // UMMA N (multiple of 16, <= 256)
-  int tmem_cols;           // power of two >= max(32, round_up(block_n, 32))
+  int acc_stride;          // TMEM columns between the two accumulators (power of two >= block_n)
+  int tmem_cols;           // 2 * acc_stride
   int stages;
-  int a_tx_bytes;           // bytes one A box delivers (bw*bh*bn rows of 128 B)
-  int nsplit;              // split-K factor (gridDim.z)
+  int a_tx_bytes;          // bytes one A box delivers (bw*bh*bn rows of 128 B)
+  int nsplit;              // split-K factor
+  int per_split;           // k-blocks per split
   void* out;
   long long ldo;
   int out_fp32;
@@ -74,6 +80,92 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+struct TileCoord {
+  int n0, w0, h0, nb0, z, kb_begin, nkb;
+};
+
+// Debug timeline (sdb_debug_gemm_trace): CTA 0 records SM-clock stamps per tile, 8 slots each:
+// 0 producer tile start, 1 producer all loads issued, 2 issuer before accumulator wait, 3 issuer first
+// operands landed, 4 issuer last MMA committed, 5 epilogue waiting, 6 accumulator ready, 7 tile stored.
+constexpr int GEMM_TRACE_TILES = 64;
+__device__ long long g_gemm_trace[GEMM_TRACE_TILES * 8];
+__device__ int g_gemm_trace_on = 0;
+__device__ __forceinline__ void trace_stamp(int tile_local, int slot) {
+  if (g_gemm_trace_on && blockIdx.x == 0 && tile_local < GEMM_TRACE_TILES)
+    g_gemm_trace[tile_local * 8 + slot] = clock64();
+}
+
+// Tile order: output-channel tile fastest, so CTAs that run at the same time share the activation
+// tile through L2 and the (smaller) weight matrix stays L2-resident. In pair mode (CG = 2) a "tile"
+// is two consecutive row tiles; CTA rank r of the pair owns row tile 2*t + r.
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile, int cta_rank) {
+  TileCoord t;
+  const int n_tile = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  int mt = (r % p.m_tiles) * CG + cta_rank;
+  t.z = r / p.m_tiles;
+  const int tw_i = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th_i = mt % p.tiles_h;
+  const int tn_i = mt / p.tiles_h;
+  t.w0 = tw_i * p.bw;
+  t.h0 = th_i * p.bh;
+  t.nb0 = tn_i * p.bn;
+  t.n0 = n_tile * p.block_n;
+  const int nkb_total = p.ntaps * p.cblocks;
+  t.kb_begin = t.z * p.per_split;
+  t.nkb = min(nkb_total, t.kb_begin + p.per_split) - t.kb_begin;
+  return t;
+}
+
+// Residual values of the 4 columns x 8 rows one lane owns in a 32-column chunk (zeros where absent).
+__device__ __forceinline__ void load_residual(const GemmTcParams& p, const long long (&mrow)[8], int col0,
+                                              int cl, int ncol, float4 (&r)[8]) {
+  const bool vec_ok = (cl + 4 <= ncol);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long m = mrow[i];
+    if (m < 0 || cl >= ncol) continue;
+    const long long roff = m * p.ldr + col0 + cl;
+    if (p.res_fp32) {
+      const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
+      if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r[i].x), "=f"(r[i].y), "=f"(r[i].z), "=f"(r[i].w)
+                     : "l"(rp));
+      } else {
+        r[i].x = rp[0];
+        if (cl + 1 < ncol) r[i].y = rp[1];
+        if (cl + 2 < ncol) r[i].z = rp[2];
+        if (cl + 3 < ncol) r[i].w = rp[3];
+      }
+    } else {
+      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+      if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 7u) == 0)) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp));
+        r[i] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
+      } else {
+        r[i].x = __bfloat162float(rp[0]);
+        if (cl + 1 < ncol) r[i].y = __bfloat162float(rp[1]);
+        if (cl + 2 < ncol) r[i].z = __bfloat162float(rp[2]);
+        if (cl + 3 < ncol) r[i].w = __bfloat162float(rp[3]);
+      }
+    }
+  }
+}
+
+// Persistent, warp-specialised kernel. CG = 1: one CTA per SM computes 128 x block_n tiles.
+// CG = 2: a cluster of two CTAs (one SM pair) computes 256 x block_n tiles with cta_group::2 MMAs -
+// each CTA stages its own 128 rows of A and HALF of the W tile, so a pipeline stage holds fewer bytes
+// per FLOP and the ring gets deeper for the same shared memory.
+//   warp 0      TMA producer (A boxes + W tiles into a `stages`-deep ring)
+//   warp 1      tcgen05.mma issuer (leader CTA only); two TMEM accumulators, so tile i+1 accumulates
+//               while tile i drains
+//   warps 2-9   epilogue: tcgen05.ld -> swizzled shared staging -> row-coalesced global I/O, with the
+//               residual of the next chunk prefetched into registers
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -81,29 +173,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b_stage_bytes = p.block_n * GEMM_BK * 2;
+  const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+  const bool leader = (cta_rank == 0);
+  const int first_tile = blockIdx.x / CG;
+  const int tile_step = gridDim.x / CG;
+  const int b_rows = p.block_n / CG;                     // W rows this CTA stages per k-block
+  const int b_stage_bytes = b_rows * GEMM_BK * 2;
   const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint8_t* epi_smem = smem + p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
-  uint64_t* accum_bar = empty_bar + GEMM_MAX_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  // ---- tile coordinates
-  const int n_tile = blockIdx.y;
-  int mt = blockIdx.x;
-  const int tw_i = mt % p.tiles_w;
-  mt /= p.tiles_w;
-  const int th_i = mt % p.tiles_h;
-  const int tn_i = mt / p.tiles_h;
-  const int w0 = tw_i * p.bw, h0 = th_i * p.bh, nb0 = tn_i * p.bn;
-  const int n0 = n_tile * p.block_n;
-
-  // ---- this CTA's slice of the reduction
-  const int nkb_total = p.ntaps * p.cblocks;
-  const int per_split = (nkb_total + p.nsplit - 1) / p.nsplit;
-  const int kb_begin = blockIdx.z * per_split;
-  const int kb_end = min(nkb_total, kb_begin + per_split);
-  const int nkb = max(0, kb_end - kb_begin);
+  uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;                // [2] accumulator drained (leader's copy is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a0);
@@ -113,192 +195,289 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CG);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+  if constexpr (CG == 2) {
+    cluster_sync_all();          // the peer's barriers exist before anything remote can reach them
+    if (warp == 1) {
+      tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+      tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+  } else {
+    if (warp == 1) {
+      tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer (one lane issues; the warp stays converged on the waits)
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % p.stages;
-      if (i >= p.stages) mbar_wait(&empty_bar[s], ((i / p.stages) - 1) & 1, 1);
-      if (lane == 0) {
-        const int kb = kb_begin + i;
-        const int tap = kb / p.cblocks;
-        const int cb = kb - tap * p.cblocks;
+    // ===== TMA producer. The whole warp walks the loop (so every value stays warp-uniform and lives
+    // in uniform registers); one elected lane issues. Stage / phase / tap / channel block advance
+    // incrementally - no divisions on this critical instruction chain.
+    int s = 0;
+    uint32_t ph = 1;                      // parity of the "slot is free" phase (fresh barriers pass)
+    const uint32_t tx_bytes = (uint32_t)((p.a_tx_bytes + b_stage_bytes) * CG);
+    const int ctot = p.C0 + p.C1;
+    int ltp = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
+      const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+      trace_stamp(ltp, 0);
+      int tap = t.kb_begin / p.cblocks;
+      int cb = t.kb_begin - tap * p.cblocks;
+      const int wn = t.n0 + cta_rank * b_rows;
+      for (int i = 0; i < t.nkb; ++i) {
+        mbar_wait(&empty_bar[s], ph, 1);
         uint8_t* a_dst = smem + s * stage_bytes;
         uint8_t* b_dst = a_dst + GEMM_A_STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)(p.a_tx_bytes + b_stage_bytes));
         const bool second = cb >= p.cblocks0;
         const CUtensorMap* ma = second ? &p.map_a1 : &p.map_a0;
         const int c = (second ? (cb - p.cblocks0) : cb) * GEMM_BK;
-        if (p.a_rank == 2) {
-          tma_load_2d(ma, &full_bar[s], a_dst, c, w0);
-        } else {
-          tma_load_5d(ma, &full_bar[s], a_dst, c + p.tap_dc_sel[tap] * p.tap_dc_unit,
-                      w0 + p.tap_dw[tap], p.tap_d2[tap], h0 + p.tap_dh[tap], nb0);
+        const int wk = tap * ctot + cb * GEMM_BK;
+        const int ca = c + p.tap_dc_sel[tap] * p.tap_dc_unit;
+        const int cw = t.w0 + p.tap_dw[tap];
+        const int c2 = p.tap_d2[tap];
+        const int chh = t.h0 + p.tap_dh[tap];
+        if (elect_one()) {
+          // the leader's barrier collects the bytes of both CTAs
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          if constexpr (CG == 2) {
+            if (p.a_rank == 2) tma_load_2d_pair(ma, &full_bar[s], a_dst, c, t.w0);
+            else tma_load_5d_pair(ma, &full_bar[s], a_dst, ca, cw, c2, chh, t.nb0);
+            tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst, wk, wn);
+          } else {
+            if (p.a_rank == 2) tma_load_2d(ma, &full_bar[s], a_dst, c, t.w0);
+            else tma_load_5d(ma, &full_bar[s], a_dst, ca, cw, c2, chh, t.nb0);
+            tma_load_2d(&p.map_w, &full_bar[s], b_dst, wk, wn);
+          }
         }
-        tma_load_2d(&p.map_w, &full_bar[s], b_dst, tap * (p.C0 + p.C1) + cb * GEMM_BK, n0);
+        __syncwarp();
+        if (++cb == p.cblocks) { cb = 0; ++tap; }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
+      trace_stamp(ltp, 1);
     }
   } else if (warp == 1) {
-    // ===== MMA issuer
-    const uint32_t idesc = make_idesc_bf16(GEMM_BM, (uint32_t)p.block_n);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % p.stages;
-      mbar_wait(&full_bar[s], (i / p.stages) & 1, 2);
+    // ===== MMA issuer: warp 1 of the leader CTA, one elected lane issues
+    if (leader) {
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, (uint32_t)p.block_n);
+      const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem));
+      const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + GEMM_A_STAGE_BYTES);
+      const uint32_t stage_step = (uint32_t)(stage_bytes >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      uint32_t soff = 0;                     // s * stage_bytes >> 4
+      int lt = 0;
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
+        const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+        const int acc = lt & 1;
+        trace_stamp(lt, 2);
+        if (lt >= 2) mbar_wait(&tempty_bar[acc], ((lt >> 1) - 1) & 1, 4);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
+        uint32_t accum = 0;
+        for (int i = 0; i < t.nkb; ++i) {
+          mbar_wait(&full_bar[s], ph, 2);
+          if (i == 0) trace_stamp(lt, 3);
+          tc_fence_after();
+          const uint64_t a_desc = a_desc0 + soff;
+          const uint64_t b_desc = b_desc0 + soff;
+          if (elect_one()) {
+            // advancing 16 bf16 (32 bytes) along K inside the 128B swizzle atom: +2 in (addr>>4)
+            if constexpr (CG == 2) {
+              mma_ss_pair(d_tmem, a_desc, b_desc, idesc, accum);
+              mma_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+              mma_ss_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+              mma_ss_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              tc_commit_pair(&empty_bar[s], 3);
+            } else {
+              mma_ss(d_tmem, a_desc, b_desc, idesc, accum);
+              mma_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+              mma_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+              mma_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              tc_commit(&empty_bar[s]);
+            }
+          }
+          __syncwarp();
+          accum = 1;
+          soff += stage_step;
+          if (++s == p.stages) { s = 0; ph ^= 1u; soff = 0; }
+        }
+        if (elect_one()) {
+          if constexpr (CG == 2) tc_commit_pair(&tfull_bar[acc], 3);
+          else tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        trace_stamp(lt, 4);
+      }
+    }
+  } else {
+    // ===== Epilogue warps. Warp e = warp - 2 owns TMEM lanes [32*(warp%4), +32) and the 32-column
+    // chunks e/4, e/4 + 2, ...  Phase 1: thread = row, TMEM -> 128B-swizzled shared chunk.
+    // Phase 2: 8 lanes per row, 16 bytes each, so every global access is a full 128-byte row segment.
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    uint8_t* stg = epi_smem + e * GEMM_EPI_STAGE_BYTES;
+    const uint32_t stg_addr = smem_u32(stg);
+    const int nchunks = (p.block_n + 31) / 32;
+    const int sub = lane >> 3;   // row within a group of 4
+    const int c4 = lane & 7;     // 16-byte column group
+    const int cl = c4 * 4;       // first of this lane's 4 columns in a chunk
+    const bool has_res = (p.residual != nullptr) && (p.nsplit == 1);
+    int lt = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
+      const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+      const int acc = lt & 1;
+      // rows this lane touches in phase 2: local rows sub + 4*i
+      long long mrow[8];
+      float rbias[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = q * 32 + i * 4 + sub;
+        const int dw = r % p.bw;
+        const int dh = (r / p.bw) % p.bh;
+        const int dn = r / (p.bw * p.bh);
+        const int ww = t.w0 + dw, hh = t.h0 + dh, nn = t.nb0 + dn;
+        const bool ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
+        mrow[i] = ok ? ((long long)nn * p.HO + hh) * p.WO + ww : -1;
+        rbias[i] = (p.bias_mode == 2 && ok) ? __ldg(p.bias + mrow[i]) : 0.0f;
+      }
+      // residual of this warp's first chunk: in flight while the tile is still accumulating
+      float4 rnext[8];
+      if (has_res && half < nchunks) {
+        const int c0n = t.n0 + half * 32;
+        load_residual(p, mrow, c0n, cl, min(32, min(p.block_n - half * 32, p.N - c0n)), rnext);
+      }
+      if (e == 0 && lane == 0) trace_stamp(lt, 5);
+      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1, 3);
+      if (e == 0 && lane == 0) trace_stamp(lt, 6);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-        const uint32_t b_addr = a_addr + GEMM_A_STAGE_BYTES;
-        const uint64_t a_desc = make_kmajor_sw128_desc(a_addr);
-        const uint64_t b_desc = make_kmajor_sw128_desc(b_addr);
+      const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+      for (int ch = half; ch < nchunks; ch += 2) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + (uint32_t)(ch * 32), v);
+        float4 rcur[8];
+        if (has_res) {
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          // advancing 16 bf16 (32 bytes) along K inside the 128B swizzle atom: +2 in (addr>>4)
-          mma_ss(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                 (i > 0 || k > 0) ? 1u : 0u);
+          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+          if (ch + 2 < nchunks) {
+            const int c0n = t.n0 + (ch + 2) * 32;
+            load_residual(p, mrow, c0n, cl, min(32, min(p.block_n - (ch + 2) * 32, p.N - c0n)), rnext);
+          }
         }
-        tc_commit(&empty_bar[s]);
-        if (i == nkb - 1) tc_commit(accum_bar);
+        tmem_ld_wait();
+        // phase 1: row `lane` of the chunk -> staging, 16-byte pieces XOR-swizzled by the row
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = stg_addr + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v[4 * j]),
+                       "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        // phase 2
+        const int col0 = t.n0 + ch * 32;
+        const int ncol = min(32, min(p.block_n - ch * 32, p.N - col0));
+        const bool vec_ok = (cl + 4 <= ncol);
+        float4 cbias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias_mode == 1 && cl < ncol) {
+          cbias.x = __ldg(p.bias + col0 + cl);
+          if (cl + 1 < ncol) cbias.y = __ldg(p.bias + col0 + cl + 1);
+          if (cl + 2 < ncol) cbias.z = __ldg(p.bias + col0 + cl + 2);
+          if (cl + 3 < ncol) cbias.w = __ldg(p.bias + col0 + cl + 3);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int lr = i * 4 + sub;
+          const long long m = mrow[i];
+          if (m < 0 || cl >= ncol) continue;
+          float4 x;
+          {
+            const uint32_t src = stg_addr + (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "r"(src));
+          }
+          if (p.nsplit > 1) {
+            float* wsp = p.workspace + ((long long)t.z * p.m_total + m) * p.N + col0 + cl;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(wsp) & 15u) == 0)) {
+              *reinterpret_cast<float4*>(wsp) = x;
+            } else {
+              wsp[0] = x.x;
+              if (cl + 1 < ncol) wsp[1] = x.y;
+              if (cl + 2 < ncol) wsp[2] = x.z;
+              if (cl + 3 < ncol) wsp[3] = x.w;
+            }
+            continue;
+          }
+          x.x += cbias.x + rbias[i]; x.y += cbias.y + rbias[i];
+          x.z += cbias.z + rbias[i]; x.w += cbias.w + rbias[i];
+          if (p.act != 0) {
+            x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
+            x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
+          }
+          if (has_res) {
+            x.x += rcur[i].x; x.y += rcur[i].y; x.z += rcur[i].z; x.w += rcur[i].w;
+          }
+          const long long ooff = m * p.ldo + col0 + cl;
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + ooff;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+              *reinterpret_cast<float4*>(op) = x;
+            } else {
+              op[0] = x.x;
+              if (cl + 1 < ncol) op[1] = x.y;
+              if (cl + 2 < ncol) op[2] = x.z;
+              if (cl + 3 < ncol) op[3] = x.w;
+            }
+          }
+          __nv_bfloat16* bp = p.out_fp32 ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
+          if (bp != nullptr) {
+            __nv_bfloat16* op = bp + ooff;
+            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 7u) == 0)) {
+              *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+            } else {
+              op[0] = __float2bfloat16_rn(x.x);
+              if (cl + 1 < ncol) op[1] = __float2bfloat16_rn(x.y);
+              if (cl + 2 < ncol) op[2] = __float2bfloat16_rn(x.z);
+              if (cl + 3 < ncol) op[3] = __float2bfloat16_rn(x.w);
+            }
+          }
+        }
+        __syncwarp();
       }
+      // all tcgen05.ld of this accumulator have completed (tmem_ld_wait above): hand it back to the
+      // MMA issuer (the leader's barrier; a remote arrive from the peer CTA)
+      tc_fence_before();
       __syncwarp();
-    }
-  }
-
-  // ===== Epilogue: all 8 warps. Warp w reads TMEM lanes [32*(w%4), +32), column chunks w/4, w/4+2, ...
-  __syncwarp();
-  if (nkb > 0) mbar_wait(accum_bar, 0, 3);
-  tc_fence_after();
-
-  const int q = warp & 3;
-  const int r = q * 32 + lane;  // row of the tile owned by this thread
-  const int dw = r % p.bw;
-  const int dh = (r / p.bw) % p.bh;
-  const int dn = r / (p.bw * p.bh);
-  const int ww = w0 + dw, hh = h0 + dh, nn = nb0 + dn;
-  const bool row_ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
-  const long long m = ((long long)nn * p.HO + hh) * p.WO + ww;
-  const int nchunks = (p.block_n + 31) / 32;
-  const float row_bias = (p.bias_mode == 2 && row_ok) ? __ldg(p.bias + m) : 0.0f;
-
-  for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
-    uint32_t v[32];
-    if (nkb > 0) {
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0u;
-    }
-    const int col0 = n0 + ch * 32;
-    const int ncol = min(32, min(p.block_n - ch * 32, p.N - col0));
-    if (row_ok && ncol > 0) {
-      if (p.nsplit > 1) {
-        float* wsp = p.workspace + ((long long)blockIdx.z * p.m_total + m) * p.N + col0;
-        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(wsp) & 15u) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(wsp + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) wsp[j] = __uint_as_float(v[j]);
-        }
-      } else {
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (p.bias_mode == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) x[j] += __ldg(p.bias + col0 + j);
-        } else if (p.bias_mode == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] += row_bias;
-        }
-        if (p.act != 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = apply_act(x[j], p.act);
-        }
-        if (p.residual != nullptr && p.res_fp32) {
-          const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + col0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(rp + j));
-              x[j + 0] += u.x; x[j + 1] += u.y; x[j + 2] += u.z; x[j + 3] += u.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) x[j] += rp[j];
-          }
-        } else if (p.residual != nullptr) {
-          const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + col0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + j));
-              x[j + 0] += bf16lo(u.x); x[j + 1] += bf16hi(u.x);
-              x[j + 2] += bf16lo(u.y); x[j + 3] += bf16hi(u.y);
-              x[j + 4] += bf16lo(u.z); x[j + 5] += bf16hi(u.z);
-              x[j + 6] += bf16lo(u.w); x[j + 7] += bf16hi(u.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) x[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (p.out_fp32) {
-          float* op = reinterpret_cast<float*>(p.out) + m * p.ldo + col0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(op + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = x[j];
-          }
-        }
-        __nv_bfloat16* bp = p.out_fp32 ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
-        if (bp != nullptr) {
-          __nv_bfloat16* op = bp + m * p.ldo + col0;
-          if (ncol == 32 && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 u;
-              u.x = pack_bf16x2(x[j + 0], x[j + 1]);
-              u.y = pack_bf16x2(x[j + 2], x[j + 3]);
-              u.z = pack_bf16x2(x[j + 4], x[j + 5]);
-              u.w = pack_bf16x2(x[j + 6], x[j + 7]);
-              *reinterpret_cast<uint4*>(op + j) = u;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncol) op[j] = __float2bfloat16_rn(x[j]);
-          }
-        }
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
+        else mbar_arrive(&tempty_bar[acc]);
+        if (e == 0) trace_stamp(lt, 7);
       }
     }
-    __syncwarp();
   }
 
+  __syncwarp();      // the single-thread producer / issuer loops rejoin their warps here
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  if constexpr (CG == 2) {
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // Split-K finalize: out = act(sum_z ws[z] + bias) + residual.
@@ -359,6 +538,19 @@ static int pick_tile_box(int NB, int HO, int WO, int* bw, int* bh, int* bn) {
   return best_tiles > 0 ? 0 : -1;
 }
 
+static int device_sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -366,6 +558,20 @@ static int pow2_cols(int n) {
 }
 
 }  // namespace sdb
+
+// Debug: switch the per-tile timeline of CTA 0 on/off, or (on < 0) copy GEMM_TRACE_TILES*8 stamps out.
+extern "C" int sdb_debug_gemm_trace(int on, long long* out_host) {
+  if (on >= 0) {
+    long long zero[sdb::GEMM_TRACE_TILES * 8];
+    memset(zero, 0, sizeof(zero));
+    cudaMemcpyToSymbol(sdb::g_gemm_trace, zero, sizeof(zero));
+    cudaMemcpyToSymbol(sdb::g_gemm_trace_on, &on, sizeof(int));
+    return SDB_OK;
+  }
+  if (!out_host) return SDB_ERR_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(out_host, sdb::g_gemm_trace, sizeof(long long) * sdb::GEMM_TRACE_TILES * 8);
+  return e == cudaSuccess ? SDB_OK : SDB_ERR_CUDA;
+}
 
 extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   using namespace sdb;
@@ -478,29 +684,37 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     return SDB_ERR_ARG;
   }
   p.block_n = block_n;
-  p.tmem_cols = pow2_cols(((block_n + 31) / 32) * 32);
+  p.acc_stride = pow2_cols(((block_n + 31) / 32) * 32);
+  p.tmem_cols = 2 * p.acc_stride;
   const int n_tiles = (a->Cout + block_n - 1) / block_n;
+  // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two row tiles
+  int cg = (m_tiles >= 2) ? 2 : 1;
+  if (a->cta_pair == 1) cg = 1;
+  if (a->cta_pair == 2) cg = 2;
   {
     uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)a->Cout};
     const long long ldw = a->ldw ? a->ldw : p.ktot;
     uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {64, (uint32_t)block_n};
+    uint32_t box[2] = {64, (uint32_t)(block_n / cg)};
     if ((rc = make_tmap_bf16(&p.map_w, a->w, 2, dims, str, box, "gemm W"))) return rc;
   }
 
   // ---- pipeline depth from the shared-memory budget
-  const int stage_bytes = GEMM_A_STAGE_BYTES + block_n * GEMM_BK * 2;
-  const int smem_budget = a->smem_budget > 0 ? a->smem_budget : (block_n > 160 ? 220 * 1024 : 110 * 1024);
-  int stages = (smem_budget - 2048) / stage_bytes;
+  const int stage_bytes = GEMM_A_STAGE_BYTES + (block_n / cg) * GEMM_BK * 2;
+  const int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + 256;
+  const int smem_budget = (a->smem_budget > 0 && a->smem_budget < 227 * 1024) ? a->smem_budget : 227 * 1024;
+  int stages = (smem_budget - fixed_bytes) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
-  if (stages < 2) stages = 2;
+  if (stages < 2) { set_error("sdb_gemm_tc: shared-memory budget too small"); return SDB_ERR_ARG; }
   const int nkb_total = p.ntaps * p.cblocks;
   int nsplit = a->nsplit > 0 ? a->nsplit : 1;
   if (nsplit > nkb_total) nsplit = nkb_total;
+  p.per_split = (nkb_total + nsplit - 1) / nsplit;
+  nsplit = (nkb_total + p.per_split - 1) / p.per_split;   // no empty slice
   if (nsplit > 1 && !a->workspace) { set_error("sdb_gemm_tc: split-K needs a workspace"); return SDB_ERR_ARG; }
   p.nsplit = nsplit;
   p.stages = stages;
-  const int smem_bytes = stages * stage_bytes + 1024 + 256;
+  const int smem_bytes = stages * stage_bytes + fixed_bytes;
 
   p.out = a->out;
   p.ldo = a->ldo ? a->ldo : a->Cout;
@@ -520,15 +734,41 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
-  if (m_tiles > 2147483647LL || n_tiles > 65535) { set_error("sdb_gemm_tc: grid too large"); return SDB_ERR_UNSUPPORTED; }
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)nsplit);
-  gemm_tc_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+  const long long row_tiles = (m_tiles + cg - 1) / cg;        // 256-row tiles in pair mode
+  const long long total_tiles = row_tiles * n_tiles * nsplit;
+  if (total_tiles > 2147483647LL) { set_error("sdb_gemm_tc: too many tiles"); return SDB_ERR_UNSUPPORTED; }
+  p.m_tiles = (int)row_tiles;
+  p.n_tiles = n_tiles;
+  p.total_tiles = (int)total_tiles;
+  const int num_sms = device_sm_count();
+  const long long slots = num_sms / cg;                       // CTAs (or CTA pairs) resident at once
+  const unsigned grid = (unsigned)((total_tiles < slots ? total_tiles : slots) * cg);
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = (cg == 2) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, p)
+                              : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, p);
+    if (e != cudaSuccess) { set_error("gemm_tc_kernel launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
+  }
   if ((rc = check_launch("gemm_tc_kernel"))) return rc;
   if (nsplit > 1) {
     const long long total = p.m_total * p.N;

@@ -92,7 +92,7 @@ def _choose_split(m_tiles, cout, block_n, nkb):
 
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
-         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0):
+         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
     lib = _ext.lib()
     _chk(a0, torch.bfloat16, "a0")
@@ -148,6 +148,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         ws = torch.empty((nsplit, rows, cout), device=a0.device, dtype=torch.float32)
         args.workspace = _p(ws)
     args.nsplit = nsplit
+    args.cta_pair = cta_pair
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
                2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size())
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")

@@ -1,0 +1,134 @@
+"""Per-kernel micro-benchmark over the distinct problem sizes of one UNet evaluation at batch B
+(M scales with N = 2B). CUDA-event timing, `--iters` back-to-back launches after
+`--warmup`, an L2-sized scratch write between timed groups.
+
+  python tools/kernel_bench.py [--batch 8] [--only substr] [--iters 10] [--json out.json]
+A single launch of one case for ncu:  python tools/kernel_bench.py --only conv3x3_320_320_64 --iters 1 --warmup 0
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pytorch_stable_diffusion_b200 import _ext, ops  # noqa: E402
+
+DEV = "cuda"
+PAIR = 0
+
+
+def bf(*shape, scale=1.0):
+    return (torch.randn(*shape, device=DEV) * scale).bfloat16()
+
+
+def cases(B):
+    N = 2 * B
+    out = []
+
+    def lin(name, S, K, Cout, count, res=False, fp32=False):
+        M = N * S
+        a = bf(M, K)
+        w = bf(Cout, K, scale=K ** -0.5)
+        b = torch.randn(Cout, device=DEV)
+        r = torch.randn(M, Cout, device=DEV) if res else None
+        fl = 2.0 * M * K * Cout
+        out.append((f"linear_{name}_{M}x{K}x{Cout}", count, fl,
+                    lambda: ops.linear(a, w, bias=b, residual=r, out_fp32=fp32, cta_pair=PAIR)))
+
+    def conv(name, Hh, C0, C1, Cout, count, kind=ops.GEMM_CONV3X3_S1):
+        x0 = bf(N, Hh, Hh, C0)
+        x1 = bf(N, Hh, Hh, C1) if C1 else None
+        w = bf(Cout, 9 * (C0 + C1), scale=(9 * (C0 + C1)) ** -0.5)
+        b = torch.randn(Cout, device=DEV)
+        ho = Hh // 2 if kind != ops.GEMM_CONV3X3_S1 else Hh
+        fl = 2.0 * N * ho * ho * Cout * 9 * (C0 + C1)
+        out.append((f"conv3x3_{name}_{C0 + C1}_{Cout}_{Hh}", count, fl,
+                    lambda: ops.gemm(x0, w, Cout, kind=kind, a1=x1, bias=b, conv_dims=(N, Hh, Hh), c0=C0, c1=C1,
+                                     out_fp32=True, cta_pair=PAIR)))
+
+    def attn(name, S, Skv, d, count):
+        heads = 8
+        c = heads * d
+        skv_pad = (Skv + 7) // 8 * 8
+        q = bf(N * S, c)
+        k = bf(N * skv_pad, c)
+        vt = bf(c, N * skv_pad)
+        o = torch.empty(N * S, c, device=DEV, dtype=torch.bfloat16)
+        fl = 4.0 * N * heads * S * Skv * d
+        out.append((f"attn_{name}_S{S}_kv{Skv}_d{d}", count, fl,
+                    lambda: ops.attention(q, k, vt, o, NB=N, heads=heads, d=d, S=S, Skv=Skv, Skv_pad=skv_pad,
+                                          ldq=c, ldk=c, ldo=c)))
+
+    for S, C in ((4096, 320), (1024, 640), (256, 1280)):
+        lin("proj", S, C, C, 15, res=True, fp32=True)     # out_proj x2, q_proj, conv_in/out
+        lin("qk", S, C, 2 * C, 5)
+        lin("geglu1", S, C, 4 * C, 5)
+        lin("geglu2", S, 4 * C, C, 5, res=True)
+        attn("self", S, S, C // 8, 5)
+        attn("cross", S, 77, C // 8, 5)
+    conv("res", 64, 320, 0, 320, 9)
+    conv("res", 32, 640, 0, 640, 8)
+    conv("res", 16, 1280, 0, 1280, 9)
+    conv("res", 8, 1280, 0, 1280, 11)
+    conv("cat", 8, 1280, 1280, 1280, 3)
+    conv("cat", 16, 1280, 1280, 1280, 2)
+    conv("cat", 16, 1280, 640, 1280, 1)
+    conv("cat", 32, 1280, 640, 640, 1)
+    conv("cat", 32, 640, 640, 640, 1)
+    conv("cat", 32, 640, 320, 640, 1)
+    conv("cat", 64, 640, 320, 320, 1)
+    conv("cat", 64, 320, 320, 320, 2)
+    conv("down", 64, 320, 0, 320, 1, kind=ops.GEMM_CONV3X3_S2)
+    conv("down", 32, 640, 0, 640, 1, kind=ops.GEMM_CONV3X3_S2)
+    conv("down", 16, 1280, 0, 1280, 1, kind=ops.GEMM_CONV3X3_S2)
+    # VAE decoder tail (per-sample sizes; batch B)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--json", default="")
+    ap.add_argument("--pair", type=int, default=0, help="0 auto, 1 single-CTA tiles, 2 CTA pairs")
+    args = ap.parse_args()
+    global PAIR
+    PAIR = args.pair
+    torch.manual_seed(0)
+    scratch = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
+    rows = []
+    tot_ms = 0.0
+    tot_fl = 0.0
+    for name, count, fl, fn in cases(args.batch):
+        if args.only and args.only not in name:
+            continue
+        for _ in range(args.warmup):
+            fn()
+        scratch.zero_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        tf = fl / (ms * 1e-3) / 1e12
+        rows.append({"case": name, "count_per_unet_eval": count, "ms": ms, "tflops": tf})
+        tot_ms += ms * count
+        tot_fl += fl * count
+        print(f"{name:44s} x{count:<3d} {ms * 1e3:9.1f} us  {tf:8.1f} TFLOP/s", flush=True)
+    fault = _ext.read_fault()
+    print(f"weighted total: {tot_ms:.2f} ms per UNet evaluation in these kernels, "
+          f"{tot_fl / max(tot_ms, 1e-9) / 1e9:.1f} TFLOP/s aggregate; fault={fault}")
+    if args.json:
+        json.dump(rows, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
