@@ -97,6 +97,7 @@ typedef struct sdb_attn_args {
   long long ldq, ldk, ldo;
   int causal;             /* key t visible to query s iff t <= s (sd/attention.py:58-62)         */
   float scale;            /* 1/sqrt(d) (sd/attention.py:66,223)                                  */
+  int variant;            /* 0 = choose; 1 = force the one-tile (128 queries per CTA) kernel       */
 } sdb_attn_args;
 
 /* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),

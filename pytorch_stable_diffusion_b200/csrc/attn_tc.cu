@@ -102,15 +102,16 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
       for (int c = 0; c < p.dchunks; ++c)
         tma_load_4d(&p.map_q, q_full, q_smem + c * ATT_CHUNK_BYTES, c * 64, h, q0, n);
     }
+    __syncwarp();
     for (int j = 0; j < nkv; ++j) {
       const int s = j & 1;
       if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) - 1) & 1, 11);
-      if (lane == 0) {
+      if (elect_one()) {
         uint8_t* kd = kv_smem + s * stage_bytes;
         uint8_t* vd = kd + k_bytes;
         mbar_arrive_expect_tx(&kv_full[s], (uint32_t)stage_bytes);
@@ -131,7 +132,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const int s = j & 1;
       mbar_wait(&kv_full[s], (j >> 1) & 1, 13);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t k_addr = smem_u32(kv_smem + s * stage_bytes);
         for (int ks = 0; ks < p.dk_steps; ++ks) {
           const uint32_t off = (uint32_t)((ks >> 2) * ATT_CHUNK_BYTES + (ks & 3) * 32);
@@ -148,7 +149,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       if (j + 1 < nkv) issue_qk(j + 1);
       mbar_wait(&p_full[s], (j >> 1) & 1, 14);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t v_addr = smem_u32(kv_smem + s * stage_bytes + k_bytes);
         for (int ks = 0; ks < ATT_BKV / 16; ++ks) {
           const uint32_t off = (uint32_t)((ks >> 2) * v_chunk_bytes + (ks & 3) * 32);
@@ -267,6 +268,269 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Two-tile variant (head dim <= 128, no causal mask): one CTA owns 256 queries as two 128-query tiles
+// that share every K / V^T block. While the softmax warpgroup of one tile works on S_t, the tensor
+// pipe runs the other tile's P.V and the next Q.K^T, so exponentials (MUFU) and MMAs overlap:
+//   warp 0     TMA: both Q tiles once, then K block + V^T block per 128 keys into a 3-stage ring
+//   warp 1     tcgen05.mma issuer (one elected lane), order per key block j:
+//                P0.V(j)  Q0.K(j+1)  P1.V(j)  Q1.K(j+1)
+//   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one query row per thread)
+// TMEM: S0/P0 at columns [0,128), S1/P1 at [128,256), O0 at [256,384), O1 at [384,512).
+constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_STAGES = 3;
+
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn2_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int h = blockIdx.y;
+  const int n = blockIdx.z;
+
+  const int q_bytes = p.dchunks * ATT_CHUNK_BYTES;          // one 128-query tile
+  const int k_bytes = p.dchunks * ATT_CHUNK_BYTES;
+  const int v_chunk_bytes = p.dv_pad * 128;
+  const int stage_bytes = k_bytes + 2 * v_chunk_bytes;
+  uint8_t* q_smem = smem;
+  uint8_t* kv_smem = smem + 2 * q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + ATT2_STAGES * stage_bytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;                  // [ATT2_STAGES]
+  uint64_t* kv_empty = kv_full + ATT2_STAGES;    // [ATT2_STAGES]
+  uint64_t* s_full = kv_empty + ATT2_STAGES;     // [2]
+  uint64_t* p_full = s_full + 2;                 // [2]
+  uint64_t* o_done = p_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int nkv = (p.Skv + ATT_BKV - 1) / ATT_BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_q);
+    tma_prefetch_desc(&p.map_k);
+    tma_prefetch_desc(&p.map_vt);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT2_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, (uint32_t)(2 * q_bytes));
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(&p.map_q, q_full, q_smem + t * q_bytes + c * ATT_CHUNK_BYTES, c * 64, h,
+                      q0 + t * ATT_BQ, n);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 1;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&kv_empty[st], ph, 21);
+      uint8_t* kd = kv_smem + st * stage_bytes;
+      uint8_t* vd = kd + k_bytes;
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&kv_full[st], (uint32_t)stage_bytes);
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(&p.map_k, &kv_full[st], kd + c * ATT_CHUNK_BYTES, c * 64, h, j * ATT_BKV, n);
+        tma_load_3d(&p.map_vt, &kv_full[st], vd, j * ATT_BKV, n, h * p.d);
+        tma_load_3d(&p.map_vt, &kv_full[st], vd + v_chunk_bytes, j * ATT_BKV + 64, n, h * p.d);
+      }
+      __syncwarp();
+      if (++st == ATT2_STAGES) { st = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer
+    const uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV);
+    const uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, (uint32_t)p.dv_pad);
+    const uint32_t q_addr = smem_u32(q_smem);
+    const uint32_t kv_addr = smem_u32(kv_smem);
+    mbar_wait(q_full, 0, 22);
+    // S_t = Q_t . K(stage)^T
+    auto issue_qk = [&](int t, int st) {
+      const uint32_t qa = q_addr + (uint32_t)(t * q_bytes);
+      const uint32_t ka = kv_addr + (uint32_t)(st * stage_bytes);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(t * 128);
+      if (elect_one()) {
+        for (int ks = 0; ks < p.dk_steps; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * ATT_CHUNK_BYTES + (ks & 3) * 32);
+          mma_ss(d_tmem, make_kmajor_sw128_desc(qa + off), make_kmajor_sw128_desc(ka + off), idesc_qk,
+                 ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&s_full[t]);
+      }
+      __syncwarp();
+    };
+    // O_t += P_t . V(stage)
+    auto issue_pv = [&](int t, int st, bool first, bool release) {
+      const uint32_t va = kv_addr + (uint32_t)(st * stage_bytes + k_bytes);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(256 + t * 128);
+      const uint32_t p_tmem = tmem_base + (uint32_t)(t * 128);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < ATT_BKV / 16; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * v_chunk_bytes + (ks & 3) * 32);
+          mma_ts(d_tmem, p_tmem + (uint32_t)(ks * 8), make_kmajor_sw128_desc(va + off), idesc_pv,
+                 (!first || ks > 0) ? 1u : 0u);
+        }
+        tc_commit(&o_done[t]);
+        if (release) tc_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&kv_full[0], 0, 23);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    int st = 0;
+    uint32_t ph_kv = 0;                 // phase of kv_full[next stage]
+    for (int j = 0; j < nkv; ++j) {
+      int st_next = st + 1;
+      uint32_t ph_next = ph_kv;
+      if (st_next == ATT2_STAGES) { st_next = 0; ph_next ^= 1u; }
+      const bool more = (j + 1 < nkv);
+      const uint32_t par = (uint32_t)(j & 1);
+      mbar_wait(&p_full[0], par, 24);
+      tc_fence_after();
+      issue_pv(0, st, j == 0, false);
+      if (more) {
+        mbar_wait(&kv_full[st_next], ph_next, 25);
+        tc_fence_after();
+        issue_qk(0, st_next);
+      }
+      mbar_wait(&p_full[1], par, 26);
+      tc_fence_after();
+      issue_pv(1, st, j == 0, true);
+      if (more) issue_qk(1, st_next);
+      st = st_next;
+      ph_kv = ph_next;
+    }
+  } else {
+    // ===================== softmax / correction / output: warps 2-5 tile 0, warps 6-9 tile 1
+    const int t = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int qrow = q0 + t * ATT_BQ + row;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(t * 128);
+    const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(256 + t * 128);
+    float m_ref = -INFINITY;  // maximum the exponentials are currently taken against
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_full[t], (uint32_t)(j & 1), 27);
+      tc_fence_after();
+      uint32_t sv[128];
+      tmem_ld32(s_addr + 0, sv + 0);
+      tmem_ld32(s_addr + 32, sv + 32);
+      tmem_ld32(s_addr + 64, sv + 64);
+      tmem_ld32(s_addr + 96, sv + 96);
+      tmem_ld_wait();
+      const int visible = p.Skv - j * ATT_BKV;          // keys [0, visible) of this block are real
+      float mloc = -INFINITY;
+      if (visible >= 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mloc = fmaxf(mloc, __uint_as_float(sv[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const float v = (i < visible) ? __uint_as_float(sv[i]) : -INFINITY;
+          sv[i] = __float_as_uint(v);
+          mloc = fmaxf(mloc, v);
+        }
+      }
+      const float m_new = fmaxf(m_ref, mloc);
+      // lazy rescale: keep the old reference maximum while the new one is within 2^8 of it
+      const bool need = (m_new > m_ref) && ((m_new - m_ref) * sl2 > 8.0f);
+      const bool any_need = __any_sync(0xffffffffu, need);
+      if (any_need && j > 0) {
+        mbar_wait(&o_done[t], (uint32_t)((j - 1) & 1), 28);
+        tc_fence_after();
+        const float factor = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
+        for (int c = 0; c < p.dv_pad; c += 16) {
+          uint32_t ov[16];
+          tmem_ld16(o_addr + (uint32_t)c, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * factor);
+          tmem_st16(o_addr + (uint32_t)c, ov);
+        }
+        tmem_st_wait();
+        l_run *= factor;
+      }
+      if (need) m_ref = m_new;
+      const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
+      float lsum0 = 0.f, lsum1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int i = 0; i < 128; i += 2) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+        lsum0 += p0;
+        lsum1 += p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run += lsum0 + lsum1;
+      tmem_st32(s_addr + 0, pk + 0);
+      tmem_st32(s_addr + 32, pk + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    // ---- epilogue: O / l -> bf16
+    mbar_wait(&o_done[t], (uint32_t)((nkv - 1) & 1), 29);
+    tc_fence_after();
+    const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + ((long long)n * p.S + qrow) * p.ldo + (long long)h * p.d;
+    for (int c = 0; c < p.dv_pad; c += 16) {
+      uint32_t ov[16];
+      tmem_ld16(o_addr + (uint32_t)c, ov);
+      tmem_ld_wait();
+      if (qrow < p.S) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = c + g * 8;
+          if (col + 8 <= p.d) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + col) = u;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace sdb
 
 extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
@@ -322,19 +586,29 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.dv_pad = dv_pad;
   const int q_bytes = p.dchunks * ATT_CHUNK_BYTES;
   const int stage_bytes = p.dchunks * ATT_CHUNK_BYTES + 2 * dv_pad * 128;
-  const int smem_bytes = q_bytes + 2 * stage_bytes + 1024 + 256;
-  if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
+  static bool configured[64] = {false};
   {
-    static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
       cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            227 * 1024);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
   }
+  // two 128-query tiles per CTA when the accumulators fit (d <= 128) and there is more than one tile
+  const int smem2 = 2 * q_bytes + ATT2_STAGES * stage_bytes + 1024 + 256;
+  const bool two_tile = !a->causal && a->d <= 128 && a->S > ATT_BQ && smem2 <= 227 * 1024 && a->variant != 1;
+  if (two_tile) {
+    dim3 grid((unsigned)((a->S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)), (unsigned)a->heads, (unsigned)a->NB);
+    attn2_tc_kernel<<<grid, ATT2_THREADS, smem2, (cudaStream_t)stream>>>(p);
+    return check_launch("attn2_tc_kernel");
+  }
+  const int smem_bytes = q_bytes + 2 * stage_bytes + 1024 + 256;
+  if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((a->S + ATT_BQ - 1) / ATT_BQ), (unsigned)a->heads, (unsigned)a->NB);
   attn_tc_kernel<<<grid, ATT_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
   return check_launch("attn_tc_kernel");

@@ -174,7 +174,8 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
     return out.view(shape)
 
 
-def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0):
+def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0,
+              variant=0):
     lib = _ext.lib()
     a = AttnArgs()
     a.q, a.k, a.vt, a.out = _p(_chk(q, torch.bfloat16, "q")), _p(_chk(k, torch.bfloat16, "k")), \
@@ -183,6 +184,7 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
     a.ldq, a.ldk, a.ldo = ldq, ldk, ldo
     a.causal = 1 if causal else 0
     a.scale = 1.0 / math.sqrt(d)
+    a.variant = variant
     ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
                2.0 * NB * heads * d * (2 * S + 2 * Skv))
     _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")
