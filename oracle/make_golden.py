@@ -167,7 +167,10 @@ def main():
 
     h = models["diffusion"].register_forward_hook(hook)
     dec_in = {}
-    hd = models["decoder"].register_forward_pre_hook(lambda m, inp: dec_in.setdefault("z", inp[0].clone()))
+    def grab_decoder_input(mod, inp):     # must return None: a returned tensor would replace the input
+        dec_in.setdefault("z", inp[0].clone())
+
+    hd = models["decoder"].register_forward_pre_hook(grab_decoder_input)
     t0 = time.time()
     image = ref["pipeline"].generate(prompt="a", uncond_prompt="b", input_image=None, strength=0.8, do_cfg=True,
                                      cfg_scale=7.5, sampler_name="ddpm", n_inference_steps=50, models=models,
@@ -186,7 +189,7 @@ def main():
     dog = Image.open("/root/reference/images/dog.jpg")
     counter["i"] = 0
     dec_in.clear()
-    hd = models["decoder"].register_forward_pre_hook(lambda m, inp: dec_in.setdefault("z", inp[0].clone()))
+    hd = models["decoder"].register_forward_pre_hook(grab_decoder_input)
     image = ref["pipeline"].generate(prompt="a", uncond_prompt="b", input_image=dog, strength=0.8, do_cfg=True,
                                      cfg_scale=7.5, sampler_name="ddpm", n_inference_steps=5, models=models,
                                      seed=42, device="cpu", idle_device=None, tokenizer=tok)
