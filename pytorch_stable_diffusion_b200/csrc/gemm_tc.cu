@@ -29,6 +29,7 @@ constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;     // warp 0 TMA, warp 1
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KiB
 constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;          // one 32x32 fp32 chunk per epilogue warp
+constexpr int GEMM_RES_RING = 3;                           // residual chunks in flight per epilogue warp (+1)
 
 struct GemmTcParams {
   CUtensorMap map_a0;
@@ -67,6 +68,8 @@ struct GemmTcParams {
   int bias_mode;           // 0 none, 1 per column, 2 per row
   const void* residual;    // bf16, or fp32 when res_fp32
   int res_fp32;
+  int res_async;           // fp32 residual streamed through a per-warp cp.async ring in shared memory
+  int res_direct;          // fp32 residual, 16-byte aligned, fetched with vector loads per chunk
   long long ldr;
   __nv_bfloat16* out2;     // optional bf16 copy of the output (same row stride), or nullptr
   int act;                 // 0 none, 1 quick-GELU, 2 SiLU
@@ -90,9 +93,14 @@ struct TileCoord {
 constexpr int GEMM_TRACE_TILES = 64;
 __device__ long long g_gemm_trace[GEMM_TRACE_TILES * 8];
 __device__ int g_gemm_trace_on = 0;
-__device__ __forceinline__ void trace_stamp(int tile_local, int slot) {
-  if (g_gemm_trace_on && blockIdx.x == 0 && tile_local < GEMM_TRACE_TILES)
-    g_gemm_trace[tile_local * 8 + slot] = clock64();
+// `trc` is the trace mode read ONCE per kernel (0 for every CTA but the first): the stamps sit next to
+// the single-thread issue loops, where a global load per call would itself distort the timeline.
+__device__ __forceinline__ void trace_stamp(int trc, int tile_local, int slot) {
+  if (trc && !(trc & 8) && tile_local < GEMM_TRACE_TILES) g_gemm_trace[tile_local * 8 + slot] = clock64();
+}
+// mode 8: epilogue-internal stamps of warp 2 / lane 0 for the first chunk of every tile
+__device__ __forceinline__ void trace_epi(int trc, int tile_local, int slot) {
+  if ((trc & 8) && tile_local < GEMM_TRACE_TILES) g_gemm_trace[tile_local * 8 + slot] = clock64();
 }
 
 // Tile order: output-channel tile fastest, so CTAs that run at the same time share the activation
@@ -119,43 +127,6 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
   return t;
 }
 
-// Residual values of the 4 columns x 8 rows one lane owns in a 32-column chunk (zeros where absent).
-__device__ __forceinline__ void load_residual(const GemmTcParams& p, const long long (&mrow)[8], int col0,
-                                              int cl, int ncol, float4 (&r)[8]) {
-  const bool vec_ok = (cl + 4 <= ncol);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long m = mrow[i];
-    if (m < 0 || cl >= ncol) continue;
-    const long long roff = m * p.ldr + col0 + cl;
-    if (p.res_fp32) {
-      const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
-      if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15u) == 0)) {
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(r[i].x), "=f"(r[i].y), "=f"(r[i].z), "=f"(r[i].w)
-                     : "l"(rp));
-      } else {
-        r[i].x = rp[0];
-        if (cl + 1 < ncol) r[i].y = rp[1];
-        if (cl + 2 < ncol) r[i].z = rp[2];
-        if (cl + 3 < ncol) r[i].w = rp[3];
-      }
-    } else {
-      const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
-      if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 7u) == 0)) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp));
-        r[i] = make_float4(bf16lo(u.x), bf16hi(u.x), bf16lo(u.y), bf16hi(u.y));
-      } else {
-        r[i].x = __bfloat162float(rp[0]);
-        if (cl + 1 < ncol) r[i].y = __bfloat162float(rp[1]);
-        if (cl + 2 < ncol) r[i].z = __bfloat162float(rp[2]);
-        if (cl + 3 < ncol) r[i].w = __bfloat162float(rp[3]);
-      }
-    }
-  }
-}
-
 // Persistent, warp-specialised kernel. CG = 1: one CTA per SM computes 128 x block_n tiles.
 // CG = 2: a cluster of two CTAs (one SM pair) computes 256 x block_n tiles with cta_group::2 MMAs -
 // each CTA stages its own 128 rows of A and HALF of the W tile, so a pipeline stage holds fewer bytes
@@ -173,6 +144,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int trc = (blockIdx.x == 0) ? g_gemm_trace_on : 0;
   const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const bool leader = (cta_rank == 0);
   const int first_tile = blockIdx.x / CG;
@@ -232,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     int ltp = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
       const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
-      trace_stamp(ltp, 0);
+      trace_stamp(trc, ltp, 0);
       int tap = t.kb_begin / p.cblocks;
       int cb = t.kb_begin - tap * p.cblocks;
       const int wn = t.n0 + cta_rank * b_rows;
@@ -265,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         if (++cb == p.cblocks) { cb = 0; ++tap; }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      trace_stamp(ltp, 1);
+      trace_stamp(trc, ltp, 1);
     }
   } else if (warp == 1) {
     // ===== MMA issuer: warp 1 of the leader CTA, one elected lane issues
@@ -281,14 +253,14 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         const int acc = lt & 1;
-        trace_stamp(lt, 2);
+        trace_stamp(trc, lt, 2);
         if (lt >= 2) mbar_wait(&tempty_bar[acc], ((lt >> 1) - 1) & 1, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         uint32_t accum = 0;
         for (int i = 0; i < t.nkb; ++i) {
           mbar_wait(&full_bar[s], ph, 2);
-          if (i == 0) trace_stamp(lt, 3);
+          if (i == 0) trace_stamp(trc, lt, 3);
           tc_fence_after();
           const uint64_t a_desc = a_desc0 + soff;
           const uint64_t b_desc = b_desc0 + soff;
@@ -318,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           else tc_commit(&tfull_bar[acc]);
         }
         __syncwarp();
-        trace_stamp(lt, 4);
+        trace_stamp(trc, lt, 4);
       }
     }
   } else {
@@ -335,48 +307,130 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const int c4 = lane & 7;     // 16-byte column group
     const int cl = c4 * 4;       // first of this lane's 4 columns in a chunk
     const bool has_res = (p.residual != nullptr) && (p.nsplit == 1);
+    const bool res_async = has_res && p.res_async;
+    const bool res_direct = has_res && p.res_direct;
+    // warp-uniform: the vectorised epilogue applies (no split-K partials, residual via the ring or
+    // absent, 16-byte aligned fp32 rows / 8-byte aligned bf16 rows)
+    const bool fast_ok =
+        (p.nsplit == 1) && (!has_res || res_async || res_direct) && (p.ldo % 4 == 0) &&
+        (p.out_fp32 ? ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 &&
+                       (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 7u) == 0))
+                    : ((reinterpret_cast<uintptr_t>(p.out) & 7u) == 0)) &&
+        (p.bias_mode != 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0);
+    const uint32_t ring_addr = smem_u32(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES +
+                                        e * (GEMM_RES_RING * GEMM_EPI_STAGE_BYTES));
+    // (dw, dh, dn) of the 8 tile rows this lane touches in phase 2 (local rows sub + 4*i): fixed for the
+    // whole kernel, so the divisions happen once and not per tile
+    int rdec[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = q * 32 + i * 4 + sub;
+      const int dw = r % p.bw;
+      const int dh = (r / p.bw) % p.bh;
+      const int dn = r / (p.bw * p.bh);
+      rdec[i] = dw | (dh << 8) | (dn << 16);
+    }
+    auto rows_for = [&](const TileCoord& t, int (&mr)[8]) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int dn = rdec[i] >> 16;
+        const int ww = t.w0 + (rdec[i] & 0xff), hh = t.h0 + ((rdec[i] >> 8) & 0xff), nn = t.nb0 + dn;
+        const bool ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
+        mr[i] = ok ? (nn * p.HO + hh) * p.WO + ww : -1;       // output row index, -1 = outside the tensor
+      }
+    };
+    // ---- residual prefetch cursor: walks the same (tile, chunk) sequence as the main loop,
+    // GEMM_RES_RING - 1 chunks ahead, each chunk one cp.async group into ring slot seq % GEMM_RES_RING.
+    // A lane later reads back exactly the 16-byte pieces it requested itself, so cp.async.wait_group is
+    // the only synchronisation needed.
+    int pf_tile = first_tile, pf_lt = 0, pf_ch = half, pf_slot = 0;
+    int pf_mrow[8];
+    TileCoord pf_t;
+    if (res_async) {
+      while (pf_tile < p.total_tiles && pf_ch >= nchunks) { pf_tile += tile_step; ++pf_lt; pf_ch = (half + pf_lt) & 1; }
+      if (pf_tile < p.total_tiles) { pf_t = decode_tile<CG>(p, pf_tile, cta_rank); rows_for(pf_t, pf_mrow); }
+    }
+    auto issue_prefetch = [&]() {
+      if (pf_tile < p.total_tiles) {
+        const int c0n = pf_t.n0 + pf_ch * 32;
+        const int ncn = min(32, min(p.block_n - pf_ch * 32, p.N - c0n));
+        if (cl + 4 <= ncn) {
+          const uint32_t dst0 = ring_addr + (uint32_t)(pf_slot * GEMM_EPI_STAGE_BYTES);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = pf_mrow[i];
+            if (m < 0) continue;
+            const int lr = i * 4 + sub;
+            const float* src = reinterpret_cast<const float*>(p.residual) + (long long)m * p.ldr + c0n + cl;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4))),
+                         "l"(src)
+                         : "memory");
+          }
+        }
+        pf_ch += 2;
+        if (pf_ch >= nchunks) {
+          do { pf_tile += tile_step; ++pf_lt; pf_ch = (half + pf_lt) & 1; } while (pf_tile < p.total_tiles && pf_ch >= nchunks);
+          if (pf_tile < p.total_tiles) { pf_t = decode_tile<CG>(p, pf_tile, cta_rank); rows_for(pf_t, pf_mrow); }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (++pf_slot == GEMM_RES_RING) pf_slot = 0;
+    };
+    if (res_async) {
+#pragma unroll
+      for (int dpf = 0; dpf < GEMM_RES_RING - 1; ++dpf) issue_prefetch();
+    }
+    int rd_slot = 0;       // ring slot of the chunk being consumed
     int lt = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
       const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
       const int acc = lt & 1;
-      // rows this lane touches in phase 2: local rows sub + 4*i
-      long long mrow[8];
-      float rbias[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = q * 32 + i * 4 + sub;
-        const int dw = r % p.bw;
-        const int dh = (r / p.bw) % p.bh;
-        const int dn = r / (p.bw * p.bh);
-        const int ww = t.w0 + dw, hh = t.h0 + dh, nn = t.nb0 + dn;
-        const bool ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
-        mrow[i] = ok ? ((long long)nn * p.HO + hh) * p.WO + ww : -1;
-        rbias[i] = (p.bias_mode == 2 && ok) ? __ldg(p.bias + mrow[i]) : 0.0f;
-      }
-      // residual of this warp's first chunk: in flight while the tile is still accumulating
-      float4 rnext[8];
-      if (has_res && half < nchunks) {
-        const int c0n = t.n0 + half * 32;
-        load_residual(p, mrow, c0n, cl, min(32, min(p.block_n - half * 32, p.N - c0n)), rnext);
-      }
-      if (e == 0 && lane == 0) trace_stamp(lt, 5);
+      const int ch_first = (half + lt) & 1;     // alternate so both halves get the odd chunk in turn
+      int mrow[8];
+      rows_for(t, mrow);
+      if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
       mbar_wait(&tfull_bar[acc], (lt >> 1) & 1, 3);
-      if (e == 0 && lane == 0) trace_stamp(lt, 6);
+      if (e == 0 && lane == 0) { trace_stamp(trc, lt, 6); trace_epi(trc, lt, 1); }
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-      for (int ch = half; ch < nchunks; ch += 2) {
+      for (int ch = ch_first; ch < nchunks; ch += 2) {
+        const int col0 = t.n0 + ch * 32;
+        const int ncol = min(32, min(p.block_n - ch * 32, p.N - col0));
+        const bool vec_ok = (cl + 4 <= ncol);
+        // bias of this lane's 4 columns: requested before the accumulator load so that its latency
+        // hides behind tcgen05.ld and phase 1
+        float4 cbias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias_mode == 1 && cl < ncol) {
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(p.bias + col0 + cl) & 15u) == 0)) {
+            cbias = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cl));
+          } else {
+            cbias.x = __ldg(p.bias + col0 + cl);
+            if (cl + 1 < ncol) cbias.y = __ldg(p.bias + col0 + cl + 1);
+            if (cl + 2 < ncol) cbias.z = __ldg(p.bias + col0 + cl + 2);
+            if (cl + 3 < ncol) cbias.w = __ldg(p.bias + col0 + cl + 3);
+          }
+        }
         uint32_t v[32];
         tmem_ld32(t_addr + (uint32_t)(ch * 32), v);
-        float4 rcur[8];
-        if (has_res) {
+        if (res_async) issue_prefetch();                       // chunk seq + GEMM_RES_RING - 1
+        // long-K tiles keep their shared memory for pipeline stages: the residual of this chunk is
+        // requested here and lands while the accumulator is loaded and staged
+        float4 rdir[8];
+        if (res_direct && fast_ok && ncol == 32) {
+          const float* rb0 = reinterpret_cast<const float*>(p.residual) + col0 + cl;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
-          if (ch + 2 < nchunks) {
-            const int c0n = t.n0 + (ch + 2) * 32;
-            load_residual(p, mrow, c0n, cl, min(32, min(p.block_n - (ch + 2) * 32, p.N - c0n)), rnext);
+          for (int i = 0; i < 8; ++i) {
+            rdir[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mrow[i] >= 0) {
+              const float* rp = rb0 + (long long)mrow[i] * p.ldr;
+              asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rdir[i].x), "=f"(rdir[i].y), "=f"(rdir[i].z), "=f"(rdir[i].w)
+                           : "l"(rp));
+            }
           }
         }
         tmem_ld_wait();
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
         // phase 1: row `lane` of the chunk -> staging, 16-byte pieces XOR-swizzled by the row
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -385,78 +439,163 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                        "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
                        : "memory");
         }
+        if (res_async) asm volatile("cp.async.wait_group %0;" ::"n"(GEMM_RES_RING - 1) : "memory");
         __syncwarp();
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
         // phase 2
-        const int col0 = t.n0 + ch * 32;
-        const int ncol = min(32, min(p.block_n - ch * 32, p.N - col0));
-        const bool vec_ok = (cl + 4 <= ncol);
-        float4 cbias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias_mode == 1 && cl < ncol) {
-          cbias.x = __ldg(p.bias + col0 + cl);
-          if (cl + 1 < ncol) cbias.y = __ldg(p.bias + col0 + cl + 1);
-          if (cl + 2 < ncol) cbias.z = __ldg(p.bias + col0 + cl + 2);
-          if (cl + 3 < ncol) cbias.w = __ldg(p.bias + col0 + cl + 3);
-        }
+        const uint32_t rslot = ring_addr + (uint32_t)(rd_slot * GEMM_EPI_STAGE_BYTES);
+        if (fast_ok && ncol == 32) {
+          // fast path (full chunk, aligned pointers): all shared-memory reads first, then the math,
+          // then the stores - eight independent chains per lane, no per-element guards
+          float4 x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int lr = i * 4 + sub;
-          const long long m = mrow[i];
-          if (m < 0 || cl >= ncol) continue;
-          float4 x;
-          {
-            const uint32_t src = stg_addr + (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
+          for (int i = 0; i < 8; ++i) {
+            const int lr = i * 4 + sub;
+            const uint32_t swz = (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                         : "r"(src));
+                         : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                         : "r"(stg_addr + swz));
           }
-          if (p.nsplit > 1) {
-            float* wsp = p.workspace + ((long long)t.z * p.m_total + m) * p.N + col0 + cl;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(wsp) & 15u) == 0)) {
-              *reinterpret_cast<float4*>(wsp) = x;
-            } else {
-              wsp[0] = x.x;
-              if (cl + 1 < ncol) wsp[1] = x.y;
-              if (cl + 2 < ncol) wsp[2] = x.z;
-              if (cl + 3 < ncol) wsp[3] = x.w;
+          if (p.bias_mode == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float rb = (mrow[i] >= 0) ? __ldg(p.bias + mrow[i]) : 0.f;
+              x[i].x += rb; x[i].y += rb; x[i].z += rb; x[i].w += rb;
             }
-            continue;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x += cbias.x; x[i].y += cbias.y; x[i].z += cbias.z; x[i].w += cbias.w;
+            }
           }
-          x.x += cbias.x + rbias[i]; x.y += cbias.y + rbias[i];
-          x.z += cbias.z + rbias[i]; x.w += cbias.w + rbias[i];
           if (p.act != 0) {
-            x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
-            x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
-          }
-          if (has_res) {
-            x.x += rcur[i].x; x.y += rcur[i].y; x.z += rcur[i].z; x.w += rcur[i].w;
-          }
-          const long long ooff = m * p.ldo + col0 + cl;
-          if (p.out_fp32) {
-            float* op = reinterpret_cast<float*>(p.out) + ooff;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
-              *reinterpret_cast<float4*>(op) = x;
-            } else {
-              op[0] = x.x;
-              if (cl + 1 < ncol) op[1] = x.y;
-              if (cl + 2 < ncol) op[2] = x.z;
-              if (cl + 3 < ncol) op[3] = x.w;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x = apply_act(x[i].x, p.act); x[i].y = apply_act(x[i].y, p.act);
+              x[i].z = apply_act(x[i].z, p.act); x[i].w = apply_act(x[i].w, p.act);
             }
+          }
+          if (res_async) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int lr = i * 4 + sub;
+              const uint32_t swz = (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
+              float4 rr;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                           : "r"(rslot + swz));
+              x[i].x += rr.x; x[i].y += rr.y; x[i].z += rr.z; x[i].w += rr.w;
+            }
+          } else if (res_direct) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x += rdir[i].x; x[i].y += rdir[i].y; x[i].z += rdir[i].z; x[i].w += rdir[i].w;
+            }
+          }
+          if (p.out_fp32) {
+            float* ob = reinterpret_cast<float*>(p.out) + col0 + cl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mrow[i] >= 0) *reinterpret_cast<float4*>(ob + (long long)mrow[i] * p.ldo) = x[i];
           }
           __nv_bfloat16* bp = p.out_fp32 ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
           if (bp != nullptr) {
-            __nv_bfloat16* op = bp + ooff;
-            if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 7u) == 0)) {
-              *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-            } else {
-              op[0] = __float2bfloat16_rn(x.x);
-              if (cl + 1 < ncol) op[1] = __float2bfloat16_rn(x.y);
-              if (cl + 2 < ncol) op[2] = __float2bfloat16_rn(x.z);
-              if (cl + 3 < ncol) op[3] = __float2bfloat16_rn(x.w);
+            __nv_bfloat16* ob = bp + col0 + cl;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mrow[i] >= 0)
+                *reinterpret_cast<uint2*>(ob + (long long)mrow[i] * p.ldo) =
+                    make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+          }
+        } else {
+  #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int lr = i * 4 + sub;
+            const int m = mrow[i];
+            if (m < 0 || cl >= ncol) continue;
+            const uint32_t swz = (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "r"(stg_addr + swz));
+            if (p.nsplit > 1) {
+              float* wsp = p.workspace + ((long long)t.z * p.m_total + m) * p.N + col0 + cl;
+              if (vec_ok && ((reinterpret_cast<uintptr_t>(wsp) & 15u) == 0)) {
+                *reinterpret_cast<float4*>(wsp) = x;
+              } else {
+                wsp[0] = x.x;
+                if (cl + 1 < ncol) wsp[1] = x.y;
+                if (cl + 2 < ncol) wsp[2] = x.z;
+                if (cl + 3 < ncol) wsp[3] = x.w;
+              }
+              continue;
+            }
+            const float rb = (p.bias_mode == 2) ? __ldg(p.bias + m) : 0.0f;   // per-row bias (swapped GEMMs)
+            x.x += cbias.x + rb; x.y += cbias.y + rb;
+            x.z += cbias.z + rb; x.w += cbias.w + rb;
+            if (p.act != 0) {
+              x.x = apply_act(x.x, p.act); x.y = apply_act(x.y, p.act);
+              x.z = apply_act(x.z, p.act); x.w = apply_act(x.w, p.act);
+            }
+            if (res_async) {
+              float4 rr;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                           : "r"(rslot + swz));
+              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+            } else if (has_res) {
+              // bf16 or unaligned fp32 residual: direct loads (not on the hot path of the engines)
+              const long long roff = (long long)m * p.ldr + col0 + cl;
+              if (p.res_fp32) {
+                const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
+                x.x += rp[0];
+                if (cl + 1 < ncol) x.y += rp[1];
+                if (cl + 2 < ncol) x.z += rp[2];
+                if (cl + 3 < ncol) x.w += rp[3];
+              } else {
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+                if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 7u) == 0)) {
+                  const uint2 u = __ldg(reinterpret_cast<const uint2*>(rp));
+                  x.x += bf16lo(u.x); x.y += bf16hi(u.x); x.z += bf16lo(u.y); x.w += bf16hi(u.y);
+                } else {
+                  x.x += __bfloat162float(rp[0]);
+                  if (cl + 1 < ncol) x.y += __bfloat162float(rp[1]);
+                  if (cl + 2 < ncol) x.z += __bfloat162float(rp[2]);
+                  if (cl + 3 < ncol) x.w += __bfloat162float(rp[3]);
+                }
+              }
+            }
+            const long long ooff = (long long)m * p.ldo + col0 + cl;
+            if (p.out_fp32) {
+              float* op = reinterpret_cast<float*>(p.out) + ooff;
+              if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 15u) == 0)) {
+                *reinterpret_cast<float4*>(op) = x;
+              } else {
+                op[0] = x.x;
+                if (cl + 1 < ncol) op[1] = x.y;
+                if (cl + 2 < ncol) op[2] = x.z;
+                if (cl + 3 < ncol) op[3] = x.w;
+              }
+            }
+            __nv_bfloat16* bp = p.out_fp32 ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
+            if (bp != nullptr) {
+              __nv_bfloat16* op = bp + ooff;
+              if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 7u) == 0)) {
+                *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+              } else {
+                op[0] = __float2bfloat16_rn(x.x);
+                if (cl + 1 < ncol) op[1] = __float2bfloat16_rn(x.y);
+                if (cl + 2 < ncol) op[2] = __float2bfloat16_rn(x.z);
+                if (cl + 3 < ncol) op[3] = __float2bfloat16_rn(x.w);
+              }
             }
           }
         }
+        if (++rd_slot == GEMM_RES_RING) rd_slot = 0;
         __syncwarp();
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 4);
       }
+      if (e == 0 && lane == 0) trace_epi(trc, lt, 5);
       // all tcgen05.ld of this accumulator have completed (tmem_ld_wait above): hand it back to the
       // MMA issuer (the leader's barrier; a remote arrive from the peer CTA)
       tc_fence_before();
@@ -464,7 +603,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
         else mbar_arrive(&tempty_bar[acc]);
-        if (e == 0) trace_stamp(lt, 7);
+        if (e == 0) trace_stamp(trc, lt, 7);
       }
     }
   }
@@ -701,7 +840,16 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
 
   // ---- pipeline depth from the shared-memory budget
   const int stage_bytes = GEMM_A_STAGE_BYTES + (block_n / cg) * GEMM_BK * 2;
-  const int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + 256;
+  // fp32 residuals stream through a cp.async ring (3 chunks per epilogue warp) when 16-byte aligned
+  const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
+  const int want_split = a->nsplit > 1;
+  const bool res_vec = (a->residual != nullptr && a->res_fp32 && !want_split && (ldr_eff % 4) == 0 &&
+                        (a->Cout % 4) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0);
+  // short reductions are epilogue-bound (ring: deep prefetch); long ones keep the shared memory for stages
+  const int nkb_all = p.ntaps * p.cblocks;
+  p.res_async = (res_vec && nkb_all <= 32) ? 1 : 0;
+  p.res_direct = (res_vec && !p.res_async) ? 1 : 0;
+  const int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)) + 1024 + 256;
   const int smem_budget = (a->smem_budget > 0 && a->smem_budget < 227 * 1024) ? a->smem_budget : 227 * 1024;
   int stages = (smem_budget - fixed_bytes) / stage_bytes;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;

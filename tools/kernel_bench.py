@@ -38,16 +38,17 @@ def cases(B):
         out.append((f"linear_{name}_{M}x{K}x{Cout}", count, fl,
                     lambda: ops.linear(a, w, bias=b, residual=r, out_fp32=fp32, cta_pair=PAIR)))
 
-    def conv(name, Hh, C0, C1, Cout, count, kind=ops.GEMM_CONV3X3_S1):
+    def conv(name, Hh, C0, C1, Cout, count, kind=ops.GEMM_CONV3X3_S1, res=False):
         x0 = bf(N, Hh, Hh, C0)
         x1 = bf(N, Hh, Hh, C1) if C1 else None
         w = bf(Cout, 9 * (C0 + C1), scale=(9 * (C0 + C1)) ** -0.5)
         b = torch.randn(Cout, device=DEV)
         ho = Hh // 2 if kind != ops.GEMM_CONV3X3_S1 else Hh
         fl = 2.0 * N * ho * ho * Cout * 9 * (C0 + C1)
+        r = torch.randn(N * ho * ho, Cout, device=DEV) if res else None
         out.append((f"conv3x3_{name}_{C0 + C1}_{Cout}_{Hh}", count, fl,
                     lambda: ops.gemm(x0, w, Cout, kind=kind, a1=x1, bias=b, conv_dims=(N, Hh, Hh), c0=C0, c1=C1,
-                                     out_fp32=True, cta_pair=PAIR)))
+                                     residual=r, out_fp32=True, out2=True if res else None, cta_pair=PAIR)))
 
     def attn(name, S, Skv, d, count):
         heads = 8
@@ -69,10 +70,14 @@ def cases(B):
         lin("geglu2", S, 4 * C, C, 5, res=True)
         attn("self", S, S, C // 8, 5)
         attn("cross", S, 77, C // 8, 5)
-    conv("res", 64, 320, 0, 320, 9)
-    conv("res", 32, 640, 0, 640, 8)
-    conv("res", 16, 1280, 0, 1280, 9)
-    conv("res", 8, 1280, 0, 1280, 11)
+    conv("res", 64, 320, 0, 320, 4)
+    conv("merged", 64, 320, 0, 320, 5, res=True)      # conv_merged: fp32 residual in, fp32 + bf16 out
+    conv("res", 32, 640, 0, 640, 3)
+    conv("merged", 32, 640, 0, 640, 5, res=True)
+    conv("res", 16, 1280, 0, 1280, 3)
+    conv("merged", 16, 1280, 0, 1280, 6, res=True)
+    conv("res", 8, 1280, 0, 1280, 4)
+    conv("merged", 8, 1280, 0, 1280, 7, res=True)
     conv("cat", 8, 1280, 1280, 1280, 3)
     conv("cat", 16, 1280, 1280, 1280, 2)
     conv("cat", 16, 1280, 640, 1280, 1)
