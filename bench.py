@@ -39,7 +39,8 @@ UNIT = "images/s"
 N_STEPS = 50
 CFG = 7.5
 H = W = 512
-UNET_GFLOP_PER_IMAGE_STEP = 1498.25     # SURVEY.md §8d, algorithmic, CFG pair, 64x64 latent
+UNET_GFLOP_PER_IMAGE_STEP_UNFOLDED = 1498.25   # SURVEY.md §8d, algorithmic, CFG pair, 64x64 latent
+GEGLU_FOLD_SAVING_GFLOP = 179.1        # linear_geglu_2 . linear_geglu_1[:4C] composed into one C x C map
 VAE_GFLOP_PER_IMAGE = 2514.52
 CLIP_GFLOP_PER_PROMPT = 13.30
 
@@ -199,9 +200,11 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from pytorch_stable_diffusion_b200 import _ext, ops, pipeline, synthetic
+    from pytorch_stable_diffusion_b200 import _ext, engine, ops, pipeline, synthetic
     from pytorch_stable_diffusion_b200.ddpm import DDPMSampler
     peaks = load_peaks()
+    UNET_GFLOP_PER_IMAGE_STEP = UNET_GFLOP_PER_IMAGE_STEP_UNFOLDED - (
+        GEGLU_FOLD_SAVING_GFLOP if engine.FOLD_GEGLU else 0.0)
     B = args.batch
     lh, lw = H // 8, W // 8
 
@@ -386,6 +389,8 @@ def main():
                                    f"batch {B} per GPU, 50 DDPM steps, CFG 7.5, CUDA-graph-captured loop",
                        "batch_per_gpu": B, "global_batch": B * world, "n_inference_steps": N_STEPS,
                        "cfg_scale": CFG, "parallelism": f"seed-sharded x{world}, no collective",
+                       "geglu_folded": bool(engine.FOLD_GEGLU),
+                       "unet_gflop_per_image_step_algorithmic": UNET_GFLOP_PER_IMAGE_STEP,
                        "l2": "inputs larger than L2: 1.7 GB of bf16 weights streamed per UNet evaluation"},
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches,
             "roofline": roof, "cpu_baseline": cpu,

@@ -72,6 +72,7 @@ typedef struct sdb_gemm_args {
   int nsplit;             /* split-K factor, 0/1 = none                                          */
   int smem_budget;        /* bytes of shared memory for the pipeline, 0 = choose                 */
   int cta_pair;           /* 0 = choose; 1 = one CTA per tile (128 rows); 2 = CTA pairs (256 rows) */
+  int out_f16;            /* 16-bit `out` is IEEE half instead of bf16 (Cout % 32 == 0, no split-K)  */
 } sdb_gemm_args;
 
 /* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,
@@ -98,6 +99,10 @@ typedef struct sdb_attn_args {
   int causal;             /* key t visible to query s iff t <= s (sd/attention.py:58-62)         */
   float scale;            /* 1/sqrt(d) (sd/attention.py:66,223)                                  */
   int variant;            /* 0 = choose; 1 = force the one-tile (128 queries per CTA) kernel       */
+  int sum_row;            /* vt holds R = round16(d + 1) rows per head (head h at rows [h*R, h*R + R)), row d of
+                             every head is all ones: the denominator of the softmax is accumulated by the
+                             P.V tensor-core product itself. No causal mask, d <= 112.                */
+  int p_f16;              /* with sum_row: exponentials are taken two at a time in f16x2 and P is f16 */
 } sdb_attn_args;
 
 /* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),
@@ -106,10 +111,12 @@ int sdb_attention(const sdb_attn_args* args, void* stream);
 
 /* ---- normalisation (HBM-bound) ------------------------------------------------------------ */
 /* GroupNorm statistics over NHWC x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0), each bf16 or
- * fp32 (x?_fp32):
- * stats[n][g] = {sum, sum of squares} in fp64; stats must be zeroed by the caller
- * (sdb_fill_zero). nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;
+ * fp32 (x?_fp32). Deterministic: every thread block writes its per-group partial {sum, sum of squares}
+ * (fp64) into `stats`, a caller-provided buffer of sdb_groupnorm_stats_bytes(NB, groups) bytes that
+ * needs no initialisation; sdb_groupnorm_apply (same NB, HW, C0, C1, groups) adds the partials in a
+ * fixed order. nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;
  * sd/encoder.py:86. */
+long long sdb_groupnorm_stats_bytes(int NB, int groups);
 int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, long long HW,
                         int C0, int C1, int groups, int x0_fp32, int x1_fp32, void* stream);
 /* y = (x - mean) * rstd * gamma + beta, optionally followed by SiLU (F.silu: sd/diffusion.py:176,

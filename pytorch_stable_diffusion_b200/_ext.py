@@ -18,7 +18,7 @@ class GemmArgs(ctypes.Structure):
         ("NB", c_int), ("HI", c_int), ("WI", c_int), ("C0", c_int), ("C1", c_int), ("Cout", c_int),
         ("lda0", c_ll), ("lda1", c_ll), ("ldw", c_ll), ("ldo", c_ll), ("ldr", c_ll),
         ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
-        ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int),
+        ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int), ("out_f16", c_int),
     ]
 
 
@@ -26,7 +26,7 @@ class AttnArgs(ctypes.Structure):
     _fields_ = [
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p), ("out", c_void_p), ("NB", c_int),
         ("heads", c_int), ("d", c_int), ("S", c_int), ("Skv", c_int), ("Skv_pad", c_int), ("vt_ld", c_int),
-        ("ldq", c_ll), ("ldk", c_ll), ("ldo", c_ll), ("causal", c_int), ("scale", c_float), ("variant", c_int),
+        ("ldq", c_ll), ("ldk", c_ll), ("ldo", c_ll), ("causal", c_int), ("scale", c_float), ("variant", c_int), ("sum_row", c_int), ("p_f16", c_int),
         ("variant", c_int),
     ]
 
@@ -40,6 +40,7 @@ SIGNATURES = {
     "sdb_gemm_tc": [ctypes.POINTER(GemmArgs), c_void_p],
     "sdb_debug_gemm_trace": [c_int, ctypes.POINTER(ctypes.c_longlong)],
     "sdb_attention": [ctypes.POINTER(AttnArgs), c_void_p],
+    "sdb_groupnorm_stats_bytes": [c_int, c_int],
     "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
                             c_void_p],
     "sdb_groupnorm_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll,
@@ -63,7 +64,8 @@ SIGNATURES = {
     "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
-_RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong}
+_RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong,
+             "sdb_groupnorm_stats_bytes": ctypes.c_longlong}
 
 _lib = None
 

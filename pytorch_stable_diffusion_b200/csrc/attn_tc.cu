@@ -35,12 +35,23 @@ struct AttnParams {
   float scale_log2;
   int dchunks;   // ceil(d / 64)
   int dk_steps;  // ceil(d / 16)
-  int dv_pad;    // d rounded up to 16
+  int dv_pad;    // V^T rows per head fed to the P.V MMA (multiple of 16, >= d)
+  int vt_rows;   // V^T rows per head in memory (d, or dv_pad when the ones row is present)
+  int sum_col;   // column of O that accumulates the softmax denominator (V^T ones row), or -1
+  int p_f16;     // P is stored as f16 (exponentials taken two at a time in f16x2) instead of bf16
+  int stages;    // K/V ring depth of the two-tile kernel (2 or 3)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two exponentials per MUFU operation: (lo, hi) fp32 -> f16x2 -> 2^x in f16x2
+__device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
+  uint32_t h, y;
+  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
   return y;
 }
 
@@ -279,7 +290,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one query row per thread)
 // TMEM: S0/P0 at columns [0,128), S1/P1 at [128,256), O0 at [256,384), O1 at [384,512).
 constexpr int ATT2_THREADS = 320;
-constexpr int ATT2_STAGES = 3;
+constexpr int ATT2_MAX_STAGES = 3;
 
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn2_tc_kernel(const __grid_constant__ AttnParams p) {
@@ -298,23 +309,34 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
   const int stage_bytes = k_bytes + 2 * v_chunk_bytes;
   uint8_t* q_smem = smem;
   uint8_t* kv_smem = smem + 2 * q_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + ATT2_STAGES * stage_bytes);
+  const int nstages = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + nstages * stage_bytes);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                  // [ATT2_STAGES]
-  uint64_t* kv_empty = kv_full + ATT2_STAGES;    // [ATT2_STAGES]
-  uint64_t* s_full = kv_empty + ATT2_STAGES;     // [2]
+  uint64_t* kv_full = bars + 1;                      // [ATT2_MAX_STAGES]
+  uint64_t* kv_empty = kv_full + ATT2_MAX_STAGES;    // [ATT2_MAX_STAGES]
+  uint64_t* s_full = kv_empty + ATT2_MAX_STAGES;     // [2]
   uint64_t* p_full = s_full + 2;                 // [2]
   uint64_t* o_done = p_full + 2;                 // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = o_done + 2;                 // [2] softmax has S_t in registers (separate-P layout)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  // TMEM columns. Narrow heads (dv_pad <= 64) keep P apart from S, so Q.K^T of the next key block can
+  // overwrite S_t while the softmax of the current one is still computing and P_t waits for its P.V:
+  //   separate:  S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
+  //   aliased:   S0/P0 [0,128) S1/P1 [128,256) O0 [256,384) O1 [384,512)
+  const bool p_sep = p.dv_pad <= 64;
+  const uint32_t p_col0 = p_sep ? 256u : 0u, p_colstep = p_sep ? 64u : 128u;
+  const uint32_t o_col0 = p_sep ? 384u : 256u, o_colstep = p_sep ? 64u : 128u;
 
   const int nkv = (p.Skv + ATT_BKV - 1) / ATT_BKV;
+  const int trc = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_gemm_trace_on : 0;
+#define ATT_STAMP(j, slot) do { if (trc && (j) < GEMM_TRACE_TILES) g_gemm_trace[(j) * 8 + (slot)] = clock64(); } while (0)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_q);
     tma_prefetch_desc(&p.map_k);
     tma_prefetch_desc(&p.map_vt);
     mbar_init(q_full, 1);
-    for (int i = 0; i < ATT2_STAGES; ++i) {
+    for (int i = 0; i < nstages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
@@ -322,6 +344,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
       mbar_init(&o_done[i], 1);
+      mbar_init(&s_free[i], 128);
     }
     fence_mbar_init();
   }
@@ -354,16 +377,17 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
         mbar_arrive_expect_tx(&kv_full[st], (uint32_t)stage_bytes);
         for (int c = 0; c < p.dchunks; ++c)
           tma_load_4d(&p.map_k, &kv_full[st], kd + c * ATT_CHUNK_BYTES, c * 64, h, j * ATT_BKV, n);
-        tma_load_3d(&p.map_vt, &kv_full[st], vd, j * ATT_BKV, n, h * p.d);
-        tma_load_3d(&p.map_vt, &kv_full[st], vd + v_chunk_bytes, j * ATT_BKV + 64, n, h * p.d);
+        tma_load_3d(&p.map_vt, &kv_full[st], vd, j * ATT_BKV, n, h * p.vt_rows);
+        tma_load_3d(&p.map_vt, &kv_full[st], vd + v_chunk_bytes, j * ATT_BKV + 64, n, h * p.vt_rows);
       }
       __syncwarp();
-      if (++st == ATT2_STAGES) { st = 0; ph ^= 1u; }
+      if (++st == nstages) { st = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer
     const uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV);
-    const uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, (uint32_t)p.dv_pad);
+    // p_f16 variant: P (A operand, from TMEM) and V^T (B operand) are both IEEE half (formats 0)
+    const uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, (uint32_t)p.dv_pad) & (p.p_f16 ? ~((7u << 7) | (7u << 10)) : ~0u);
     const uint32_t q_addr = smem_u32(q_smem);
     const uint32_t kv_addr = smem_u32(kv_smem);
     mbar_wait(q_full, 0, 22);
@@ -385,8 +409,8 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     // O_t += P_t . V(stage)
     auto issue_pv = [&](int t, int st, bool first, bool release) {
       const uint32_t va = kv_addr + (uint32_t)(st * stage_bytes + k_bytes);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(256 + t * 128);
-      const uint32_t p_tmem = tmem_base + (uint32_t)(t * 128);
+      const uint32_t d_tmem = tmem_base + o_col0 + (uint32_t)t * o_colstep;
+      const uint32_t p_tmem = tmem_base + p_col0 + (uint32_t)t * p_colstep;
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < ATT_BKV / 16; ++ks) {
@@ -408,21 +432,42 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < nkv; ++j) {
       int st_next = st + 1;
       uint32_t ph_next = ph_kv;
-      if (st_next == ATT2_STAGES) { st_next = 0; ph_next ^= 1u; }
+      if (st_next == nstages) { st_next = 0; ph_next ^= 1u; }
       const bool more = (j + 1 < nkv);
       const uint32_t par = (uint32_t)(j & 1);
-      mbar_wait(&p_full[0], par, 24);
-      tc_fence_after();
-      issue_pv(0, st, j == 0, false);
-      if (more) {
-        mbar_wait(&kv_full[st_next], ph_next, 25);
+      if (p_sep) {
+        // next key block's scores first: they only need S_t to have been read, not P_t.V to be done
+        if (more) {
+          mbar_wait(&kv_full[st_next], ph_next, 25);
+          mbar_wait(&s_free[0], par, 30);
+          tc_fence_after();
+          issue_qk(0, st_next);
+          mbar_wait(&s_free[1], par, 31);
+          tc_fence_after();
+          issue_qk(1, st_next);
+        }
+        if (lane == 0) ATT_STAMP(j, 7);
+        mbar_wait(&p_full[0], par, 24);
         tc_fence_after();
-        issue_qk(0, st_next);
+        issue_pv(0, st, j == 0, false);
+        if (lane == 0) ATT_STAMP(j, 6);
+        mbar_wait(&p_full[1], par, 26);
+        tc_fence_after();
+        issue_pv(1, st, j == 0, true);
+      } else {
+        mbar_wait(&p_full[0], par, 24);
+        tc_fence_after();
+        issue_pv(0, st, j == 0, false);
+        if (more) {
+          mbar_wait(&kv_full[st_next], ph_next, 25);
+          tc_fence_after();
+          issue_qk(0, st_next);
+        }
+        mbar_wait(&p_full[1], par, 26);
+        tc_fence_after();
+        issue_pv(1, st, j == 0, true);
+        if (more) issue_qk(1, st_next);
       }
-      mbar_wait(&p_full[1], par, 26);
-      tc_fence_after();
-      issue_pv(1, st, j == 0, true);
-      if (more) issue_qk(1, st_next);
       st = st_next;
       ph_kv = ph_next;
     }
@@ -434,12 +479,16 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     const int qrow = q0 + t * ATT_BQ + row;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(t * 128);
-    const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(256 + t * 128);
+    const uint32_t p_addr = tmem_base + lane_addr + p_col0 + (uint32_t)t * p_colstep;
+    const uint32_t o_addr = tmem_base + lane_addr + o_col0 + (uint32_t)t * o_colstep;
     float m_ref = -INFINITY;  // maximum the exponentials are currently taken against
     float l_run = 0.f;
     const float sl2 = p.scale_log2;
+    const bool tr0 = (t == 0 && quad == 2 && lane == 0);
     for (int j = 0; j < nkv; ++j) {
+      if (tr0) ATT_STAMP(j, 0);
       mbar_wait(&s_full[t], (uint32_t)(j & 1), 27);
+      if (tr0) ATT_STAMP(j, 1);
       tc_fence_after();
       uint32_t sv[128];
       tmem_ld32(s_addr + 0, sv + 0);
@@ -447,18 +496,29 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       tmem_ld32(s_addr + 64, sv + 64);
       tmem_ld32(s_addr + 96, sv + 96);
       tmem_ld_wait();
+      if (p_sep) {                       // S_t is in registers: the next Q.K^T may overwrite it
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+      }
+      if (tr0) ATT_STAMP(j, 2);
       const int visible = p.Skv - j * ATT_BKV;          // keys [0, visible) of this block are real
       float mloc = -INFINITY;
-      if (visible >= 128) {
+      if (visible < 128) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mloc = fmaxf(mloc, __uint_as_float(sv[i]));
-      } else {
+        for (int i = 0; i < 128; ++i)
+          if (i >= visible) sv[i] = 0xff800000u;           // -inf
+      }
+      {
+        // four independent chains: a single running maximum is a 64-deep dependent chain
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const float v = (i < visible) ? __uint_as_float(sv[i]) : -INFINITY;
-          sv[i] = __float_as_uint(v);
-          mloc = fmaxf(mloc, v);
+        for (int i = 0; i < 128; i += 8) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(sv[i + 0]), __uint_as_float(sv[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])));
         }
+        mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float m_new = fmaxf(m_ref, mloc);
       // lazy rescale: keep the old reference maximum while the new one is within 2^8 of it
@@ -481,26 +541,57 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       if (need) m_ref = m_new;
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      float lsum0 = 0.f, lsum1 = 0.f;
+      if (tr0) ATT_STAMP(j, 3);
       uint32_t pk[64];
+      if (p.p_f16) {
+        // denominator comes from the V^T ones row (sum_col >= 0 is required with p_f16)
 #pragma unroll
-      for (int i = 0; i < 128; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
-        lsum0 += p0;
-        lsum1 += p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 128; i += 2)
+          pk[i >> 1] = ex2_f16x2(fmaf(__uint_as_float(sv[i]), sl2, -mb), fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+      } else if (p.sum_col >= 0) {
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+      } else {
+        float lsum0 = 0.f, lsum1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+          lsum0 += p0;
+          lsum1 += p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        l_run += lsum0 + lsum1;
       }
-      l_run += lsum0 + lsum1;
-      tmem_st32(s_addr + 0, pk + 0);
-      tmem_st32(s_addr + 32, pk + 32);
+      if (tr0) ATT_STAMP(j, 4);
+      if (p_sep && j > 0) {              // P_t of the previous block must have been consumed by its P.V
+        mbar_wait(&o_done[t], (uint32_t)((j - 1) & 1), 32);
+        tc_fence_after();
+      }
+      tmem_st32(p_addr + 0, pk + 0);
+      tmem_st32(p_addr + 32, pk + 32);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      if (tr0) ATT_STAMP(j, 5);
     }
     // ---- epilogue: O / l -> bf16
     mbar_wait(&o_done[t], (uint32_t)((nkv - 1) & 1), 29);
     tc_fence_after();
+    if (p.sum_col >= 0) {               // l = sum_k P[k] * 1, accumulated by the MMA in column sum_col of O
+      uint32_t lv[16];
+      tmem_ld16(o_addr + (uint32_t)(p.sum_col & ~15), lv);
+      tmem_ld_wait();
+      float l = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.sum_col & 15)) l = __uint_as_float(lv[i]);
+      l_run = l;
+    }
     const float inv = (l_run > 0.f) ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + ((long long)n * p.S + qrow) * p.ldo + (long long)h * p.d;
     for (int c = 0; c < p.dv_pad; c += 16) {
@@ -569,9 +660,17 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     uint32_t box[4] = {64, 1, 128, 1};
     if ((rc = make_tmap_bf16(&p.map_k, a->k, 4, dims, str, box, "attention K"))) return rc;
   }
-  const int dv_pad = ((a->d + 15) / 16) * 16;
+  // V^T rows per head: d, or (sum_row) round16(d + 1) with row d all ones - the P.V MMA then also
+  // accumulates the softmax denominator in column d of O
+  const int dv_pad = ((a->d + (a->sum_row ? 1 : 0) + 15) / 16) * 16;
+  const int vt_rows = a->sum_row ? dv_pad : a->d;
+  if (a->p_f16 && !a->sum_row) { set_error("sdb_attention: p_f16 needs sum_row"); return SDB_ERR_ARG; }
+  if (a->sum_row && (a->causal || a->d > 112)) {
+    set_error("sdb_attention: sum_row is implemented by the two-tile kernel only (no causal mask, d <= 112)");
+    return SDB_ERR_UNSUPPORTED;
+  }
   {
-    uint64_t dims[3] = {(uint64_t)vt_ld, (uint64_t)a->NB, (uint64_t)a->heads * a->d};
+    uint64_t dims[3] = {(uint64_t)vt_ld, (uint64_t)a->NB, (uint64_t)a->heads * vt_rows};
     uint64_t str[2] = {(uint64_t)vt_ld * 2, (uint64_t)vt_ld * 2 * a->NB};
     uint32_t box[3] = {64, 1, (uint32_t)dv_pad};
     if ((rc = make_tmap_bf16(&p.map_vt, a->vt, 3, dims, str, box, "attention V^T"))) return rc;
@@ -584,6 +683,9 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.dchunks = (a->d + 63) / 64;
   p.dk_steps = (a->d + 15) / 16;
   p.dv_pad = dv_pad;
+  p.vt_rows = vt_rows;
+  p.sum_col = a->sum_row ? a->d : -1;
+  p.p_f16 = a->p_f16;
   const int q_bytes = p.dchunks * ATT_CHUNK_BYTES;
   const int stage_bytes = p.dchunks * ATT_CHUNK_BYTES + 2 * dv_pad * 128;
   static bool configured[64] = {false};
@@ -600,13 +702,18 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     }
   }
   // two 128-query tiles per CTA when the accumulators fit (d <= 128) and there is more than one tile
-  const int smem2 = 2 * q_bytes + ATT2_STAGES * stage_bytes + 1024 + 256;
-  const bool two_tile = !a->causal && a->d <= 128 && a->S > ATT_BQ && smem2 <= 227 * 1024 && a->variant != 1;
+  int stages2 = (227 * 1024 - 2 * q_bytes - 1024 - 256) / stage_bytes;
+  if (stages2 > ATT2_MAX_STAGES) stages2 = ATT2_MAX_STAGES;
+  p.stages = stages2;
+  const int smem2 = stages2 >= 2 ? 2 * q_bytes + stages2 * stage_bytes + 1024 + 256 : (1 << 30);
+  const bool two_tile = !a->causal && a->d <= 128 && (a->S > ATT_BQ || a->sum_row) && smem2 <= 227 * 1024 &&
+                        (a->variant != 1 || a->sum_row);
   if (two_tile) {
     dim3 grid((unsigned)((a->S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)), (unsigned)a->heads, (unsigned)a->NB);
     attn2_tc_kernel<<<grid, ATT2_THREADS, smem2, (cudaStream_t)stream>>>(p);
     return check_launch("attn2_tc_kernel");
   }
+  if (a->sum_row) { set_error("sdb_attention: sum_row does not fit the two-tile kernel for d = %d", a->d); return SDB_ERR_UNSUPPORTED; }
   const int smem_bytes = q_bytes + 2 * stage_bytes + 1024 + 256;
   if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((a->S + ATT_BQ - 1) / ATT_BQ), (unsigned)a->heads, (unsigned)a->NB);

@@ -64,6 +64,7 @@ struct GemmTcParams {
   void* out;
   long long ldo;
   int out_fp32;
+  int out_f16;             // 16-bit output is IEEE half instead of bf16 (V^T for the f16 attention variant)
   const float* bias;
   int bias_mode;           // 0 none, 1 per column, 2 per row
   const void* residual;    // bf16, or fp32 when res_fp32
@@ -505,7 +506,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             for (int i = 0; i < 8; ++i)
               if (mrow[i] >= 0)
                 *reinterpret_cast<uint2*>(ob + (long long)mrow[i] * p.ldo) =
-                    make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+                    p.out_f16 ? make_uint2(pack_f16x2(x[i].x, x[i].y), pack_f16x2(x[i].z, x[i].w))
+                              : make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
           }
         } else {
   #pragma unroll
@@ -867,6 +869,12 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.out = a->out;
   p.ldo = a->ldo ? a->ldo : a->Cout;
   p.out_fp32 = a->out_fp32;
+  p.out_f16 = a->out_f16;
+  if (a->out_f16 && ((reinterpret_cast<uintptr_t>(a->out) & 7u) != 0 || a->residual != nullptr ||
+                     a->out_fp32 || a->nsplit > 1 || (a->Cout % 32) != 0 || ((a->ldo ? a->ldo : a->Cout) % 4) != 0)) {
+    set_error("sdb_gemm_tc: out_f16 needs a 16-bit output, no split-K, Cout %% 32 == 0 and ldo %% 4 == 0");
+    return SDB_ERR_UNSUPPORTED;
+  }
   p.bias = a->bias;
   p.bias_mode = a->bias ? (a->bias_per_row ? 2 : 1) : 0;
   p.residual = a->residual;

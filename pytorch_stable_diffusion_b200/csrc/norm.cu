@@ -30,16 +30,18 @@ __device__ __forceinline__ void load8(const void* base, long long elem_off, int 
   }
 }
 
-// Thread layout shared by stats and apply: V = (C0+C1)/8 16-byte vectors per pixel; a block holds
+// Thread layout shared by stats and apply: V = (C0+C1)/8 8-channel vectors per pixel; a block holds
 // `lanes` pixels side by side, thread t -> (vector t % V, pixel lane t / V). Each thread keeps the
 // same 8 channels for its whole life, so per-channel state lives in registers.
-// grid = (chunks, NB); every block walks pixels [chunk*ppc, (chunk+1)*ppc).
+// grid = (chunks, NB); every block walks pixels [chunk*ppc, (chunk+1)*ppc), four pixels per thread in
+// flight. Statistics are deterministic: every block writes its per-group partial sums to
+// stats[n][chunk][g][2] (no atomics, nothing to zero) and the apply kernel adds the chunks in order.
+constexpr int GN_MAX_CHUNKS = 128;
+
 __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
                                 double* __restrict__ stats, long long HW, int C0, int C1, int groups,
                                 long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
-  // per-thread partial sums, [lanes][ctot] each for sum and sum of squares; reduced per group in a
-  // fixed order so that a block's contribution does not depend on thread scheduling
-  extern __shared__ float s_part[];
+  extern __shared__ float s_part[];     // [lanes][ctot] sums, then [lanes][ctot] sums of squares
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int v = t % V;
@@ -61,7 +63,17 @@ __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restr
     for (int j = 0; j < 8; ++j) { sum[j] = 0.f; sq[j] = 0.f; }
     const long long p_begin = (long long)blockIdx.x * ppc;
     const long long p_end = min(HW, p_begin + ppc);
-    for (long long p = p_begin + pl; p < p_end; p += lanes) {
+    long long p = p_begin + pl;
+    for (; p + 3LL * lanes < p_end; p += 4LL * lanes) {
+      float f[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(src, base + (p + (long long)u * lanes) * stride, src_fp32, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sum[j] += f[u][j]; sq[j] += f[u][j] * f[u][j]; }
+    }
+    for (; p < p_end; p += lanes) {
       float f[8];
       load8(src, base + p * stride, src_fp32, f);
 #pragma unroll
@@ -80,9 +92,9 @@ __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restr
       const float* pq = s_sq + l * ctot + g * cpg;
       for (int c = 0; c < cpg; ++c) { a += (double)ps[c]; b += (double)pq[c]; }
     }
-    double* dst = stats + ((long long)n * groups + g) * 2;
-    atomicAdd(dst, a);
-    atomicAdd(dst + 1, b);
+    double* dst = stats + (((long long)n * GN_MAX_CHUNKS + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 
@@ -90,31 +102,43 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
                                 const double* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                 long long HW, int C0, int C1, int groups, float eps, int silu,
-                                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
+                                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32,
+                                int stat_chunks) {
+  __shared__ float s_mean[64];
+  __shared__ float s_rstd[64];
   const int n = blockIdx.y;
   const int t = threadIdx.x;
+  const int ctot = C0 + C1;
+  const int cpg = ctot / groups;
+  // fixed-order sum of the per-chunk partial statistics of this sample
+  for (int g = t; g < groups; g += blockDim.x) {
+    double s = 0.0, ss = 0.0;
+    const double* src = stats + ((long long)n * GN_MAX_CHUNKS * groups + g) * 2;
+    for (int c = 0; c < stat_chunks; ++c) {
+      s += src[(long long)c * groups * 2];
+      ss += src[(long long)c * groups * 2 + 1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = ss / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
   const int v = t % V;
   const int pl = t / V;
   if (pl >= lanes) return;
   const int V0 = C0 >> 3;
-  const int ctot = C0 + C1;
-  const int cpg = ctot / groups;
-  const double cnt = (double)HW * cpg;
   float sc[8], sh[8];
   const int c0 = v * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
     const int g = c / cpg;
-    const double s = stats[((long long)n * groups + g) * 2];
-    const double ss = stats[((long long)n * groups + g) * 2 + 1];
-    const double mean = s / cnt;
-    double var = ss / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float ga = gamma[c], be = beta[c];
-    sc[j] = rstd * ga;
-    sh[j] = be - (float)mean * rstd * ga;
+    sc[j] = s_rstd[g] * ga;
+    sh[j] = be - s_mean[g] * s_rstd[g] * ga;
   }
   const bool second = v >= V0;
   const void* src = second ? x1 : x0;
@@ -125,7 +149,23 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
   __nv_bfloat16* obase = out + (long long)n * HW * ctot + c0;
   const long long p_begin = (long long)blockIdx.x * ppc;
   const long long p_end = min(HW, p_begin + ppc);
-  for (long long p = p_begin + pl; p < p_end; p += lanes) {
+  long long p = p_begin + pl;
+  for (; p + 3LL * lanes < p_end; p += 4LL * lanes) {
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load8(src, base + (p + (long long)u * lanes) * stride, src_fp32, f[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = f[u][j] * sc[j] + sh[j];
+        if (silu) y = silu_f(y);
+        f[u][j] = y;
+      }
+      *reinterpret_cast<uint4*>(obase + (p + (long long)u * lanes) * ctot) = pack8(f[u]);
+    }
+  }
+  for (; p < p_end; p += lanes) {
     float f[8];
     load8(src, base + p * stride, src_fp32, f);
 #pragma unroll
@@ -193,6 +233,79 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
   }
 }
 
+// fp32 rows, float4 loads, two rows per warp iteration (more bytes in flight per SM), grid-stride over
+// row pairs. VPL = float4 vectors per lane = ceil(C / 128).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, void* __restrict__ out, long long rows, int C,
+                     float eps, int out_fp32) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int V = C >> 2;
+  const float invC = 1.0f / (float)C;
+  for (long long pair = warp0; pair * 2 < rows; pair += nwarps) {
+    float4 f[2][VPL];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long row = pair * 2 + r;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        f[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < V && row < rows) {
+          const float* src = x + row * C + v * 4;
+          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(f[r][i].x), "=f"(f[r][i].y), "=f"(f[r][i].z), "=f"(f[r][i].w)
+                       : "l"(src));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long row = pair * 2 + r;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) sum += (f[r][i].x + f[r][i].y) + (f[r][i].z + f[r][i].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + i * 32 < V) {
+          const float a = f[r][i].x - mean, b = f[r][i].y - mean, c = f[r][i].z - mean, d = f[r][i].w - mean;
+          sq += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * invC + eps);
+      if (row >= rows) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + v);
+          float4 y;
+          y.x = (f[r][i].x - mean) * rstd * g.x + b.x;
+          y.y = (f[r][i].y - mean) * rstd * g.y + b.y;
+          y.z = (f[r][i].z - mean) * rstd * g.z + b.z;
+          y.w = (f[r][i].w - mean) * rstd * g.w + b.w;
+          if (out_fp32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * C + v * 4) = y;
+          } else {
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * C + v * 4) =
+                make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+          }
+        }
+      }
+    }
+  }
+}
+
 // One block per row, the row staged in shared memory (cols * 4 bytes).
 __global__ void softmax_rows_kernel(const float* __restrict__ scores, __nv_bfloat16* __restrict__ probs,
                                     int cols, float scale_log2) {
@@ -254,6 +367,7 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
   long long want = (148LL * 4 + NB - 1) / NB;
   long long max_chunks = (HW + *lanes * 4 - 1) / (*lanes * 4);
   if (want > max_chunks) want = max_chunks;
+  if (want > GN_MAX_CHUNKS) want = GN_MAX_CHUNKS;
   if (want < 1) want = 1;
   *ppc = (HW + want - 1) / want;
   *chunks = (int)((HW + *ppc - 1) / *ppc);
@@ -261,6 +375,10 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
 }
 
 }  // namespace sdb
+
+extern "C" long long sdb_groupnorm_stats_bytes(int NB, int groups) {
+  return (long long)NB * sdb::GN_MAX_CHUNKS * groups * 2 * (long long)sizeof(double);
+}
 
 extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB,
                                    long long HW, int C0, int C1, int groups, int x0_fp32, int x1_fp32,
@@ -293,7 +411,7 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
                                    int x0_fp32, int x1_fp32, void* stream) {
   using namespace sdb;
   const int ctot = C0 + C1;
-  if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 ||
+  if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 || groups > 64 ||
       ctot % groups != 0 || C0 % 8 != 0 || C1 % 8 != 0 || (C1 > 0 && !x1)) {
     set_error("sdb_groupnorm_apply: bad arguments");
     return SDB_ERR_ARG;
@@ -305,7 +423,7 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
   }
   gn_apply_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
       x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V, lanes,
-      x0_fp32, x1_fp32);
+      x0_fp32, x1_fp32, chunks);
   return check_launch("gn_apply_kernel");
 }
 
@@ -317,6 +435,23 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
     return SDB_ERR_ARG;
   }
   const int warps = 8;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                         reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15u) == 0;
+  if (in_fp32 && aligned && C % 4 == 0 && C <= 1280) {
+    const int vpl = (C / 4 + 31) / 32;
+    long long blocks = ((rows + 1) / 2 + warps - 1) / warps;
+    const long long cap = 148LL * 8;
+    if (blocks > cap) blocks = cap;
+    const float* xf = reinterpret_cast<const float*>(x);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SDB_LN(V) layernorm_f32_kernel<V><<<(unsigned)blocks, warps * 32, 0, st>>>(xf, gamma, beta, out, rows, C, eps, out_fp32)
+    if (vpl <= 3) SDB_LN(3);
+    else if (vpl <= 5) SDB_LN(5);
+    else if (vpl <= 6) SDB_LN(6);
+    else SDB_LN(10);
+#undef SDB_LN
+    return check_launch("layernorm_f32_kernel");
+  }
   const long long blocks = (rows + warps - 1) / warps;
   layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
       x, gamma, beta, out, rows, C, eps, in_fp32, out_fp32);

@@ -202,10 +202,12 @@ class Diffusion(nn.Module, engine.EngineCache):
         if time.shape[0] != 1:
             raise ValueError("the time embedding is batch-independent: expected shape (1, 320)")
         tvec = eng.time_vectors(time.to(device=latent.device, dtype=torch.float32).contiguous())[0]
-        key = (context.data_ptr(), context._version, tuple(context.shape))
+        # cross-attention K / V^T depend only on the context: cached while the caller keeps passing the
+        # same (unmodified) tensor object. The cache holds a reference, so the storage cannot be reused
+        # by another tensor behind our back.
         cached = self.__dict__.get("_sdb_ctx")
-        if cached is None or cached[0] != key or cached[1] is not eng:
-            cached = (key, eng, eng.context_kv(context))
+        if (cached is None or cached[0] is not context or cached[1] != context._version or cached[2] is not eng):
+            cached = (context, context._version, eng, eng.context_kv(context))
             self.__dict__["_sdb_ctx"] = cached
         x = ops.nchw_to_nhwc_bf16(latent.to(torch.float32))
-        return ops.nhwc_to_nchw_f32(eng.forward_nhwc(x, tvec, cached[2]))
+        return ops.nhwc_to_nchw_f32(eng.forward_nhwc(x, tvec, cached[3]))

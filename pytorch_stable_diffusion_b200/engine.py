@@ -19,6 +19,13 @@ from . import ops
 
 CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
 
+# The reference's feed-forward is linear_geglu_2(linear_geglu_1(x)[..., :4C]) with NO non-linearity in
+# between (the GEGLU gate is computed and dropped, sd/diffusion.py:359-363), i.e. one affine map. With
+# FOLD_GEGLU the two weight matrices are composed once at pack time (fp64) into a single C x C matrix:
+# W = W2 . W1[:4C], b = W2 . b1[:4C] + b2 (SURVEY.md "Hard parts"; the FLOP numerator in bench.py drops
+# by the saved 179 GFLOP per image-step accordingly). Set to False to run the two GEMMs separately.
+FOLD_GEGLU = True
+
 
 # ------------------------------------------------------------------------------------------------
 # packing
@@ -105,9 +112,18 @@ def pack_unet_attn(m, dev):
     pk.wo2, pk.bo2 = pack_linear(m.attention_2.out_proj, dev)
     pk.ln3 = pack_norm(m.layernorm_3, dev)
     # the GEGLU gate half is dead in the reference (sd/diffusion.py:359-363): keep the first 4C rows only
-    pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev)
-    pk.bg1 = _f32(m.linear_geglu_1.bias[:4 * c], dev)
-    pk.wg2, pk.bg2 = pack_linear(m.linear_geglu_2, dev)
+    if FOLD_GEGLU:
+        w1 = m.linear_geglu_1.weight.detach()[:4 * c].to(device=dev, dtype=torch.float64)
+        b1 = m.linear_geglu_1.bias.detach()[:4 * c].to(device=dev, dtype=torch.float64)
+        w2 = m.linear_geglu_2.weight.detach().to(device=dev, dtype=torch.float64)
+        b2 = m.linear_geglu_2.bias.detach().to(device=dev, dtype=torch.float64)
+        pk.wg = (w2 @ w1).to(torch.bfloat16).contiguous()
+        pk.bg = (w2 @ b1 + b2).to(torch.float32).contiguous()
+        pk.wg1 = None
+    else:
+        pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev)
+        pk.bg1 = _f32(m.linear_geglu_1.bias[:4 * c], dev)
+        pk.wg2, pk.bg2 = pack_linear(m.linear_geglu_2, dev)
     pk.cout_w, pk.cout_b = pack_conv1x1(m.conv_output, dev)
     return pk
 
@@ -234,8 +250,11 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True)
     # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
     l3 = ops.layernorm(t2, *pk.ln3)
-    g = ops.linear(l3, pk.wg1, bias=pk.bg1)
-    t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)          # only conv_output reads it: bf16
+    if pk.wg1 is None:
+        t3 = ops.linear(l3, pk.wg, bias=pk.bg, residual=t2)       # folded affine map; only conv_output reads it: bf16
+    else:
+        g = ops.linear(l3, pk.wg1, bias=pk.bg1)
+        t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)
     out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=x.f.view(m, c), out_fp32=True,
                      out2=True if want_b16 else None)
     return _stream(out, (n, h, w, c))

@@ -70,29 +70,51 @@ def _chk(t, dtype, name):
     return t
 
 
-def _choose_block_n(cout):
-    if cout % 256 == 0:
-        return 256
-    if cout % 160 == 0:
-        return 160
-    if cout % 128 == 0:
-        return 128
-    if cout >= 256:
-        return 256
-    return ((cout + 15) // 16) * 16
+def _mma_clks(n):
+    """Measured on B200 (tools/micro/mma_rate.cu): one tcgen05.mma M=128 K=16 costs max(88, N/2) cycles."""
+    return max(88.0, n / 2.0)
 
 
-def _choose_split(m_tiles, cout, block_n, nkb):
-    """Split the reduction when the output tiles alone cannot fill the 148 SMs."""
-    tiles = m_tiles * ((cout + block_n - 1) // block_n)
-    if tiles >= NUM_SMS // 2 or nkb < 16:
-        return 1
-    return max(1, min(NUM_SMS // tiles, nkb // 8, 16))
+def _choose_tiling(rows, cout, nkb, has_split_ws=True):
+    """(block_n, nsplit) minimising a wave-quantisation cost model over the persistent grid.
+
+    Tiles are 256 rows x block_n (CTA pairs, 74 slots on a 148-SM part) or 128 x block_n when there is
+    a single row tile. cost = rounds * (k-blocks per split * 4 MMAs + epilogue) [+ split-K finalize]."""
+    m_tiles = (rows + 127) // 128
+    cg = 2 if m_tiles >= 2 else 1
+    row_tiles = (m_tiles + cg - 1) // cg
+    slots = NUM_SMS // cg
+    cands = []
+    for bn in (256, 192, 160, 128, 96, 64):
+        if bn > cout and bn != ((cout + 15) // 16) * 16:
+            continue
+        cands.append(bn)
+    small = ((cout + 15) // 16) * 16
+    if small <= 256 and small not in cands:
+        cands.append(small)
+    best = None
+    for bn in cands:
+        n_tiles = (cout + bn - 1) // bn
+        waste = n_tiles * bn / float(cout)            # padded columns still cost MMA time
+        for ns in (1, 2, 3, 4, 6, 8):
+            if ns > 1 and (not has_split_ws or nkb < 16 * ns):
+                continue
+            per = (nkb + ns - 1) // ns
+            tiles = row_tiles * n_tiles * ((nkb + per - 1) // per)
+            rounds = (tiles + slots - 1) // slots
+            epi = 600.0 * ((bn + 31) // 32) / 2.0 + 1500.0
+            cost = rounds * (per * 4 * _mma_clks(bn) + 400.0 + epi * 0.25)
+            if ns > 1:                                 # fp32 partials written + read back by the finalize kernel
+                cost += 2500.0 + rows * cout * 4.0 * (ns + 1) / (NUM_SMS * 16.0)
+            cost *= 1.0 + 0.02 * (waste - 1.0)
+            if best is None or cost < best[0]:
+                best = (cost, bn, ns)
+    return best[1], best[2]
 
 
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
-         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0):
+         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
     lib = _ext.lib()
     _chk(a0, torch.bfloat16, "a0")
@@ -129,7 +151,9 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.lda0, args.lda1, args.ldw, args.ldo, args.ldr = lda0, lda1, ldw, ldo, ldr
     if out is None:
         out = torch.empty((rows, cout), device=a0.device,
-                          dtype=torch.float32 if out_fp32 else torch.bfloat16)
+                          dtype=torch.float32 if out_fp32 else (torch.float16 if out_f16 else torch.bfloat16))
+    if out_f16:
+        nsplit = 1
     args.out = _p(out)
     args.out_fp32 = 1 if out_fp32 else 0
     if out2 is True:
@@ -137,18 +161,23 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.out2 = _p(out2)
     args.bias_per_row = 1 if bias_per_row else 0
     args.act = act
-    if block_n == 0:
-        block_n = _choose_block_n(cout)
-    args.block_n = block_n
     nkb = ntaps * ((c0 + 63) // 64 + (c1 + 63) // 64)
-    if nsplit == 0:
-        nsplit = _choose_split(m_tiles, cout, block_n, nkb)
+    if block_n == 0 or nsplit == 0:
+        bn_auto, ns_auto = _choose_tiling(rows, cout, nkb)
+        if block_n == 0:
+            block_n = bn_auto
+            if nsplit == 0:
+                nsplit = ns_auto
+        elif nsplit == 0:
+            nsplit = 1
+    args.block_n = block_n
     ws = None
     if nsplit > 1:
         ws = torch.empty((nsplit, rows, cout), device=a0.device, dtype=torch.float32)
         args.workspace = _p(ws)
     args.nsplit = nsplit
     args.cta_pair = cta_pair
+    args.out_f16 = 1 if out_f16 else 0
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
                2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size())
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
@@ -175,16 +204,18 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
 
 
 def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0,
-              variant=0):
+              variant=0, sum_row=False, p_f16=False):
     lib = _ext.lib()
     a = AttnArgs()
     a.q, a.k, a.vt, a.out = _p(_chk(q, torch.bfloat16, "q")), _p(_chk(k, torch.bfloat16, "k")), \
-        _p(_chk(vt, torch.bfloat16, "vt")), _p(_chk(out, torch.bfloat16, "out"))
+        _p(_chk(vt, torch.float16 if p_f16 else torch.bfloat16, "vt")), _p(_chk(out, torch.bfloat16, "out"))
     a.NB, a.heads, a.d, a.S, a.Skv, a.Skv_pad, a.vt_ld = NB, heads, d, S, Skv, Skv_pad, vt_ld
     a.ldq, a.ldk, a.ldo = ldq, ldk, ldo
     a.causal = 1 if causal else 0
     a.scale = 1.0 / math.sqrt(d)
     a.variant = variant
+    a.sum_row = 1 if sum_row else 0
+    a.p_f16 = 1 if p_f16 else 0
     ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
                2.0 * NB * heads * d * (2 * S + 2 * Skv))
     _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")
@@ -202,11 +233,10 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
     c0 = x0.shape[-1]
     hw = x0.numel() // (n * c0)
     c1 = x1.shape[-1] if x1 is not None else 0
-    stats = torch.empty((n, groups, 2), device=x0.device, dtype=torch.float64)
+    stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
     ev = _prof("groupnorm", 0.0, 2.0 * in_bytes + 2.0 * (nel0 + nel1))
-    _ext.check(lib.sdb_fill_zero(_p(stats), stats.numel() * 8, _stream()), "sdb_fill_zero")
     _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
                "sdb_groupnorm_stats")
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)

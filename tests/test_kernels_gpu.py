@@ -62,6 +62,9 @@ def test_linear_epilogue_bias_act_residual():
     report("linear+bias+qgelu+res", out, ref * torch.sigmoid(1.702 * ref) + r.float(), 1e-2)
     out = ops.linear(a, w, bias=b, out_fp32=True)
     report("linear fp32 out", out, ref, 2e-3)
+    out = ops.linear(a, w, bias=b, out_f16=True)
+    assert out.dtype == torch.float16
+    report("linear f16 out", out, ref, 2e-3)
 
 
 def test_linear_small_n_fp32_and_row_bias():
@@ -261,6 +264,38 @@ def test_attention(N, heads, d, S, Skv, causal, amp):
     vf = v.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
     ref = ref_attention(qf, kf, vf, causal).transpose(1, 2).reshape(N * S, C)
     report(f"attention d={d} S={S} Skv={Skv} causal={causal}", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("d,S,Skv,p_f16", [
+    (40, 4096, 4096, False), (40, 4096, 4096, True), (80, 1024, 1024, False), (80, 1024, 1024, True),
+    (40, 1024, 77, False), (40, 1024, 77, True), (80, 576, 576, True), (40, 64, 64, True), (40, 1024, 1024, True),
+])
+def test_attention_sum_row(d, S, Skv, p_f16):
+    """Denominator accumulated by the P.V product through a ones row in V^T; optionally f16x2 exps."""
+    ops = _ops()
+    setup_exact_fp32()
+    N, heads = 2, 8
+    C = heads * d
+    R = (d + 1 + 15) // 16 * 16
+    Skv_pad = (Skv + 7) // 8 * 8
+    amp = 3.0 if (S == 1024 and Skv == 1024) else 1.0
+    q = (rnd(N * S, C) * amp).bfloat16()
+    k = (rnd(N, Skv_pad, C, seed=1) * amp).bfloat16()
+    v = rnd(N, Skv_pad, C, seed=2).bfloat16()
+    vt = torch.zeros(heads, R, N, Skv_pad, device=DEV, dtype=torch.bfloat16)
+    vt[:, :d] = v.view(N, Skv_pad, heads, d).permute(2, 3, 0, 1)
+    vt[:, d] = 1.0
+    vt = vt.view(heads * R, N, Skv_pad).contiguous()
+    if p_f16:
+        vt = vt.to(torch.float16)          # exact: bf16 values of this magnitude are representable in half
+    out = torch.empty(N * S, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k.view(N * Skv_pad, C), vt, out, NB=N, heads=heads, d=d, S=S, Skv=Skv,
+                  Skv_pad=Skv_pad, ldq=C, ldk=C, ldo=C, sum_row=True, p_f16=p_f16)
+    qf = q.float().view(N, S, heads, d).transpose(1, 2)
+    kf = k.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
+    vf = v.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
+    ref = ref_attention(qf, kf, vf, False).transpose(1, 2).reshape(N * S, C)
+    report(f"attention sum_row d={d} S={S} Skv={Skv} p_f16={p_f16}", out, ref, 1e-2)
 
 
 # ------------------------------------------------------------------------------------ elementwise

@@ -18,6 +18,7 @@ from pytorch_stable_diffusion_b200 import _ext, ops  # noqa: E402
 
 DEV = "cuda"
 PAIR = 0
+ATTN_MODE = 0     # 0 plain, 1 ones-row denominator, 2 ones-row + f16x2 exponentials
 
 
 def bf(*shape, scale=1.0):
@@ -56,12 +57,16 @@ def cases(B):
         skv_pad = (Skv + 7) // 8 * 8
         q = bf(N * S, c)
         k = bf(N * skv_pad, c)
-        vt = bf(c, N * skv_pad)
+        sr = ATTN_MODE > 0 and d <= 112
+        rows = heads * ((d + 16) // 16 * 16) if sr else c
+        vt = bf(rows, N * skv_pad)
+        if sr and ATTN_MODE > 1:
+            vt = vt.to(torch.float16)
         o = torch.empty(N * S, c, device=DEV, dtype=torch.bfloat16)
         fl = 4.0 * N * heads * S * Skv * d
         out.append((f"attn_{name}_S{S}_kv{Skv}_d{d}", count, fl,
                     lambda: ops.attention(q, k, vt, o, NB=N, heads=heads, d=d, S=S, Skv=Skv, Skv_pad=skv_pad,
-                                          ldq=c, ldk=c, ldo=c)))
+                                          ldq=c, ldk=c, ldo=c, sum_row=sr, p_f16=sr and ATTN_MODE > 1)))
 
     for S, C in ((4096, 320), (1024, 640), (256, 1280)):
         lin("proj", S, C, C, 15, res=True, fp32=True)     # out_proj x2, q_proj, conv_in/out
@@ -101,9 +106,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--json", default="")
     ap.add_argument("--pair", type=int, default=0, help="0 auto, 1 single-CTA tiles, 2 CTA pairs")
+    ap.add_argument("--attn-mode", type=int, default=0, help="0 plain, 1 ones-row denominator, 2 + f16x2 exps")
     args = ap.parse_args()
-    global PAIR
+    global PAIR, ATTN_MODE
     PAIR = args.pair
+    ATTN_MODE = args.attn_mode
     torch.manual_seed(0)
     scratch = torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
     rows = []

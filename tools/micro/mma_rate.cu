@@ -35,7 +35,11 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int iters, int 
         mbar_wait(&done_bar, 1, 98);
         tc_fence_after();
       }
-      for (int k = 0; k < kper; ++k) mma_ss(tmem, a_desc + (uint64_t)(2 * (k & 3)), b_desc + (uint64_t)(2 * (k & 3)), idesc, 1u);
+      if (mode & 4) {                       // A operand from TMEM (columns 256..), as the P.V product of attention
+        for (int k = 0; k < kper; ++k) mma_ts(tmem, tmem + 256 + 8 * (k & 7), b_desc + (uint64_t)(2 * (k & 3)), idesc, 1u);
+      } else {
+        for (int k = 0; k < kper; ++k) mma_ss(tmem, a_desc + (uint64_t)(2 * (k & 3)), b_desc + (uint64_t)(2 * (k & 3)), idesc, 1u);
+      }
       if (mode & 1) {                       // per-k-block commit to a ring barrier (nobody waits on it)
         tc_commit(&ring[s]);
         if (++s == 8) s = 0;
@@ -56,10 +60,10 @@ int main() {
   long long* d;
   cudaMalloc(&d, 16);
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  const int ns[] = {64, 128, 160, 256};
-  for (int mode = 0; mode < 4; ++mode)
+  const int ns[] = {48, 64, 96, 128, 160, 256};
+  for (int mode = 0; mode < 8; mode += 4)
   for (int n : ns) {
-    const int iters = 500, kper = 4;
+    const int iters = 250, kper = 8;
     mma_rate_kernel<<<1, 128, 60 * 1024>>>(n, iters, kper, mode, d);
     cudaDeviceSynchronize();
     mma_rate_kernel<<<1, 128, 60 * 1024>>>(n, iters, kper, mode, d);
