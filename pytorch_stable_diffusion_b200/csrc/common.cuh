@@ -323,7 +323,14 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// SiLU = x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU (tanh.approx, rel. error ~2^-11, below the
+// bf16 rounding of every consumer) instead of an exponential plus a division.
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 }  // namespace sdb

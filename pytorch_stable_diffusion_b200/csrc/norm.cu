@@ -106,17 +106,24 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
                                 int stat_chunks) {
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
+  extern __shared__ double s_stat[];     // [stat_chunks][groups][2] partial statistics of this sample
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int ctot = C0 + C1;
   const int cpg = ctot / groups;
-  // fixed-order sum of the per-chunk partial statistics of this sample
+  // all threads fetch the per-chunk partials in parallel (one L2 round trip), then one thread per group
+  // adds them in chunk order: the result does not depend on scheduling
+  {
+    const double* src = stats + (long long)n * GN_MAX_CHUNKS * groups * 2;
+    const int total = stat_chunks * groups * 2;
+    for (int i = t; i < total; i += blockDim.x) s_stat[i] = src[i];
+  }
+  __syncthreads();
   for (int g = t; g < groups; g += blockDim.x) {
     double s = 0.0, ss = 0.0;
-    const double* src = stats + ((long long)n * GN_MAX_CHUNKS * groups + g) * 2;
     for (int c = 0; c < stat_chunks; ++c) {
-      s += src[(long long)c * groups * 2];
-      ss += src[(long long)c * groups * 2 + 1];
+      s += s_stat[(c * groups + g) * 2];
+      ss += s_stat[(c * groups + g) * 2 + 1];
     }
     const double cnt = (double)HW * cpg;
     const double mean = s / cnt;
@@ -421,7 +428,14 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
     set_error("sdb_groupnorm_apply: unsupported channel count %d", ctot);
     return SDB_ERR_UNSUPPORTED;
   }
-  gn_apply_kernel<<<dim3(chunks, NB), threads, 0, (cudaStream_t)stream>>>(
+  const size_t smem_apply = (size_t)chunks * groups * 2 * sizeof(double);
+  static bool apply_configured = false;
+  if (!apply_configured) {
+    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double));
+    apply_configured = true;
+  }
+  gn_apply_kernel<<<dim3(chunks, NB), threads, smem_apply, (cudaStream_t)stream>>>(
       x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V, lanes,
       x0_fp32, x1_fp32, chunks);
   return check_launch("gn_apply_kernel");

@@ -68,6 +68,36 @@ def cases(B):
                     lambda: ops.attention(q, k, vt, o, NB=N, heads=heads, d=d, S=S, Skv=Skv, Skv_pad=skv_pad,
                                           ldq=c, ldk=c, ldo=c, sum_row=sr, p_f16=sr and ATTN_MODE > 1)))
 
+    def gnorm(name, Hh, C0, C1, count, fp32=True):
+        x0 = torch.randn(N, Hh, Hh, C0, device=DEV)
+        x0 = x0 if fp32 else x0.bfloat16()
+        x1 = torch.randn(N, Hh, Hh, C1, device=DEV) if C1 else None
+        g = torch.randn(C0 + C1, device=DEV)
+        b = torch.randn(C0 + C1, device=DEV)
+        nbytes = (2 * (4 if fp32 else 2) + 2) * N * Hh * Hh * C0 + (2 * 4 + 2) * N * Hh * Hh * C1
+        out.append((f"groupnorm_{name}_{C0 + C1}_{Hh}_{'f32' if fp32 else 'bf16'}", count, nbytes * 1e3,   # "flops" column = bytes*1e3 -> reads as GB/s
+                    lambda: ops.groupnorm(x0, g, b, x1=x1, silu=True)))
+
+    def lnorm(S, C, count):
+        x = torch.randn(N * S, C, device=DEV)
+        g = torch.randn(C, device=DEV)
+        b = torch.randn(C, device=DEV)
+        out.append((f"layernorm_{N * S}x{C}", count, 6.0 * N * S * C * 1e3, lambda: ops.layernorm(x, g, b)))
+
+    gnorm("x", 64, 320, 0, 13)
+    gnorm("hid", 64, 320, 0, 7, fp32=False)
+    gnorm("cat", 64, 320, 320, 2)
+    gnorm("x", 32, 640, 0, 8)
+    gnorm("hid", 32, 640, 0, 6, fp32=False)
+    gnorm("cat", 32, 640, 640, 2)
+    gnorm("x", 16, 1280, 0, 8)
+    gnorm("hid", 16, 1280, 0, 6, fp32=False)
+    gnorm("cat", 16, 1280, 1280, 3)
+    gnorm("x", 8, 1280, 0, 6)
+    gnorm("cat", 8, 1280, 1280, 3)
+    lnorm(4096, 320, 15)
+    lnorm(1024, 640, 15)
+    lnorm(256, 1280, 15)
     for S, C in ((4096, 320), (1024, 640), (256, 1280)):
         lin("proj", S, C, C, 15, res=True, fp32=True)     # out_proj x2, q_proj, conv_in/out
         lin("qk", S, C, 2 * C, 5)
