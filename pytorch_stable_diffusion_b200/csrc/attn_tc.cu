@@ -40,22 +40,27 @@ struct AttnParams {
   int sum_col;   // column of O that accumulates the softmax denominator (V^T ones row), or -1
   int p_f16;     // P is stored as f16 (exponentials taken two at a time in f16x2) instead of bf16
   int stages;    // K/V ring depth of the two-tile kernel (2 or 3)
+  int tmem_cols; // one-tile kernel: TMEM columns to allocate (256 lets two CTAs share an SM)
+  int o_col;     // one-tile kernel: first TMEM column of O
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // pure: let the compiler schedule it freely
   return y;
 }
 // two exponentials per MUFU operation: (lo, hi) fp32 -> f16x2 -> 2^x in f16x2
 __device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
   uint32_t h, y;
-  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
   return y;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// Up to two CTAs per SM: with a single key block (cross-attention over the 77 CLIP tokens) S needs no
+// double buffer, the CTA allocates 256 TMEM columns and a second CTA hides the load -> MMA -> softmax ->
+// MMA -> store latency chain of the first.
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -72,7 +77,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   const int stage_bytes = k_bytes + 2 * v_chunk_bytes;
   uint8_t* q_smem = smem;
   uint8_t* kv_smem = smem + q_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + 2 * stage_bytes);
+  const int kv_stages = (p.tmem_cols == 256) ? 1 : 2;      // a single key block needs one stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + kv_stages * stage_bytes);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -102,14 +108,14 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base + 256;
+  const uint32_t tmem_o = tmem_base + (uint32_t)p.o_col;
 
   if (warp == 0) {
     // ===================== TMA producer
@@ -276,7 +282,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 
@@ -706,15 +712,19 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   if (stages2 > ATT2_MAX_STAGES) stages2 = ATT2_MAX_STAGES;
   p.stages = stages2;
   const int smem2 = stages2 >= 2 ? 2 * q_bytes + stages2 * stage_bytes + 1024 + 256 : (1 << 30);
+  // a single key block (cross-attention): two light one-tile CTAs per SM beat one two-tile CTA
+  const bool single_block = (a->Skv <= ATT_BKV) && dv_pad <= 128 && !a->sum_row;
+  p.tmem_cols = single_block ? 256 : 512;
+  p.o_col = single_block ? 128 : 256;
   const bool two_tile = !a->causal && a->d <= 128 && (a->S > ATT_BQ || a->sum_row) && smem2 <= 227 * 1024 &&
-                        (a->variant != 1 || a->sum_row);
+                        (a->variant != 1 || a->sum_row) && !(single_block && a->variant != 2);
   if (two_tile) {
     dim3 grid((unsigned)((a->S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)), (unsigned)a->heads, (unsigned)a->NB);
     attn2_tc_kernel<<<grid, ATT2_THREADS, smem2, (cudaStream_t)stream>>>(p);
     return check_launch("attn2_tc_kernel");
   }
   if (a->sum_row) { set_error("sdb_attention: sum_row does not fit the two-tile kernel for d = %d", a->d); return SDB_ERR_UNSUPPORTED; }
-  const int smem_bytes = q_bytes + 2 * stage_bytes + 1024 + 256;
+  const int smem_bytes = q_bytes + (single_block ? 1 : 2) * stage_bytes + 1024 + 256;
   if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((a->S + ATT_BQ - 1) / ATT_BQ), (unsigned)a->heads, (unsigned)a->NB);
   attn_tc_kernel<<<grid, ATT_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
