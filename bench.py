@@ -244,6 +244,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def mark(msg):
+        if os.environ.get("SDB_BENCH_DEBUG"):
+            torch.cuda.synchronize()
+            print(f"[bench rank {rank}] {msg} fault={_ext.read_fault()}", file=sys.stderr, flush=True)
+
     if args.profile_only:
         with torch.no_grad():
             eng = models["diffusion"]._engine()
@@ -260,14 +265,18 @@ def main():
     with torch.no_grad():
         # ---- warm-up (first call captures the CUDA graph of the 50-step loop)
         n_before_capture = _ext.launch_count()
+        mark("inputs ready")
         t_cap = time.perf_counter()
         img = step_device()
         torch.cuda.synchronize()
         t_cap = time.perf_counter() - t_cap
+        mark("first step (graph captured)")
         loop = next(iter(pipeline._GRAPH_CACHE.values()))
         for _ in range(args.warmup - 1):
             img = step_device()
+        mark("warm-up done")
         barrier()
+        mark("barrier passed")
 
         # ---- timed region: K steps, inputs already in HBM
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -282,6 +291,7 @@ def main():
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        mark("timed region done")
         eager_launches = _ext.launch_count() - n0
         clk = clocks.stop()
         graph_launches = loop.graph_launches
@@ -409,5 +419,20 @@ def main():
     return 0
 
 
+def _run():
+    # The contract is ONE JSON line on stdout. Libraries (NCCL's version banner, for one) write to file
+    # descriptor 1 on their own, so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    # the saved original.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    sys.stdout = out
+    try:
+        return main()
+    finally:
+        out.flush()
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(_run())

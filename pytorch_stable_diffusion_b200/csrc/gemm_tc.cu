@@ -154,7 +154,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const int b_stage_bytes = b_rows * GEMM_BK * 2;
   const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES);
+  // [staging: one chunk per epilogue warp][residual ring: GEMM_RES_RING chunks per warp, if any][barriers]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(
+      epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)));
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                // [2] accumulator drained (leader's copy is used)
