@@ -275,6 +275,65 @@ def test_generate_50_steps_vs_reference_golden(models, oracle):
     assert p >= 35.0
 
 
+def test_768_config(models, weights, oracle):
+    """BASELINE.json configs[4]: 768x768 (4x96x96 latent, 9216/2304/576/144-token attention): one UNet
+    evaluation and a 2-step generate against the oracle on the same device."""
+    from pytorch_stable_diffusion_b200 import pipeline
+    from pytorch_stable_diffusion_b200.pipeline import get_time_embedding
+    gen = torch.Generator().manual_seed(31)
+    lat = torch.randn(2, 4, 96, 96, generator=gen).to(DEV)
+    ctx = torch.randn(2, 77, 768, generator=gen).to(DEV)
+    temb = get_time_embedding(640).to(DEV)
+    with torch.no_grad():
+        ref = oracle.diffusion_forward(weights["diffusion"], lat, ctx, temb)
+        report("Diffusion 96x96 latent (768^2)", models["diffusion"](lat, ctx, temb), ref, TOL)
+    cond, uncond = canonical_tokens()
+    ref_img, _ = oracle.generate(weights, cond, uncond, seed=42, n_inference_steps=2, latent_hw=(96, 96), device=DEV)
+    img = pipeline.generate("a", "b", models=models, seeds=[42], n_inference_steps=2, device=DEV,
+                            tokenizer=StubTokenizer(), height=768, width=768)
+    assert img.shape == (768, 768, 3)
+    p = _psnr(oracle, img, ref_img)
+    print(f"[768^2 txt2img 2 steps] PSNR vs oracle = {p:.2f} dB", flush=True)
+    assert p >= 35.0
+
+
+def test_generate_without_cfg_and_prompt_lists(models, weights, oracle):
+    """do_cfg=False (sd/pipeline.py:123-131) and per-sample prompts in one batch."""
+    from pytorch_stable_diffusion_b200 import pipeline
+    cond, uncond = canonical_tokens()
+    ref_img, _ = oracle.generate(weights, cond, None, seed=7, n_inference_steps=3, do_cfg=False, device=DEV)
+    img = pipeline.generate("a", None, do_cfg=False, models=models, seeds=[7], n_inference_steps=3, device=DEV,
+                            tokenizer=StubTokenizer())
+    p = _psnr(oracle, img, ref_img)
+    print(f"[do_cfg=False 3 steps] PSNR vs oracle = {p:.2f} dB", flush=True)
+    assert p >= 35.0
+    # two samples with swapped prompt roles == the two single-sample runs
+    kw = dict(models=models, n_inference_steps=2, device=DEV, tokenizer=StubTokenizer(), return_all=True)
+    both = pipeline.generate(["a", "b"], ["b", "a"], seeds=[5, 6], batch_size=2, **kw)
+    one = pipeline.generate("b", "a", seeds=[6], batch_size=1, **kw)
+    p = oracle.psnr_u8(both[1], one[0])
+    print(f"[prompt list, sample 1 vs single run] PSNR = {p:.2f} dB", flush=True)
+    assert p >= 38.0
+
+
+def test_sampler_device_paths(oracle):
+    """DDPMSampler.step / add_noise on CUDA tensors run the fused kernels and match the oracle."""
+    from pytorch_stable_diffusion_b200.ddpm import DDPMSampler
+    g = torch.Generator(device=DEV).manual_seed(3)
+    s = DDPMSampler(g)
+    s.set_inference_timesteps(50)
+    lat = torch.randn(2, 4, 16, 16, device=DEV)
+    eps = torch.randn(2, 4, 16, 16, device=DEV)
+    g2 = torch.Generator(device=DEV).manual_seed(3)
+    noise = torch.randn(eps.shape, generator=g2, device=DEV)
+    osm = oracle.OracleDDPM(lambda shape: noise)
+    osm.set_inference_timesteps(50)
+    report("DDPMSampler.step t=500", s.step(500, lat, eps), osm.step(500, lat, eps), 1e-5)
+    report("DDPMSampler.step t=0", s.step(0, lat, eps), osm.step(0, lat, eps), 1e-5)
+    g.manual_seed(3)
+    report("DDPMSampler.add_noise", s.add_noise(lat, torch.tensor([780])), osm.add_noise(lat, 780), 1e-5)
+
+
 def test_generate_errors(models):
     from pytorch_stable_diffusion_b200 import pipeline
     with pytest.raises(ValueError):
