@@ -27,18 +27,20 @@ class LaunchProfiler:
     def __init__(self):
         self.records = []
 
-    def begin(self, name, flops=0.0, nbytes=0.0):
+    def begin(self, name, flops=0.0, nbytes=0.0, shape=None):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        self.records.append([name, float(flops), float(nbytes), e0, e1])
+        self.records.append([name, float(flops), float(nbytes), e0, e1, shape])
         return e1
 
-    def summary(self):
+    def summary(self, by_shape=False):
+        """{name (or (name, shape)): launches, ms, flops, bytes} over the recorded launches."""
         torch.cuda.synchronize()
         out = {}
-        for name, flops, nbytes, e0, e1 in self.records:
-            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for name, flops, nbytes, e0, e1, shape in self.records:
+            key = (name, shape) if by_shape else name
+            d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
@@ -49,8 +51,8 @@ class LaunchProfiler:
 PROFILER = None
 
 
-def _prof(name, flops=0.0, nbytes=0.0):
-    return PROFILER.begin(name, flops, nbytes) if PROFILER is not None else None
+def _prof(name, flops=0.0, nbytes=0.0, shape=None):
+    return PROFILER.begin(name, flops, nbytes, shape) if PROFILER is not None else None
 
 
 def _prof_end(ev):
@@ -179,7 +181,8 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.cta_pair = cta_pair
     args.out_f16 = 1 if out_f16 else 0
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
-               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size())
+               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size(),
+               shape=f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps}")
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
     _prof_end(ev)
     return (out, out2) if out2 is not None else out
