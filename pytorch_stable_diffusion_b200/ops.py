@@ -181,7 +181,9 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.cta_pair = cta_pair
     args.out_f16 = 1 if out_f16 else 0
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
-               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size(),
+               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size()
+               + (rows * cout * residual.element_size() if residual is not None else 0)
+               + (rows * cout * 2 if out2 is not None else 0),
                shape=f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps}")
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
     _prof_end(ev)
