@@ -255,7 +255,7 @@ def main():
             ctx = models["clip"](tokens)[idx]
             kvs = eng.context_kv(ctx)
             tv = eng.time_vectors(temb)
-            x = ops.nchw_to_nhwc_bf16(latents, repeat=2)
+            x = ops.nchw_to_nhwc(latents, repeat=2, out_fp32=True)
             eng.forward_nhwc(x, tv[0], kvs)
             models["decoder"].decode_nhwc(latents[:1])
         torch.cuda.synchronize()
@@ -387,7 +387,9 @@ def main():
                         "algorithmic_bytes_per_launch": dv["bytes"] / dv["launches"],
                         "us_per_launch": 1e3 * d_ms, "share_of_unet_eval": dv["ms"] / unet_eager_ms}
 
-            t_bound = [kv for kv in gshapes if kv[1]["flops"] / max(kv[1]["bytes"], 1.0) >= ridge]
+            # the north-star's named kernel is the implicit-GEMM 3x3 conv (60 % of the UNet's FLOPs)
+            t_bound = [kv for kv in gshapes if kv[0][0] == "gemm_tc_conv3x3" and
+                       kv[1]["flops"] / max(kv[1]["bytes"], 1.0) >= ridge]
             h_bound = [kv for kv in gshapes if kv[1]["flops"] / max(kv[1]["bytes"], 1.0) < ridge]
             roof = roof_of(max(t_bound, key=lambda kv: kv[1]["ms"]), "tensor")
             roof["all_gemm_tc_launches"] = {"launches": gemm_n, "ms": gemm_ms,
@@ -398,6 +400,10 @@ def main():
                              "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] else None}
                          for k, v in sorted(summ.items())}
             breakdown["unet_eval_eager_ms"] = round(unet_eager_ms, 3)
+            breakdown["gemm_shapes"] = [
+                {"shape": f"{k[0]} {k[1]}", "launches": v["launches"], "us": round(1e3 * v["ms"] / v["launches"], 1),
+                 "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)}
+                for k, v in sorted(gshapes, key=lambda kv: -kv[1]["ms"])[:24]]
 
     fault = _ext.read_fault()
     if fault:

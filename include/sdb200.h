@@ -144,10 +144,11 @@ int sdb_nhwc_to_nchw_f32(const void* x, float* out, int NB, int C, int H, int W,
 /* Nearest-neighbour x2 (F.interpolate sd/diffusion.py:430; nn.Upsample sd/decoder.py:269). */
 int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int W, int C, void* stream);
 /* Direct convolution for tiny channel counts (Cin <= 8 or Cout <= 8): k in {1, 3}, stride 1,
- * pad (k-1)/2. x bf16 NHWC, w fp32 [Cout][k*k][Cin], out bf16 or fp32 NHWC; out2 = optional bf16
- * copy next to an fp32 out (or NULL). sd/diffusion.py:545; sd/decoder.py:235,239; sd/encoder.py:56,92. */
+ * pad (k-1)/2. x NHWC bf16 (fp32 when in_fp32), w fp32 [Cout][k*k][Cin], out bf16 or fp32 NHWC; out2 =
+ * optional bf16 copy next to an fp32 out (or NULL). sd/diffusion.py:545; sd/decoder.py:235,239;
+ * sd/encoder.py:56,92. */
 int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2, int NB,
-                    int H, int W, int Cin, int Cout, int ksize, int out_fp32, void* stream);
+                    int H, int W, int Cin, int Cout, int ksize, int out_fp32, int in_fp32, void* stream);
 /* y[r, n] = act_out( sum_k act_in(x[r, k]) * W[n, k] + bias[n] ), fp32 activations, bf16 weights.
  * The time path: TimeEmbedding (sd/diffusion.py:64-76) and SiLU+linear_time (:184-187). */
 int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R, int K,
@@ -156,10 +157,10 @@ int sdb_small_linear(const float* x, const void* w, const float* bias, float* ou
  * sd/ddpm.py:102-139). eps: fp32 NHWC (NCHW when eps_nchw) [2*NB (or NB when !do_cfg), H, W, C]; latents/noise: fp32
  * NCHW [NB, C, H, W]; coef: device fp32 [steps][5] = {sqrt(1-abar_t), sqrt(abar_t), c_x0, c_xt,
  * sigma_t}; writes latents in place and the next UNet input (bf16 NHWC, batch tiled x2 when
- * do_cfg) to next_in when non-NULL. */
+ * do_cfg; fp32 when next_fp32) to next_in when non-NULL. */
 int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise, const float* coef,
                       int step, float cfg_scale, int do_cfg, void* next_in, int NB, int C, int H,
-                      int W, int eps_nchw, void* stream);
+                      int W, int eps_nchw, int next_fp32, void* stream);
 /* VAE_AttentionBlock tail as the reference computes it (sd/decoder.py:62-71): the (n, hw, c)
  * attention output is re-viewed raw as (n, c, h, w) and added to the residual.
  * y bf16, res fp32, out fp32 (+ optional bf16 copy out2), all NHWC [NB, HW, C].
@@ -178,8 +179,8 @@ int sdb_axpby(const float* x, const float* y, float* out, float a, float b, long
 /* Post-processing (sd/pipeline.py:253-259): fp32 NHWC in [-1,1] -> uint8 NHWC, rescale to
  * [0,255], clamp, truncating cast. */
 int sdb_image_to_uint8(const float* x, unsigned char* out, long long n, void* stream);
-/* Pre-processing (sd/pipeline.py:162-173): uint8 HWC -> bf16 NHWC in [-1,1]. */
-int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, void* stream);
+/* Pre-processing (sd/pipeline.py:162-173): uint8 HWC -> NHWC in [-1,1], bf16 or (out_fp32) fp32. */
+int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, int out_fp32, void* stream);
 /* CLIPEmbedding (sd/clip.py:58-63): out[b, t, :] = table[tokens[b, t]] + pos[t]; rows
  * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out fp32 [NB, T_pad, D]. */
 int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,

@@ -52,16 +52,16 @@ SIGNATURES = {
     "sdb_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_upsample2x_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_conv_direct": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                        c_int, c_int, c_void_p],
+                        c_int, c_int, c_int, c_void_p],
     "sdb_small_linear": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_cfg_ddpm_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int,
-                          c_int, c_int, c_int, c_int, c_void_p],
+                          c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_vae_attn_scramble_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
     "sdb_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_vae_encode_tail": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sdb_axpby": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_ll, c_void_p],
     "sdb_image_to_uint8": [c_void_p, c_void_p, c_ll, c_void_p],
-    "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_void_p],
+    "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong,

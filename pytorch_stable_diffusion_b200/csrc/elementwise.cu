@@ -72,10 +72,10 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 // Direct convolution, Cin <= 8: one thread = one output pixel x 8 output channels; the weights sit in
 // shared memory transposed to [k*k*Cin][Cout] so a warp reads consecutive words.
 template <int KS>
-__global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void conv_direct_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ bias, void* __restrict__ out,
                                    __nv_bfloat16* __restrict__ out2, int NB, int H, int W, int Cin,
-                                   int Cout, int out_fp32) {
+                                   int Cout, int out_fp32, int in_fp32) {
   extern __shared__ float s_w[];  // [KS*KS*Cin][CoutPad]
   const int CoutPad = (Cout + 7) & ~7;
   const int K = KS * KS * Cin;
@@ -106,10 +106,11 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ x, const fl
       for (int kx = 0; kx < KS; ++kx) {
         const int wi = wo + kx - PAD;
         if (wi < 0 || wi >= W) continue;
-        const __nv_bfloat16* px = x + (((long long)n * H + hi) * W + wi) * Cin;
+        const long long poff = (((long long)n * H + hi) * W + wi) * Cin;
         const float* wk = s_w + (long long)((ky * KS + kx) * Cin) * CoutPad + g * 8;
         for (int ci = 0; ci < Cin; ++ci) {
-          const float a = __bfloat162float(px[ci]);
+          const float a = in_fp32 ? reinterpret_cast<const float*>(x)[poff + ci]
+                                  : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[poff + ci]);
           const float4 w0 = *reinterpret_cast<const float4*>(wk + ci * CoutPad);
           const float4 w1 = *reinterpret_cast<const float4*>(wk + ci * CoutPad + 4);
           acc[0] += a * w0.x; acc[1] += a * w0.y; acc[2] += a * w0.z; acc[3] += a * w0.w;
@@ -160,8 +161,8 @@ __global__ void small_linear_kernel(const float* __restrict__ x, const __nv_bflo
 __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* __restrict__ eps,
                                      const float* __restrict__ noise, const float* __restrict__ coef,
                                      int step, float cfg_scale, int do_cfg,
-                                     __nv_bfloat16* __restrict__ next_in, int NB, int C, int H, int W,
-                                     int eps_nchw) {
+                                     void* __restrict__ next_in, int NB, int C, int H, int W,
+                                     int eps_nchw, int next_fp32) {
   const long long hw = (long long)H * W;
   const long long total = (long long)NB * C * hw;
   const float sb = coef[step * 5 + 0];   // sqrt(1 - abar_t)
@@ -190,9 +191,16 @@ __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* _
     if (sigma != 0.f && noise != nullptr) xn += sigma * noise[i];
     latents[i] = xn;
     if (next_in != nullptr) {
-      const __nv_bfloat16 b = __float2bfloat16_rn(xn);
-      next_in[e_idx] = b;
-      if (do_cfg) next_in[e_idx + (long long)NB * hw * C] = b;
+      if (next_fp32) {
+        float* ni = reinterpret_cast<float*>(next_in);
+        ni[e_idx] = xn;
+        if (do_cfg) ni[e_idx + (long long)NB * hw * C] = xn;
+      } else {
+        __nv_bfloat16* ni = reinterpret_cast<__nv_bfloat16*>(next_in);
+        const __nv_bfloat16 b = __float2bfloat16_rn(xn);
+        ni[e_idx] = b;
+        if (do_cfg) ni[e_idx + (long long)NB * hw * C] = b;
+      }
     }
   }
 }
@@ -271,15 +279,16 @@ __global__ void image_to_uint8_kernel(const float* __restrict__ x, unsigned char
   }
 }
 
-__global__ void uint8_to_image_kernel(const unsigned char* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                      long long n) {
+__global__ void uint8_to_image_kernel(const unsigned char* __restrict__ x, void* __restrict__ out,
+                                      long long n, int out_fp32) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float v = (float)x[i];
     v -= 0.0f;
     v *= (2.0f / 255.0f);
     v += -1.0f;
-    out[i] = __float2bfloat16_rn(v);
+    if (out_fp32) reinterpret_cast<float*>(out)[i] = v;
+    else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
   }
 }
 
@@ -356,7 +365,7 @@ extern "C" int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int 
 
 extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2,
                                int NB, int H, int W, int Cin, int Cout, int ksize, int out_fp32,
-                               void* stream) {
+                               int in_fp32, void* stream) {
   if (!x || !w || !out || NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 ||
       (ksize != 1 && ksize != 3) || (out2 && !out_fp32)) {
     set_error("sdb_conv_direct: bad arguments (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
@@ -376,10 +385,10 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (ksize == 1)
     conv_direct_kernel<1><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
-        (const __nv_bfloat16*)x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32);
+        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
   else
     conv_direct_kernel<3><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
-        (const __nv_bfloat16*)x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32);
+        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
   return check_launch("conv_direct_kernel");
 }
 
@@ -398,13 +407,13 @@ extern "C" int sdb_small_linear(const float* x, const void* w, const float* bias
 extern "C" int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise,
                                  const float* coef, int step, float cfg_scale, int do_cfg,
                                  void* next_in, int NB, int C, int H, int W, int eps_nchw,
-                                 void* stream) {
+                                 int next_fp32, void* stream) {
   if (!latents || !eps || !coef || step < 0 || NB <= 0 || C <= 0 || H <= 0 || W <= 0) {
     set_error("sdb_cfg_ddpm_step: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * C * H * W;
   cfg_ddpm_step_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
-      latents, eps, noise, coef, step, cfg_scale, do_cfg, (__nv_bfloat16*)next_in, NB, C, H, W, eps_nchw);
+      latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in, NB, C, H, W, eps_nchw, next_fp32);
   return check_launch("cfg_ddpm_step_kernel");
 }
 
@@ -448,9 +457,9 @@ extern "C" int sdb_image_to_uint8(const float* x, unsigned char* out, long long 
   return check_launch("image_to_uint8_kernel");
 }
 
-extern "C" int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, void* stream) {
+extern "C" int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, int out_fp32, void* stream) {
   if (!x || !out || n <= 0) { set_error("sdb_uint8_to_image: bad arguments"); return SDB_ERR_ARG; }
-  uint8_to_image_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, (__nv_bfloat16*)out, n);
+  uint8_to_image_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, out, n, out_fp32);
   return check_launch("uint8_to_image_kernel");
 }
 

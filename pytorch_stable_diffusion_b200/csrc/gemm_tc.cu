@@ -55,8 +55,13 @@ struct GemmTcParams {
   // epilogue
   int N;                   // valid output columns (Cout)
   int block_n;             // UMMA N (multiple of 16, <= 256)
-  int acc_stride;          // TMEM columns between the two accumulators (power of two >= block_n)
-  int tmem_cols;           // 2 * acc_stride
+  int acc_stride;          // TMEM columns between the two accumulator buffers (power of two >= block_n)
+  int tmem_cols;           // 2 * acc_stride (512 in wide mode)
+  int n_acc;               // 1: one UMMA of N = block_n per k-step, two TMEM buffers (tile i+1 accumulates while
+                           //    tile i drains). 2 ("wide"): block_n = 2 * acc_n, two UMMAs per k-step sharing the
+                           //    A tile, accumulators at TMEM columns 0 and 256, ONE buffer: fewer TMA bytes per
+                           //    MMA cycle (the narrow 256 x 160 pair tile is TMA-bound), epilogue not overlapped
+  int acc_n;               // UMMA N (= block_n / n_acc)
   int stages;
   int a_tx_bytes;          // bytes one A box delivers (bw*bh*bn rows of 128 B)
   int nsplit;              // split-K factor
@@ -150,9 +155,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const bool leader = (cta_rank == 0);
   const int first_tile = blockIdx.x / CG;
   const int tile_step = gridDim.x / CG;
-  const int b_rows = p.block_n / CG;                     // W rows this CTA stages per k-block
-  const int b_stage_bytes = b_rows * GEMM_BK * 2;
+  const int b_rows = p.acc_n / CG;                       // W rows this CTA stages per k-block and accumulator
+  const int b_sub_bytes = b_rows * GEMM_BK * 2;
+  const int b_stage_bytes = p.n_acc * b_sub_bytes;
   const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
+  const int nbuf = (p.n_acc == 2) ? 1 : 2;               // TMEM accumulator buffers
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
   // [staging: one chunk per epilogue warp][residual ring: GEMM_RES_RING chunks per warp, if any][barriers]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(
@@ -230,10 +237,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             if (p.a_rank == 2) tma_load_2d_pair(ma, &full_bar[s], a_dst, c, t.w0);
             else tma_load_5d_pair(ma, &full_bar[s], a_dst, ca, cw, c2, chh, t.nb0);
             tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst, wk, wn);
+            if (p.n_acc == 2) tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
           } else {
             if (p.a_rank == 2) tma_load_2d(ma, &full_bar[s], a_dst, c, t.w0);
             else tma_load_5d(ma, &full_bar[s], a_dst, ca, cw, c2, chh, t.nb0);
             tma_load_2d(&p.map_w, &full_bar[s], b_dst, wk, wn);
+            if (p.n_acc == 2) tma_load_2d(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
           }
         }
         __syncwarp();
@@ -245,7 +254,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer: warp 1 of the leader CTA, one elected lane issues
     if (leader) {
-      const uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, (uint32_t)p.block_n);
+      const uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, (uint32_t)p.acc_n);
+      const uint64_t b_half = (uint64_t)(b_sub_bytes >> 4);
+      const bool wide = (p.n_acc == 2);
       const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem));
       const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + GEMM_A_STAGE_BYTES);
       const uint32_t stage_step = (uint32_t)(stage_bytes >> 4);
@@ -255,9 +266,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       int lt = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
-        const int acc = lt & 1;
+        const int acc = wide ? 0 : (lt & 1);
         trace_stamp(trc, lt, 2);
-        if (lt >= 2) mbar_wait(&tempty_bar[acc], ((lt >> 1) - 1) & 1, 4);
+        if (lt >= nbuf) mbar_wait(&tempty_bar[acc], (uint32_t)((lt / nbuf) - 1) & 1u, 4);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         uint32_t accum = 0;
@@ -274,12 +285,24 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
               mma_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
               mma_ss_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
               mma_ss_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              if (wide) {            // second accumulator (TMEM column 256): same A tile, next acc_n W rows
+                mma_ss_pair(d_tmem + 256, a_desc, b_desc + b_half, idesc, accum);
+                mma_ss_pair(d_tmem + 256, a_desc + 2, b_desc + b_half + 2, idesc, 1u);
+                mma_ss_pair(d_tmem + 256, a_desc + 4, b_desc + b_half + 4, idesc, 1u);
+                mma_ss_pair(d_tmem + 256, a_desc + 6, b_desc + b_half + 6, idesc, 1u);
+              }
               tc_commit_pair(&empty_bar[s], 3);
             } else {
               mma_ss(d_tmem, a_desc, b_desc, idesc, accum);
               mma_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
               mma_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
               mma_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+              if (wide) {
+                mma_ss(d_tmem + 256, a_desc, b_desc + b_half, idesc, accum);
+                mma_ss(d_tmem + 256, a_desc + 2, b_desc + b_half + 2, idesc, 1u);
+                mma_ss(d_tmem + 256, a_desc + 4, b_desc + b_half + 4, idesc, 1u);
+                mma_ss(d_tmem + 256, a_desc + 6, b_desc + b_half + 6, idesc, 1u);
+              }
               tc_commit(&empty_bar[s]);
             }
           }
@@ -387,12 +410,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     int lt = 0;
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
       const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
-      const int acc = lt & 1;
+      const int acc = (p.n_acc == 2) ? 0 : (lt & 1);
       const int ch_first = (half + lt) & 1;     // alternate so both halves get the odd chunk in turn
       int mrow[8];
       rows_for(t, mrow);
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
-      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1, 3);
+      mbar_wait(&tfull_bar[acc], (uint32_t)(lt / nbuf) & 1u, 3);
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 6); trace_epi(trc, lt, 1); }
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
@@ -414,7 +437,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           }
         }
         uint32_t v[32];
-        tmem_ld32(t_addr + (uint32_t)(ch * 32), v);
+        // wide mode: chunks [0, acc_n/32) live at TMEM column 0, the rest at column 256
+        const int cpa = p.acc_n >> 5;
+        tmem_ld32(t_addr + (uint32_t)((p.n_acc == 2 && ch >= cpa) ? 256 + (ch - cpa) * 32 : ch * 32), v);
         if (res_async) issue_prefetch();                       // chunk seq + GEMM_RES_RING - 1
         // long-K tiles keep their shared memory for pipeline stages: the residual of this chunk is
         // requested here and lands while the accumulator is loaded and staged
@@ -822,13 +847,15 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     else if (a->Cout >= 256) block_n = 256;
     else block_n = ((a->Cout + 15) / 16) * 16;
   }
-  if (block_n % 16 != 0 || block_n < 16 || block_n > 256) {
+  if ((block_n % 16 != 0 || block_n < 16 || block_n > 256) && block_n != 320) {
     set_error("sdb_gemm_tc: block_n %d invalid", block_n);
     return SDB_ERR_ARG;
   }
   p.block_n = block_n;
-  p.acc_stride = pow2_cols(((block_n + 31) / 32) * 32);
-  p.tmem_cols = 2 * p.acc_stride;
+  p.n_acc = (block_n == 320) ? 2 : 1;                     // wide tiles: two accumulators of 160 columns
+  p.acc_n = block_n / p.n_acc;
+  p.acc_stride = p.n_acc == 2 ? 512 : pow2_cols(((block_n + 31) / 32) * 32);
+  p.tmem_cols = p.n_acc == 2 ? 512 : 2 * p.acc_stride;
   const int n_tiles = (a->Cout + block_n - 1) / block_n;
   // CTA pairs (cta_group::2, 256-row tiles) whenever there are at least two row tiles
   int cg = (m_tiles >= 2) ? 2 : 1;
@@ -838,12 +865,12 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)a->Cout};
     const long long ldw = a->ldw ? a->ldw : p.ktot;
     uint64_t str[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {64, (uint32_t)(block_n / cg)};
+    uint32_t box[2] = {64, (uint32_t)(p.acc_n / cg)};
     if ((rc = make_tmap_bf16(&p.map_w, a->w, 2, dims, str, box, "gemm W"))) return rc;
   }
 
   // ---- pipeline depth from the shared-memory budget
-  const int stage_bytes = GEMM_A_STAGE_BYTES + (block_n / cg) * GEMM_BK * 2;
+  const int stage_bytes = GEMM_A_STAGE_BYTES + p.n_acc * (p.acc_n / cg) * GEMM_BK * 2;
   // fp32 residuals stream through a cp.async ring (3 chunks per epilogue warp) when 16-byte aligned
   const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
   const int want_split = a->nsplit > 1;
@@ -853,9 +880,15 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   const int nkb_all = p.ntaps * p.cblocks;
   p.res_async = (res_vec && nkb_all <= 32) ? 1 : 0;
   p.res_direct = (res_vec && !p.res_async) ? 1 : 0;
-  const int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)) + 1024 + 256;
   const int smem_budget = (a->smem_budget > 0 && a->smem_budget < 227 * 1024) ? a->smem_budget : 227 * 1024;
+  int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)) + 1024 + 256;
   int stages = (smem_budget - fixed_bytes) / stage_bytes;
+  if (stages < 2 && p.res_async) {          // the residual ring does not fit next to two stages: direct loads
+    p.res_async = 0;
+    p.res_direct = 1;
+    fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + 256;
+    stages = (smem_budget - fixed_bytes) / stage_bytes;
+  }
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) { set_error("sdb_gemm_tc: shared-memory budget too small"); return SDB_ERR_ARG; }
   const int nkb_total = p.ntaps * p.cblocks;

@@ -110,10 +110,11 @@ def _conv2d_kernel(conv, x):
     """A bare nn.Conv2d entry (stem / stride-2 downsample) executed by the conv kernels."""
     _require_cuda(x, "Conv2d")
     dev = x.device
-    xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
     if conv.in_channels <= 8:
+        xn = ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True)
         pk = engine.pack_direct(conv, dev)
         return ops.nhwc_to_nchw_f32(ops.conv_direct(xn, pk.w, pk.b, pk.cout, pk.k, out_fp32=True))
+    xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
     w, b = engine.pack_conv3x3(conv, dev)
     kind = ops.GEMM_CONV3X3_S2 if conv.stride[0] == 2 else ops.GEMM_CONV3X3_S1
     return ops.nhwc_to_nchw_f32(ops.conv3x3(xn, w, conv.out_channels, bias=b, kind=kind, out_fp32=True))
@@ -209,5 +210,5 @@ class Diffusion(nn.Module, engine.EngineCache):
         if (cached is None or cached[0] is not context or cached[1] != context._version or cached[2] is not eng):
             cached = (context, context._version, eng, eng.context_kv(context))
             self.__dict__["_sdb_ctx"] = cached
-        x = ops.nchw_to_nhwc_bf16(latent.to(torch.float32))
+        x = ops.nchw_to_nhwc(latent.to(torch.float32), out_fp32=True)
         return ops.nhwc_to_nchw_f32(eng.forward_nhwc(x, tvec, cached[3]))

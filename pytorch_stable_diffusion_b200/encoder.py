@@ -38,5 +38,5 @@ class VAE_Encoder(nn.Sequential, engine.EngineCache):
         (sd/encoder.py:95-155: right/bottom pad before the stride-2 convs, reparameterisation,
         x0.18215)."""
         _require_cuda(x, "VAE_Encoder")
-        xn = ops.nchw_to_nhwc_bf16(x.to(torch.float32))
+        xn = ops.nchw_to_nhwc(x.to(torch.float32), out_fp32=True)
         return self._engine().forward_from_nhwc(xn, noise.to(device=x.device, dtype=torch.float32))

@@ -183,7 +183,8 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
     n, h, w, c0 = x.shape
     c1 = x1.shape[-1] if x1 is not None else 0
     a = ops.groupnorm(x.f, pk.gn1_w, pk.gn1_b, x1=x1.f if x1 is not None else None, silu=True)
-    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b)
+    # the hidden tensor stays fp32: it is only ever read by GroupNorm, never as a tensor-core operand
+    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b, out_fp32=True)
     a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True)
     if pk.skip_w is None:
         res = x.f.view(-1, c0)
@@ -303,7 +304,7 @@ def _reads_bf16(kind, pk):
     """Does program entry (kind, pk) read its stream input as a bf16 tensor-core operand?"""
     if kind == "res":
         return pk.skip_w is not None
-    return kind in ("up", "conv", "conv1", "attn_vae", "direct")
+    return kind in ("up", "conv", "conv1", "attn_vae")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -404,7 +405,7 @@ class UNetEngine:
         return x
 
     def forward_nhwc(self, x, tvec, kvs):
-        """x bf16 [N, h, w, 4]; tvec fp32 [sum(Cout)] (one row of time_vectors); returns eps fp32
+        """x fp32 (or bf16) NHWC [N, h, w, 4]; tvec fp32 [sum(Cout)] (one row of time_vectors); returns eps fp32
         NHWC [N, h, w, 4]. UNET.forward sd/diffusion.py:628-676 without materialising torch.cat."""
         kv_iter = iter(kvs)
         skips = []
@@ -470,7 +471,7 @@ def _run_vae_sequential(prog, x):
         elif kind == "attn_vae":
             x = run_vae_attn(pk, x)
         elif kind == "direct":
-            src = x.bf16() if isinstance(x, Stream) else x
+            src = x.f if isinstance(x, Stream) else x          # the direct convolution reads fp32 or bf16
             o = ops.conv_direct(src, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=True)
             x = Stream(*o)
         elif kind == "conv1":
@@ -501,7 +502,7 @@ class VAEDecoderEngine:
 
     def forward_nhwc(self, latents):
         """latents fp32 NCHW [B, 4, h, w] -> image fp32 NHWC [B, 8h, 8w, 3] (x / 0.18215 first)."""
-        x = ops.nchw_to_nhwc_bf16(latents, scale=1.0 / 0.18215)
+        x = ops.nchw_to_nhwc(latents, scale=1.0 / 0.18215, out_fp32=True)
         return _run_vae_sequential(self.prog, x)
 
 
@@ -513,7 +514,7 @@ class VAEEncoderEngine:
         self.prog = _pack_vae_sequential(encoder, dev, pad_rb=True)
 
     def forward_from_nhwc(self, x, noise):
-        """x bf16 NHWC [B, H, W, 3]; noise fp32 NCHW [B, 4, H/8, W/8] -> latents fp32 NCHW."""
+        """x fp32 (or bf16) NHWC [B, H, W, 3]; noise fp32 NCHW [B, 4, H/8, W/8] -> latents fp32 NCHW."""
         moments = _run_vae_sequential(self.prog, x)
         return ops.vae_encode_tail(moments, noise)
 

@@ -72,43 +72,58 @@ def _chk(t, dtype, name):
     return t
 
 
-def _mma_clks(n):
-    """Measured on B200 (tools/micro/mma_rate.cu): one tcgen05.mma M=128 K=16 costs max(88, N/2) cycles."""
-    return max(88.0, n / 2.0)
+import os as _os
+_NO_WIDE = _os.environ.get("SDB_NO_WIDE") == "1"     # A/B switch: never pick the wide (320-column) tiles
 
 
-def _choose_tiling(rows, cout, nkb, has_split_ws=True):
-    """(block_n, nsplit) minimising a wave-quantisation cost model over the persistent grid.
+def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
+    """(block_n, nsplit) from a per-SM cycle model of gemm_tc_kernel, calibrated on B200 timelines
+    (tools/gemm_trace.py, tools/micro/mma_rate.cu):
 
-    Tiles are 256 rows x block_n (CTA pairs, 74 slots on a 148-SM part) or 128 x block_n when there is
-    a single row tile. cost = rounds * (k-blocks per split * 4 MMAs + epilogue) [+ split-K finalize]."""
+      * one tcgen05.mma (M=128 per CTA, K=16) costs max(88, N/2) cycles;
+      * the TMA engine of an SM delivers ~63 B/clk: a k-block of a narrow tile moves 16 KiB of A plus
+        N/cg rows of W, which makes 256 x 160 pair tiles TMA-bound (414 instead of 354 cycles);
+      * narrow tiles (two TMEM buffers) overlap the epilogue with the next tile but pay a ~3000-cycle
+        pipeline refill at every tile start; wide tiles (block_n = 320: two 160-column accumulators sharing
+        the A tile, one buffer) are MMA-bound but their epilogue is exposed;
+      * an epilogue moves its bytes at ~20 B/clk per SM (HBM share).
+
+    Tiles are 256 rows (CTA pairs, 74 slots on a 148-SM part) or 128 rows when there is one row tile."""
     m_tiles = (rows + 127) // 128
     cg = 2 if m_tiles >= 2 else 1
     row_tiles = (m_tiles + cg - 1) // cg
     slots = NUM_SMS // cg
-    cands = []
-    for bn in (256, 192, 160, 128, 96, 64):
-        if bn > cout and bn != ((cout + 15) // 16) * 16:
-            continue
-        cands.append(bn)
-    small = ((cout + 15) // 16) * 16
-    if small <= 256 and small not in cands:
-        cands.append(small)
+    if cout % 160 == 0:
+        # the UNet's channel counts (320 / 640 / 1280): 160-column tiles waste nothing and were tuned on
+        # the timelines; 256-column tiles lose to them through padding and wave quantisation
+        cands = [160]
+    else:
+        cands = [bn for bn in (256, 192, 160, 128, 96, 64) if bn <= cout]
+        small = ((cout + 15) // 16) * 16
+        if small <= 256 and small not in cands:
+            cands.append(small)
+    if cout % 320 == 0 and not _NO_WIDE:
+        cands.append(320)
     best = None
     for bn in cands:
         n_tiles = (cout + bn - 1) // bn
-        waste = n_tiles * bn / float(cout)            # padded columns still cost MMA time
         for ns in (1, 2, 3, 4, 6, 8):
-            if ns > 1 and (not has_split_ws or nkb < 16 * ns):
+            if ns > 1 and nkb < 16 * ns:
                 continue
             per = (nkb + ns - 1) // ns
             tiles = row_tiles * n_tiles * ((nkb + per - 1) // per)
             rounds = (tiles + slots - 1) // slots
-            epi = 600.0 * ((bn + 31) // 32) / 2.0 + 1500.0
-            cost = rounds * (per * 4 * _mma_clks(bn) + 400.0 + epi * 0.25)
+            epi_bytes = 128.0 * bn * ((4 if ns > 1 else out_bytes) + (0 if ns > 1 else res_bytes))
+            epi = epi_bytes / 20.0 + 1500.0
+            if bn == 320:
+                tile = per * 8 * 88.0 + 1500.0 + epi
+            else:
+                tma = (16384.0 + (bn // cg) * 128.0) / 63.0
+                mma = 4.0 * max(88.0, bn / 2.0)
+                tile = max(per * max(tma, mma) + 3000.0, epi)
+            cost = rounds * tile
             if ns > 1:                                 # fp32 partials written + read back by the finalize kernel
-                cost += 2500.0 + rows * cout * 4.0 * (ns + 1) / (NUM_SMS * 16.0)
-            cost *= 1.0 + 0.02 * (waste - 1.0)
+                cost += 6000.0 + rows * cout * 4.0 * (ns + 1) / (NUM_SMS * 20.0)
             if best is None or cost < best[0]:
                 best = (cost, bn, ns)
     return best[1], best[2]
@@ -165,7 +180,9 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.act = act
     nkb = ntaps * ((c0 + 63) // 64 + (c1 + 63) // 64)
     if block_n == 0 or nsplit == 0:
-        bn_auto, ns_auto = _choose_tiling(rows, cout, nkb)
+        ob = (4 if out_fp32 else 2) + (2 if out2 is not None else 0)
+        rb = 0 if residual is None else residual.element_size()
+        bn_auto, ns_auto = _choose_tiling(rows, cout, nkb, ob, rb)
         if block_n == 0:
             block_n = bn_auto
             if nsplit == 0:
@@ -309,15 +326,16 @@ def upsample2x(x):
 
 
 def conv_direct(x, w, bias, cout, ksize, out_fp32=False, out2=False):
-    """x bf16 NHWC with Cin <= 8; w fp32 [Cout, k*k, Cin]. out2=True also returns a bf16 copy of an
-    fp32 output."""
+    """x NHWC (bf16 or fp32) with Cin <= 8; w fp32 [Cout, k*k, Cin]. out2=True also returns a bf16 copy
+    of an fp32 output."""
     lib = _ext.lib()
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device,
                       dtype=torch.float32 if out_fp32 else torch.bfloat16)
     o2 = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bfloat16) if out2 else None
     _ext.check(lib.sdb_conv_direct(_p(x), _p(w), _p(bias), _p(out), _p(o2), n, h, wd, cin, cout, ksize,
-                                   1 if out_fp32 else 0, _stream()), "sdb_conv_direct")
+                                   1 if out_fp32 else 0, 1 if x.dtype == torch.float32 else 0, _stream()),
+               "sdb_conv_direct")
     return (out, o2) if out2 else out
 
 
@@ -336,7 +354,9 @@ def cfg_ddpm_step(latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in, e
     lib = _ext.lib()
     n, c, h, w = latents.shape
     _ext.check(lib.sdb_cfg_ddpm_step(_p(latents), _p(eps), _p(noise), _p(coef), step, float(cfg_scale),
-                                     1 if do_cfg else 0, _p(next_in), n, c, h, w, 1 if eps_nchw else 0, _stream()),
+                                     1 if do_cfg else 0, _p(next_in), n, c, h, w, 1 if eps_nchw else 0,
+                                     1 if (next_in is not None and next_in.dtype == torch.float32) else 0,
+                                     _stream()),
                "sdb_cfg_ddpm_step")
     return latents
 
@@ -393,10 +413,11 @@ def image_to_uint8(x):
     return out
 
 
-def uint8_to_image(x):
+def uint8_to_image(x, out_fp32=False):
     lib = _ext.lib()
-    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _ext.check(lib.sdb_uint8_to_image(_p(x), _p(out), x.numel(), _stream()), "sdb_uint8_to_image")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    _ext.check(lib.sdb_uint8_to_image(_p(x), _p(out), x.numel(), 1 if out_fp32 else 0, _stream()),
+               "sdb_uint8_to_image")
     return out
 
 

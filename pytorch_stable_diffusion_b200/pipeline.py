@@ -68,7 +68,7 @@ class _Loop:
         self.eng, self.B, self.n_steps, self.do_cfg, self.cfg_scale = eng, B, n_steps, do_cfg, cfg_scale
         N = 2 * B if do_cfg else B
         self.latents = torch.zeros((B, 4, h, w), device=device, dtype=torch.float32)
-        self.x_in = torch.zeros((N, h, w, 4), device=device, dtype=torch.bfloat16)
+        self.x_in = torch.zeros((N, h, w, 4), device=device, dtype=torch.float32)   # UNet input stays fp32
         self.noise = torch.zeros((n_steps, B, 4, h, w), device=device, dtype=torch.float32)
         self.coef = torch.zeros((n_steps, 5), device=device, dtype=torch.float32)
         self.tvecs = torch.zeros((n_steps, eng.time_total), device=device, dtype=torch.float32)
@@ -87,7 +87,7 @@ class _Loop:
             for (dk, dv), (k, v) in zip(self.kvs, kvs):
                 dk.copy_(k)
                 dv.copy_(v)
-        self.x_in.copy_(ops.nchw_to_nhwc_bf16(self.latents, repeat=2 if self.do_cfg else 1))
+        self.x_in.copy_(ops.nchw_to_nhwc(self.latents, repeat=2 if self.do_cfg else 1, out_fp32=True))
 
     def run_steps(self, trace=None, timesteps=None):
         for i in range(self.n_steps):
@@ -201,7 +201,7 @@ def generate(
             encoder.to(device)
             img = np.array(input_image.resize((W, H)))
             img_u8 = torch.tensor(img, dtype=torch.uint8, device=device).unsqueeze(0)
-            x = ops.uint8_to_image(img_u8.contiguous())              # bf16 NHWC in [-1, 1]
+            x = ops.uint8_to_image(img_u8.contiguous(), out_fp32=True)   # fp32 NHWC in [-1, 1]
             if B > 1:
                 x = x.expand(B, -1, -1, -1).contiguous()
             enc_noise = noise["encoder"].to(device) if noise is not None else _draw(

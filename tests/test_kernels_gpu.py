@@ -104,6 +104,22 @@ def test_linear_strided_and_dual_source_and_splitk():
     assert float(wide[:, :N].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("M,K,N", [(512, 640, 320), (1000, 320, 640), (256, 1280, 1280), (128, 320, 320)])
+def test_linear_wide_tiles(M, K, N):
+    """block_n = 320: two 160-column accumulators per tile sharing the A operand (single TMEM buffer)."""
+    ops = _ops()
+    setup_exact_fp32()
+    a = rnd(M, K).bfloat16()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    b = rnd(N, seed=2)
+    r = rnd(M, N, seed=3)
+    ref = a.float() @ w.float().t() + b
+    report(f"linear wide {M}x{K}x{N}", ops.linear(a, w, bias=b, block_n=320, nsplit=1), ref, 1e-2)
+    out, out2 = ops.linear(a, w, bias=b, residual=r, out_fp32=True, out2=True, block_n=320, nsplit=1)
+    report(f"linear wide fp32+res {M}x{K}x{N}", out, ref + r, 2e-3)
+    assert torch.equal(out2, out.bfloat16())
+
+
 # ------------------------------------------------------------------------------------ conv
 def pack3x3(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
@@ -130,6 +146,23 @@ def test_conv3x3_s1(N, H, W, Cin, Cout):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
     out = ops.conv3x3(x, pack3x3(w), Cout, bias=b, nsplit=1, out_fp32=(Cout == 4))
     report(f"conv3x3 s1 {N}x{H}x{W} {Cin}->{Cout}", out, ref, 1e-2 if Cout != 4 else 3e-3)
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout", [(2, 64, 64, 320, 0, 320), (2, 32, 32, 640, 320, 640), (2, 16, 16, 1280, 0, 1280)])
+def test_conv3x3_wide_tiles(N, H, W, C0, C1, Cout):
+    ops = _ops()
+    setup_exact_fp32()
+    x0 = rnd(N, H, W, C0).bfloat16()
+    x1 = rnd(N, H, W, C1, seed=5).bfloat16() if C1 else None
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    r = rnd(N * H * W, Cout, seed=3)
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout) + r
+    out, out2 = ops.gemm(x0, pack3x3(w), Cout, kind=ops.GEMM_CONV3X3_S1, a1=x1, bias=b, residual=r,
+                         conv_dims=(N, H, W), c0=C0, c1=C1, out_fp32=True, out2=True, block_n=320, nsplit=1)
+    report(f"conv3x3 wide {C0 + C1}->{Cout}@{H}", out, ref, 3e-3)
+    assert torch.equal(out2, out.bfloat16())
 
 
 def test_conv3x3_residual_dual_source_splitk():
@@ -182,6 +215,8 @@ def test_conv_direct(Cin, Cout, k):
     assert torch.equal(shadow, out.bfloat16())
     out = ops.conv_direct(x, wp, b, Cout, k)
     report(f"conv_direct bf16 {Cin}->{Cout} k{k}", out, ref, 1e-2)
+    out = ops.conv_direct(x.float(), wp, b, Cout, k, out_fp32=True)          # fp32 input path
+    report(f"conv_direct fp32 in {Cin}->{Cout} k{k}", out, ref, 1e-4)
 
 
 # ------------------------------------------------------------------------------------ norms
@@ -339,6 +374,10 @@ def test_cfg_ddpm_step():
         nxt = torch.empty(2 * B, H, W, C, device=DEV, dtype=torch.bfloat16)
         ops.cfg_ddpm_step(got, eps, noise, coef, step, 7.5, True, nxt)
         report(f"cfg_ddpm_step {step}", got, ref, 1e-6)
+        got32 = lat.clone()
+        nxt32 = torch.empty(2 * B, H, W, C, device=DEV, dtype=torch.float32)
+        ops.cfg_ddpm_step(got32, eps, noise, coef, step, 7.5, True, nxt32)
+        report("next_in fp32", nxt32, ref.repeat(2, 1, 1, 1).permute(0, 2, 3, 1), 1e-6)
         report("next_in", nxt, ref.repeat(2, 1, 1, 1).permute(0, 2, 3, 1).bfloat16().float(), 1e-6)
 
 
@@ -370,6 +409,7 @@ def test_vae_scramble_tail_uint8_embed():
     f *= 2 / 255
     f += -1
     report("uint8->image", ops.uint8_to_image(u8), f, 4e-3)
+    report("uint8->image fp32", ops.uint8_to_image(u8, out_fp32=True), f, 1e-6)
     tok = torch.randint(0, 1000, (2, 77), device=DEV)
     table = rnd(1000, 768)
     pos = rnd(77, 768, seed=9)
