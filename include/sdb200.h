@@ -73,6 +73,8 @@ typedef struct sdb_gemm_args {
   int smem_budget;        /* bytes of shared memory for the pipeline, 0 = choose                 */
   int cta_pair;           /* 0 = choose; 1 = one CTA per tile (128 rows); 2 = CTA pairs (256 rows) */
   int out_f16;            /* 16-bit `out` is IEEE half instead of bf16 (Cout % 32 == 0, no split-K)  */
+  int epi_mode;           /* epilogue: 0 = choose; 1 = per-lane global stores; 2 = TMA bulk stores whenever
+                             the output geometry / alignment allows (default only for K <= 2048)          */
 } sdb_gemm_args;
 
 /* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,

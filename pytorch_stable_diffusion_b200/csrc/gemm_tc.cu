@@ -30,6 +30,8 @@ constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KiB
 constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;          // one 32x32 fp32 chunk per epilogue warp
 constexpr int GEMM_RES_RING = 3;                           // residual chunks in flight per epilogue warp (+1)
+constexpr int GEMM_BAR_BYTES = 512;                        // mbarriers + TMEM slot at the end of shared memory
+constexpr int GEMM_EPI16_BYTES = 32 * 32 * 2;              // one 32x32 16-bit chunk
 
 struct GemmTcParams {
   CUtensorMap map_a0;
@@ -81,6 +83,18 @@ struct GemmTcParams {
   int act;                 // 0 none, 1 quick-GELU, 2 SiLU
   float* workspace;        // [nsplit][M_total][N] fp32 when nsplit > 1
   long long m_total;
+  uint32_t fd_mul[4], fd_shr[4];   // fast division by n_tiles, m_tiles, tiles_w, tiles_h (decode_tile)
+  // TMA epilogue (short reductions, where the epilogue bounds the tile time): thread = row, result staged in
+  // swizzled shared memory and written with cp.async.bulk.tensor stores, fp32 residual fetched by TMA loads
+  int epi_tma;
+  int epi_bytes;           // shared memory of all epilogue warps (either path)
+  int epi_warp_bytes;      // per warp: epi_nslot fp32 slots of 4 KiB, then two 2 KiB 16-bit buffers (if any)
+  int epi_nslot;           // fp32 slots per warp (residual in, result out, in place): 0, 2, 3 or 4
+  int8_t slab_w0[4], slab_h0[4], slab_n0[4];   // origin of TMEM lane quadrant q's 32 rows inside the tile box
+  int8_t slab_ok[4];       // quadrant holds rows of the tile at all
+  CUtensorMap map_out;     // boxes of 32 columns x 32 rows (rank 2: [M][N]; rank 4: [NB][HO][WO][N])
+  CUtensorMap map_out2;
+  CUtensorMap map_res;
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -112,17 +126,22 @@ __device__ __forceinline__ void trace_epi(int trc, int tile_local, int slot) {
 // Tile order: output-channel tile fastest, so CTAs that run at the same time share the activation
 // tile through L2 and the (smaller) weight matrix stays L2-resident. In pair mode (CG = 2) a "tile"
 // is two consecutive row tiles; CTA rank r of the pair owns row tile 2*t + r.
+// x / d for 0 <= x < 2^31 with a host-computed multiplier (d = 1: mul = 0): one IMAD.HI and a shift instead of
+// the ~40-instruction software division - decode_tile sits on the critical path of every role once per tile.
+__device__ __forceinline__ int fast_div(int x, uint32_t mul, uint32_t shr) {
+  return mul ? (int)(__umulhi((uint32_t)x, mul) >> shr) : x;
+}
 template <int CG>
 __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile, int cta_rank) {
   TileCoord t;
-  const int n_tile = tile % p.n_tiles;
-  int r = tile / p.n_tiles;
-  int mt = (r % p.m_tiles) * CG + cta_rank;
-  t.z = r / p.m_tiles;
-  const int tw_i = mt % p.tiles_w;
-  mt /= p.tiles_w;
-  const int th_i = mt % p.tiles_h;
-  const int tn_i = mt / p.tiles_h;
+  int r = fast_div(tile, p.fd_mul[0], p.fd_shr[0]);
+  const int n_tile = tile - r * p.n_tiles;
+  t.z = fast_div(r, p.fd_mul[1], p.fd_shr[1]);
+  int mt = (r - t.z * p.m_tiles) * CG + cta_rank;
+  int q = fast_div(mt, p.fd_mul[2], p.fd_shr[2]);
+  const int tw_i = mt - q * p.tiles_w;
+  const int tn_i = fast_div(q, p.fd_mul[3], p.fd_shr[3]);
+  const int th_i = q - tn_i * p.tiles_h;
   t.w0 = tw_i * p.bw;
   t.h0 = th_i * p.bh;
   t.nb0 = tn_i * p.bn;
@@ -131,6 +150,41 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
   t.kb_begin = t.z * p.per_split;
   t.nkb = min(nkb_total, t.kb_begin + p.per_split) - t.kb_begin;
   return t;
+}
+
+// One accumulator row of a 32-column chunk in the TMA epilogue (thread = row): + bias (a broadcast 128-byte
+// line in shared memory, plus the per-row value), activation, + fp32 residual read from the row's swizzled
+// 16-byte pieces, fp32 result written back in place, 16-bit copy packed into pk. Compile-time variants keep
+// the 32-element body free of branches.
+template <bool ACT, bool RES, bool F32, bool F16>
+__device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t srow, uint32_t sx,
+                                         uint32_t bias_line, float rowb, int act) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 b4;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                 : "r"(bias_line + (uint32_t)(j * 16)));
+    float4 x = make_float4(__uint_as_float(v[4 * j]) + (b4.x + rowb), __uint_as_float(v[4 * j + 1]) + (b4.y + rowb),
+                           __uint_as_float(v[4 * j + 2]) + (b4.z + rowb), __uint_as_float(v[4 * j + 3]) + (b4.w + rowb));
+    if (ACT) {
+      x.x = apply_act(x.x, act); x.y = apply_act(x.y, act);
+      x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
+    }
+    const uint32_t piece = srow + ((((uint32_t)j) ^ sx) << 4);
+    if (RES) {
+      float4 rr;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                   : "r"(piece));
+      x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+    }
+    if (F32)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(piece), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
+                   : "memory");
+    if (F16) { pk[2 * j] = pack_f16x2(x.x, x.y); pk[2 * j + 1] = pack_f16x2(x.z, x.w); }
+    else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
+  }
 }
 
 // Persistent, warp-specialised kernel. CG = 1: one CTA per SM computes 128 x block_n tiles.
@@ -162,12 +216,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const int nbuf = (p.n_acc == 2) ? 1 : 2;               // TMEM accumulator buffers
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
   // [staging: one chunk per epilogue warp][residual ring: GEMM_RES_RING chunks per warp, if any][barriers]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(
-      epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + p.epi_bytes);
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_MAX_STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                // [2] accumulator drained (leader's copy is used)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;                  // [GEMM_EPI_WARPS][4] residual slot landed (TMA epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + GEMM_EPI_WARPS * 4);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.map_a0);
@@ -180,6 +234,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * CG);
+    }
+    if (p.epi_tma) {
+      for (int i = 0; i < GEMM_EPI_WARPS * 4; ++i) mbar_init(&res_bar[i], 1);
+      tma_prefetch_desc(&p.map_out);
+      if (p.out2 != nullptr) tma_prefetch_desc(&p.map_out2);
+      if (p.residual != nullptr) tma_prefetch_desc(&p.map_res);
     }
     fence_mbar_init();
   }
@@ -319,6 +379,162 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         trace_stamp(trc, lt, 4);
       }
     }
+  } else if (p.epi_tma) {
+    // ===== Epilogue, TMA form. Warp e owns TMEM lanes [32*(warp%4), +32) - 32 rows of the tile that form a
+    // rectangular box of the output tensor - and the 32-column chunks e/4, e/4 + 2, ... Thread = row: the
+    // accumulator row arrives from tcgen05.ld, the fp32 residual row (TMA-loaded, 128B-swizzled slot) is added
+    // and the result written back IN PLACE, a 16-bit copy goes to a 64B-swizzled buffer, and one lane issues the
+    // bulk tensor stores. No per-lane global address arithmetic, no second pass through shared memory.
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int nchunks = (p.block_n + 31) / 32;
+    const int nslot = p.epi_nslot;
+    const bool has_res = (p.residual != nullptr);
+    const bool f32out = (p.out_fp32 != 0);
+    const bool b16out = (!f32out) || (p.out2 != nullptr);
+    const CUtensorMap* map16 = f32out ? &p.map_out2 : &p.map_out;
+    const uint32_t wblk = smem_u32(epi_smem) + (uint32_t)(e * p.epi_warp_bytes);
+    const uint32_t b16_base = wblk + (uint32_t)(nslot * GEMM_EPI_STAGE_BYTES);
+    const uint32_t rbar0 = smem_u32(res_bar + e * 4);
+    const uint32_t bias_line = smem_u32(epi_smem) + (uint32_t)(GEMM_EPI_WARPS * p.epi_warp_bytes + e * 128);
+    const bool slab_ok = p.slab_ok[q] != 0;
+    const int sw0 = p.slab_w0[q], sh0 = p.slab_h0[q], sn0 = p.slab_n0[q];
+    const int pfd = nslot - 2;                 // residual prefetch distance in chunks (slots: ahead | current | draining)
+    // prefetch cursor: the same (tile, chunk) sequence as the main loop, pfd chunks ahead
+    int pf_tile = first_tile, pf_lt = 0, pf_ch = half, pf_slot = 0;
+    int pf_n0 = 0, pf_c1 = 0, pf_c2 = 0, pf_c3 = 0;
+    auto pf_decode = [&]() {
+      if (pf_tile < p.total_tiles) {
+        const TileCoord t = decode_tile<CG>(p, pf_tile, cta_rank);
+        pf_n0 = t.n0; pf_c1 = t.w0 + sw0; pf_c2 = t.h0 + sh0; pf_c3 = t.nb0 + sn0;
+      }
+    };
+    auto pf_settle = [&]() {       // move to the next existing chunk at or after (pf_tile, pf_ch)
+      while (pf_tile < p.total_tiles && !(pf_ch < nchunks && pf_n0 + pf_ch * 32 < p.N)) {
+        pf_tile += tile_step; ++pf_lt; pf_ch = (half + pf_lt) & 1;
+        pf_decode();
+      }
+    };
+    auto issue_prefetch = [&]() {
+      if (pf_tile < p.total_tiles) {
+        if (lane == 0) {
+          const uint32_t bar = rbar0 + (uint32_t)(pf_slot * 8);
+          const uint32_t dst = wblk + (uint32_t)(pf_slot * GEMM_EPI_STAGE_BYTES);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(GEMM_EPI_STAGE_BYTES) : "memory");
+          if (p.a_rank == 2) tma_load_2d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1);
+          else tma_load_4d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1, pf_c2, pf_c3);
+        }
+        if (++pf_slot == nslot) pf_slot = 0;
+        pf_ch += 2;
+        pf_settle();
+      }
+    };
+    if (has_res && slab_ok) {
+      pf_decode();
+      pf_settle();
+      for (int d = 0; d < pfd; ++d) issue_prefetch();
+    }
+    int slot = 0;          // fp32 slot of the chunk being processed
+    uint32_t rphase = 0;   // parity of the residual barrier of `slot`
+    int b16 = 0;           // 16-bit buffer of the chunk being processed
+    int lt = 0;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++lt) {
+      const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+      const int acc = (p.n_acc == 2) ? 0 : (lt & 1);
+      const int ch_first = (half + lt) & 1;
+      if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
+      mbar_wait(&tfull_bar[acc], (uint32_t)(lt / nbuf) & 1u, 3);
+      if (e == 0 && lane == 0) { trace_stamp(trc, lt, 6); trace_epi(trc, lt, 1); }
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+      const int cpa = p.acc_n >> 5;
+      const int c1 = t.w0 + sw0, c2 = t.h0 + sh0, c3 = t.nb0 + sn0;
+      if (slab_ok) {
+        for (int ch = ch_first; ch < nchunks; ch += 2) {
+          const int col0 = t.n0 + ch * 32;
+          if (col0 >= p.N) break;
+          const int ncol = min(32, p.N - col0);
+          // stores of the chunk before the previous one have left shared memory: its slot / 16-bit buffer
+          // are free again (and the slot the prefetch below targets is the one that chunk used)
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+          if (has_res) issue_prefetch();
+          uint32_t v[32];
+          tmem_ld32(t_addr + (uint32_t)((p.n_acc == 2 && ch >= cpa) ? 256 + (ch - cpa) * 32 : ch * 32), v);
+          // bias: requested before the accumulator wait; the 32 column values reach every row-thread through a
+          // 128-byte shared-memory line (broadcast reads)
+          float rowb = 0.f, colb = 0.f;
+          if (p.bias_mode == 2) {
+            const long long m = (long long)c1 + lane;          // rank-2 outputs only (host-checked)
+            if (m < p.m_total) rowb = __ldg(p.bias + m);
+          } else if (p.bias_mode == 1) {
+            if (lane < ncol) colb = __ldg(p.bias + col0 + lane);
+          }
+          tmem_ld_wait();
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(lane * 4)), "f"(colb) : "memory");
+          __syncwarp();
+          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
+          const uint32_t srow = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES + lane * 128);
+          if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
+          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
+          uint32_t pk[16];
+          {
+            const uint32_t sx = (uint32_t)(lane & 7);
+            switch ((p.act != 0 ? 1 : 0) | (has_res ? 2 : 0) | (f32out ? 4 : 0) | (p.out_f16 ? 8 : 0)) {
+              case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 1: epi_rows<true, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 2: epi_rows<false, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 3: epi_rows<true, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 4: epi_rows<false, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 5: epi_rows<true, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+              default: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            }
+          }
+          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
+          const uint32_t hbuf = b16_base + (uint32_t)(b16 * GEMM_EPI16_BYTES);
+          if (b16out) {
+            const uint32_t hrow = hbuf + (uint32_t)(lane * 64);
+            const uint32_t hx = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((((uint32_t)j) ^ hx) << 4)),
+                           "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                           : "memory");
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 7);
+          if (lane == 0) {
+            const uint32_t fsrc = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES);
+            if (p.a_rank == 2) {
+              if (f32out) tma_store_2d(&p.map_out, fsrc, col0, c1);
+              if (b16out) tma_store_2d(map16, hbuf, col0, c1);
+            } else {
+              if (f32out) tma_store_4d(&p.map_out, fsrc, col0, c1, c2, c3);
+              if (b16out) tma_store_4d(map16, hbuf, col0, c1, c2, c3);
+            }
+            bulk_commit();
+          }
+          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 4);
+          if (nslot > 0 && ++slot == nslot) { slot = 0; rphase ^= 1u; }
+          b16 ^= 1;
+        }
+      }
+      if (e == 0 && lane == 0) trace_epi(trc, lt, 5);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
+        else mbar_arrive(&tempty_bar[acc]);
+        if (e == 0) trace_stamp(trc, lt, 7);
+      }
+    }
+    if (lane == 0) bulk_wait<0>();       // every store of this warp has been performed before the CTA retires
+    __syncwarp();
   } else {
     // ===== Epilogue warps. Warp e = warp - 2 owns TMEM lanes [32*(warp%4), +32) and the 32-column
     // chunks e/4, e/4 + 2, ...  Phase 1: thread = row, TMEM -> 128B-swizzled shared chunk.
@@ -871,24 +1087,93 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
 
   // ---- pipeline depth from the shared-memory budget
   const int stage_bytes = GEMM_A_STAGE_BYTES + p.n_acc * (p.acc_n / cg) * GEMM_BK * 2;
-  // fp32 residuals stream through a cp.async ring (3 chunks per epilogue warp) when 16-byte aligned
   const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
+  const long long ldo_eff = a->ldo ? a->ldo : a->Cout;
   const int want_split = a->nsplit > 1;
-  const bool res_vec = (a->residual != nullptr && a->res_fp32 && !want_split && (ldr_eff % 4) == 0 &&
-                        (a->Cout % 4) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0);
-  // short reductions are epilogue-bound (ring: deep prefetch); long ones keep the shared memory for stages
   const int nkb_all = p.ntaps * p.cblocks;
-  p.res_async = (res_vec && nkb_all <= 32) ? 1 : 0;
-  p.res_direct = (res_vec && !p.res_async) ? 1 : 0;
   const int smem_budget = (a->smem_budget > 0 && a->smem_budget < 227 * 1024) ? a->smem_budget : 227 * 1024;
-  int fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)) + 1024 + 256;
-  int stages = (smem_budget - fixed_bytes) / stage_bytes;
-  if (stages < 2 && p.res_async) {          // the residual ring does not fit next to two stages: direct loads
-    p.res_async = 0;
-    p.res_direct = 1;
-    fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + 256;
-    stages = (smem_budget - fixed_bytes) / stage_bytes;
+  int fixed_bytes = 0;
+  int stages = 0;
+  // Short reductions are epilogue-bound: TMA epilogue (bulk tensor stores, residual by TMA loads) when the
+  // 32-row slabs of a tile are boxes of the output tensor and every pointer / stride meets the TMA alignment.
+  {
+    static int no_epi_tma = -1;
+    if (no_epi_tma < 0) { const char* ev = getenv("SDB_NO_EPI_TMA"); no_epi_tma = (ev && ev[0] == '1') ? 1 : 0; }
+    const bool f32o = a->out_fp32 != 0;
+    const bool has16 = !f32o || a->out2 != nullptr;
+    const int epi_mode = a->epi_mode;            // 0 auto, 1 never, 2 whenever eligible (also long reductions)
+    bool ok = !no_epi_tma && epi_mode != 1 && !want_split && (nkb_all <= 32 || epi_mode == 2);
+    ok = ok && (block_n % 32 == 0 || n_tiles == 1);
+    ok = ok && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && (f32o ? (ldo_eff % 4 == 0) : (ldo_eff % 8 == 0));
+    if (a->out2) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) & 15u) == 0 && (ldo_eff % 8 == 0);
+    if (a->residual)
+      ok = ok && a->res_fp32 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 && (ldr_eff % 4 == 0);
+    if (a->bias)
+      ok = ok && (a->bias_per_row ? (kind == SDB_GEMM_LINEAR) : ((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0));
+    const int rows = p.bw * p.bh * p.bn, plane = p.bw * p.bh;
+    if (p.a_rank == 5)
+      ok = ok && ((p.bw % 32 == 0) || (32 % p.bw == 0)) && ((plane % 32 == 0) || (32 % plane == 0)) && (rows % 32 == 0);
+    if (ok) {
+      int nslot = a->residual ? 4 : (f32o ? 2 : 0);
+      for (;;) {
+        p.epi_warp_bytes = nslot * GEMM_EPI_STAGE_BYTES + (has16 ? 2 * GEMM_EPI16_BYTES : 0);
+        fixed_bytes = GEMM_EPI_WARPS * (p.epi_warp_bytes + 128) + 1024 + GEMM_BAR_BYTES;   // + one bias line per warp
+        stages = (smem_budget - fixed_bytes) / stage_bytes;
+        if (stages >= 3 || !(a->residual && nslot == 4)) break;
+        nslot = 3;
+      }
+      if (stages >= 2) {
+        p.epi_tma = 1;
+        p.epi_nslot = nslot;
+        uint32_t box[4] = {32, 32, 1, 1};
+        for (int q = 0; q < 4; ++q) {
+          const int r0 = q * 32;
+          if (p.a_rank == 2) { p.slab_w0[q] = (int8_t)r0; p.slab_ok[q] = 1; }
+          else {
+            p.slab_ok[q] = (int8_t)(r0 < rows);
+            p.slab_w0[q] = (int8_t)(r0 % p.bw);
+            p.slab_h0[q] = (int8_t)((r0 / p.bw) % p.bh);
+            p.slab_n0[q] = (int8_t)(r0 / plane);
+          }
+        }
+        if (p.a_rank == 5) {
+          const int sbw = p.bw < 32 ? p.bw : 32;
+          const int sbh = p.bw >= 32 ? 1 : (p.bh < 32 / p.bw ? p.bh : 32 / p.bw);
+          box[1] = (uint32_t)sbw; box[2] = (uint32_t)sbh; box[3] = (uint32_t)(32 / (sbw * sbh));
+        }
+        auto mk = [&](CUtensorMap* m, const void* base, int esz, long long ld, const char* what) -> int {
+          if (p.a_rank == 2) {
+            uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->M};
+            uint64_t str[1] = {(uint64_t)ld * esz};
+            return make_tmap(m, base, esz, esz == 4 ? 128 : 64, 2, dims, str, box, what);
+          }
+          uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)p.WO, (uint64_t)p.HO, (uint64_t)p.NB};
+          uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)ld * esz * p.WO, (uint64_t)ld * esz * p.WO * p.HO};
+          return make_tmap(m, base, esz, esz == 4 ? 128 : 64, 4, dims, str, box, what);
+        };
+        if ((rc = mk(&p.map_out, a->out, f32o ? 4 : 2, ldo_eff, "gemm out"))) return rc;
+        if (a->out2 && (rc = mk(&p.map_out2, a->out2, 2, ldo_eff, "gemm out2"))) return rc;
+        if (a->residual && (rc = mk(&p.map_res, a->residual, 4, ldr_eff, "gemm residual"))) return rc;
+      }
+    }
   }
+  if (!p.epi_tma) {
+    // fp32 residuals stream through a cp.async ring (3 chunks per epilogue warp) when 16-byte aligned
+    const bool res_vec = (a->residual != nullptr && a->res_fp32 && !want_split && (ldr_eff % 4) == 0 &&
+                          (a->Cout % 4) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0);
+    // short reductions are epilogue-bound (ring: deep prefetch); long ones keep the shared memory for stages
+    p.res_async = (res_vec && nkb_all <= 32) ? 1 : 0;
+    p.res_direct = (res_vec && !p.res_async) ? 1 : 0;
+    fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES * (1 + (p.res_async ? GEMM_RES_RING : 0)) + 1024 + GEMM_BAR_BYTES;
+    stages = (smem_budget - fixed_bytes) / stage_bytes;
+    if (stages < 2 && p.res_async) {          // the residual ring does not fit next to two stages: direct loads
+      p.res_async = 0;
+      p.res_direct = 1;
+      fixed_bytes = GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + GEMM_BAR_BYTES;
+      stages = (smem_budget - fixed_bytes) / stage_bytes;
+    }
+  }
+  p.epi_bytes = fixed_bytes - 1024 - GEMM_BAR_BYTES;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) { set_error("sdb_gemm_tc: shared-memory budget too small"); return SDB_ERR_ARG; }
   const int nkb_total = p.ntaps * p.cblocks;
@@ -939,6 +1224,18 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.m_tiles = (int)row_tiles;
   p.n_tiles = n_tiles;
   p.total_tiles = (int)total_tiles;
+  {
+    const int divs[4] = {p.n_tiles, p.m_tiles, p.tiles_w, p.tiles_h};
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t d = (uint32_t)divs[i];
+      if (d <= 1) { p.fd_mul[i] = 0; p.fd_shr[i] = 0; continue; }
+      uint32_t lg = 0;
+      while ((1u << lg) < d) ++lg;                       // ceil(log2 d)
+      const uint32_t sh = 31 + lg;
+      p.fd_mul[i] = (uint32_t)(((1ull << sh) + d - 1) / d);
+      p.fd_shr[i] = sh - 32;
+    }
+  }
   const int num_sms = device_sm_count();
   const long long slots = num_sms / cg;                       // CTAs (or CTA pairs) resident at once
   const unsigned grid = (unsigned)((total_tiles < slots ? total_tiles : slots) * cg);

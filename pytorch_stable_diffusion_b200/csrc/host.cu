@@ -43,6 +43,11 @@ EncodeTiledFn get_encode_tiled() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+  return make_tmap(out, base, 2, 128, rank, dims, strides_bytes, box, what);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) {
     set_error("%s: cuTensorMapEncodeTiled unavailable (no CUDA driver)", what);
@@ -69,8 +74,12 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
       return SDB_ERR_ARG;
     }
   }
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapDataType dt = (elem_bytes == 4) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = (swizzle_bytes == 128) ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (swizzle_bytes == 64) ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : (swizzle_bytes == 32) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base),
+                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("%s: cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu,%llu] "

@@ -30,4 +30,8 @@ EncodeTiledFn get_encode_tiled();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, const char* what);
 
+// General form: elem_bytes 2 (16-bit) or 4 (fp32); swizzle_bytes 0 / 32 / 64 / 128.
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank,
+              const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, const char* what);
+
 }  // namespace sdb

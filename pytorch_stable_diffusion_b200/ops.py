@@ -131,7 +131,7 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
 
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
-         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False):
+         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
     lib = _ext.lib()
     _chk(a0, torch.bfloat16, "a0")
@@ -197,6 +197,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.nsplit = nsplit
     args.cta_pair = cta_pair
     args.out_f16 = 1 if out_f16 else 0
+    args.epi_mode = epi_mode
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
                2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size()
                + (rows * cout * residual.element_size() if residual is not None else 0)

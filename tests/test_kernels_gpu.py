@@ -120,6 +120,91 @@ def test_linear_wide_tiles(M, K, N):
     assert torch.equal(out2, out.bfloat16())
 
 
+# ------------------------------------------------------------------------------------ TMA epilogue
+@pytest.mark.parametrize("M,K,N,block_n", [
+    (4096, 320, 320, 160), (4096, 320, 320, 320), (1000, 320, 640, 160), (333, 640, 96, 96),
+    (128, 64, 32, 32), (2048, 1280, 1280, 160), (70, 320, 48, 48),
+])
+def test_linear_tma_epilogue(M, K, N, block_n):
+    """Bulk-tensor-store epilogue (epi_mode=2) against fp32 PyTorch and, bit for bit, against the per-lane
+    store epilogue (epi_mode=1): bf16 out, fp32 out + fp32 residual (+ bf16 copy), activation, f16 out."""
+    ops = _ops()
+    setup_exact_fp32()
+    a = rnd(M, K).bfloat16()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    b = rnd(N, seed=2)
+    r = rnd(M, N, seed=3)
+    ref = a.float() @ w.float().t() + b
+    kw = dict(block_n=block_n, nsplit=1)
+    got = ops.linear(a, w, bias=b, epi_mode=2, **kw)
+    report(f"tma-epi bf16 {M}x{K}x{N}", got, ref, 1e-2)
+    assert torch.equal(got, ops.linear(a, w, bias=b, epi_mode=1, **kw))
+    got = ops.linear(a, w, epi_mode=2, **kw)
+    report(f"tma-epi no bias {M}x{K}x{N}", got, ref - b, 1e-2)
+    got, got2 = ops.linear(a, w, bias=b, residual=r, out_fp32=True, out2=True, epi_mode=2, **kw)
+    report(f"tma-epi fp32+res {M}x{K}x{N}", got, ref + r, 2e-3)
+    assert torch.equal(got2, got.bfloat16())
+    old, old2 = ops.linear(a, w, bias=b, residual=r, out_fp32=True, out2=True, epi_mode=1, **kw)
+    assert torch.equal(got, old) and torch.equal(got2, old2)
+    got = ops.linear(a, w, bias=b, residual=r, out_fp32=True, epi_mode=2, **kw)
+    assert torch.equal(got, old)
+    got = ops.linear(a, w, bias=b, out_fp32=True, act=ops.ACT_QUICK_GELU, epi_mode=2, **kw)
+    report(f"tma-epi fp32 qgelu {M}x{K}x{N}", got, ref * torch.sigmoid(1.702 * ref), 2e-3)
+    got = ops.linear(a, w, bias=b, residual=r, epi_mode=2, **kw)          # bf16 out + fp32 residual
+    report(f"tma-epi bf16+res {M}x{K}x{N}", got, ref + r, 1e-2)
+    if N % 32 == 0:
+        got = ops.linear(a, w, bias=b, out_f16=True, epi_mode=2, **kw)
+        report(f"tma-epi f16 {M}x{K}x{N}", got, ref, 2e-3)
+
+
+def test_linear_tma_epilogue_row_bias_and_strided_out():
+    ops = _ops()
+    setup_exact_fp32()
+    M, K, N = 512, 320, 1000
+    x = rnd(N, K).bfloat16()
+    wv = rnd(M, K, scale=K ** -0.5, seed=4).bfloat16()
+    bv = rnd(M, seed=5)
+    ref = wv.float() @ x.float().t() + bv[:, None]
+    out = ops.gemm(wv, x, N, kind=ops.GEMM_LINEAR, M=M, c0=K, bias=bv, bias_per_row=True, epi_mode=2)
+    report("tma-epi swapped + row bias", out, ref, 1e-2)
+    wide = torch.zeros(M, 2048, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(wv, x, N, kind=ops.GEMM_LINEAR, M=M, c0=K, out=wide[:, 1024:1024 + N], ldo=2048, nsplit=1, epi_mode=2)
+    report("tma-epi ldo", wide[:, 1024:1024 + N], ref - bv[:, None], 1e-2)
+    assert float(wide[:, :1024].abs().max()) == 0.0 and float(wide[:, 1024 + N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("NB,H,W,C0,C1,Cout,kind", [
+    (2, 64, 64, 64, 0, 320, "s1"), (3, 32, 32, 128, 64, 160, "s1"), (2, 16, 16, 192, 0, 96, "s1"),
+    (5, 8, 8, 128, 0, 64, "s1"), (1, 8, 8, 64, 0, 32, "s1"), (2, 96, 96, 64, 0, 64, "s1"),
+    (2, 48, 48, 64, 0, 64, "s1"), (2, 24, 24, 64, 0, 64, "s1"), (2, 64, 64, 64, 0, 64, "s2"),
+    (3, 4, 4, 64, 0, 64, "s1"),
+])
+def test_conv3x3_tma_epilogue(NB, H, W, C0, C1, Cout, kind):
+    """Every tile-box geometry the UNet / VAE levels produce (and the ineligible ones, which must fall back)."""
+    ops = _ops()
+    setup_exact_fp32()
+    x0 = rnd(NB, H, W, C0).bfloat16()
+    x1 = rnd(NB, H, W, C1, seed=5).bfloat16() if C1 else None
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    s2 = kind == "s2"
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float(), b, padding=1, stride=2 if s2 else 1).permute(0, 2, 3, 1)
+    ho, wo = ref.shape[1], ref.shape[2]
+    ref = ref.reshape(-1, Cout)
+    r = rnd(NB * ho * wo, Cout, seed=3)
+    k = ops.GEMM_CONV3X3_S2 if s2 else ops.GEMM_CONV3X3_S1
+    kw = dict(kind=k, a1=x1, bias=b, conv_dims=(NB, H, W), c0=C0, c1=C1, nsplit=1)
+    got, got2 = ops.gemm(x0, pack3x3(w), Cout, residual=r, out_fp32=True, out2=True, epi_mode=2, **kw)
+    report(f"conv tma-epi fp32+res {C0 + C1}->{Cout}@{H}", got, ref + r, 3e-3)
+    assert torch.equal(got2, got.bfloat16())
+    old, old2 = ops.gemm(x0, pack3x3(w), Cout, residual=r, out_fp32=True, out2=True, epi_mode=1, **kw)
+    assert torch.equal(got, old) and torch.equal(got2, old2)
+    got = ops.gemm(x0, pack3x3(w), Cout, epi_mode=2, **kw)
+    report(f"conv tma-epi bf16 {C0 + C1}->{Cout}@{H}", got, ref, 1e-2)
+    assert torch.equal(got, ops.gemm(x0, pack3x3(w), Cout, epi_mode=1, **kw))
+
+
 # ------------------------------------------------------------------------------------ conv
 def pack3x3(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()

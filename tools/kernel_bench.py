@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--json", default="")
     ap.add_argument("--pair", type=int, default=0, help="0 auto, 1 single-CTA tiles, 2 CTA pairs")
+    ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the launches")
     ap.add_argument("--attn-mode", type=int, default=0, help="0 plain, 1 ones-row denominator, 2 + f16x2 exps")
     args = ap.parse_args()
     global PAIR, ATTN_MODE
@@ -154,10 +155,24 @@ def main():
         scratch.zero_()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.iters):
-            fn()
-        e1.record()
+        if args.graph:
+            # the iters launches replayed from a CUDA graph: no host launch cost between kernels (what the
+            # captured denoising loop sees); outputs are allocated by fn() inside the capture pool
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(args.iters):
+                    fn()
+            g.replay()
+            scratch.zero_()
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+        else:
+            e0.record()
+            for _ in range(args.iters):
+                fn()
+            e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         tf = fl / (ms * 1e-3) / 1e12
