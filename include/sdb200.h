@@ -126,6 +126,14 @@ int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, l
 int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats, const float* gamma,
                         const float* beta, void* out, int NB, long long HW, int C0, int C1,
                         int groups, float eps, int silu, int x0_fp32, int x1_fp32, void* stream);
+/* One-pass GroupNorm (+SiLU) for fp32 NHWC inputs: a thread-block cluster keeps (sample, slab of groups) resident
+ * in shared memory, so the tensor is read from HBM once and no statistics buffer exists. Same arithmetic
+ * contract as stats + apply (fp64 combination in a fixed order). sdb_groupnorm_fused_supported(): 0 = no plan
+ * (use stats + apply), 1 = plan with a multi-CTA cluster (correct, but slower than stats + apply whose second
+ * read hits L2), 2 = single-CTA plan (faster; the small UNet levels). */
+int sdb_groupnorm_fused_supported(long long HW, int C0, int C1, int groups);
+int sdb_groupnorm_fused(const float* x0, const float* x1, const float* gamma, const float* beta, void* out,
+                        int NB, long long HW, int C0, int C1, int groups, float eps, int silu, void* stream);
 /* nn.LayerNorm over the last axis (sd/diffusion.py:258,261,264; sd/clip.py:105,113,225).
  * x bf16 (fp32 when in_fp32) [rows, C] -> out bf16 (or fp32 when out_fp32). */
 int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out, long long rows,

@@ -46,6 +46,9 @@ SIGNATURES = {
                             c_void_p],
     "sdb_groupnorm_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll,
                             c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p],
+    "sdb_groupnorm_fused_supported": [c_ll, c_int, c_int, c_int],
+    "sdb_groupnorm_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int,
+                            c_float, c_int, c_void_p],
     "sdb_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p],
     "sdb_softmax_rows": [c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p],
     "sdb_fill_zero": [c_void_p, c_ll, c_void_p],

@@ -381,6 +381,190 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One-pass GroupNorm (+SiLU): the tensor is read from HBM exactly once.
+//
+// A thread-block cluster of CS CTAs owns (sample n, slab of G adjacent groups = SC channels); CTA r of the
+// cluster keeps pixels [r*PX, (r+1)*PX) x SC channels of the fp32 input resident in shared memory (cp.async,
+// the whole slice in flight at once), reduces per-group {sum, sum of squares} in a fixed order (fp32 per lane,
+// fp64 across lanes / warps / CTAs: bit-reproducible), exchanges the CTA partials through distributed shared
+// memory, and normalises its slice out of shared memory into the bf16 output. Two 82 KB CTAs share an SM, so
+// one CTA's load phase overlaps the other's store phase.
+struct GnFusedParams {
+  const float* x0;
+  const float* x1;
+  const float* gamma;
+  const float* beta;
+  __nv_bfloat16* out;
+  int HW, C0, C1, cpg, G, SC, CS, PX, nslabs, silu;
+  float eps;
+};
+
+constexpr int GNF_THREADS = 256;
+constexpr int GNF_WARPS = GNF_THREADS / 32;
+constexpr int GNF_MAX_SC = 128;
+
+__global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnFusedParams p) {
+  extern __shared__ __align__(16) uint8_t gnf_smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (p.CS > 1) ? (int)cluster_ctarank() : 0;
+  const int cid = blockIdx.x / p.CS;
+  const int n = cid / p.nslabs;
+  const int cb = (cid - n * p.nslabs) * p.SC;            // first channel of the slab
+  const int px0 = rank * p.PX;
+  const int npx = max(0, min(p.PX, p.HW - px0));
+  const int C = p.C0 + p.C1;
+  const int SC = p.SC;
+  float* data = reinterpret_cast<float*>(gnf_smem);                                   // [PX][SC]
+  float* part = data + (size_t)p.PX * SC;                                            // [warps][SC][2]
+  float* coef = part + GNF_WARPS * SC * 2;                                           // [SC][2]
+  double* cta_stats = reinterpret_cast<double*>(coef + 2 * SC);                       // [G][2] (16-byte aligned)
+
+  // ---- pass A: slice -> shared memory, 16 bytes per cp.async, everything in flight at once
+  {
+    const int V = SC >> 2;                               // 16-byte vectors per pixel
+    const int da = GNF_THREADS / V, db = GNF_THREADS - da * V;
+    int px = tid / V, v = tid - px * V;
+    const uint32_t dbase = smem_u32(data);
+    const long long row0 = (long long)n * p.HW + px0;
+    while (px < npx) {
+      const int c = cb + 4 * v;
+      const float* src = (c < p.C0) ? p.x0 + (row0 + px) * p.C0 + c : p.x1 + (row0 + px) * p.C1 + (c - p.C0);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dbase + (uint32_t)((px * SC + 4 * v) * 4)), "l"(src)
+                   : "memory");
+      v += db; px += da;
+      if (v >= V) { v -= V; ++px; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- pass B: per-channel partial sums: lane -> floats lane, lane + 32, ... of a pixel row (bank = lane),
+  // warp -> pixels warp, warp + 8, ...
+  {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int px = warp; px < npx; px += GNF_WARPS) {
+      const float* row = data + px * SC;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = lane + 32 * k;
+        if (c < SC) { const float x = row[c]; s[k] += x; q[k] = fmaf(x, x, q[k]); }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane + 32 * k;
+      if (c < SC) { part[(warp * SC + c) * 2] = s[k]; part[(warp * SC + c) * 2 + 1] = q[k]; }
+    }
+  }
+  __syncthreads();
+  // one warp per group: cpg x warps partials summed in fp64, fixed order
+  for (int g = warp; g < p.G; g += GNF_WARPS) {
+    double ds = 0.0, dq = 0.0;
+    const int cnt = p.cpg * GNF_WARPS;
+    for (int i = lane; i < cnt; i += 32) {
+      const int w = i / p.cpg, c = g * p.cpg + (i - w * p.cpg);
+      ds += (double)part[(w * SC + c) * 2];
+      dq += (double)part[(w * SC + c) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (lane == 0) { cta_stats[2 * g] = ds; cta_stats[2 * g + 1] = dq; }
+  }
+  __syncthreads();
+  if (p.CS > 1) cluster_sync_all();                     // every CTA's partials are published
+
+  // ---- pass C: cluster-wide statistics through distributed shared memory, per-channel scale / shift
+  if (tid < SC) {
+    const int g = tid / p.cpg;
+    double ds = 0.0, dq = 0.0;
+    if (p.CS > 1) {
+      const uint32_t local = smem_u32(cta_stats + 2 * g);
+      for (int r = 0; r < p.CS; ++r) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        double a, b;
+        asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(remote));
+        ds += a; dq += b;
+      }
+    } else {
+      ds = cta_stats[2 * g]; dq = cta_stats[2 * g + 1];
+    }
+    const double cnt = (double)p.cpg * (double)p.HW;
+    const double mean = ds / cnt;
+    double var = dq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    const float a = __ldg(p.gamma + cb + tid) * rstd;
+    coef[2 * tid] = a;
+    coef[2 * tid + 1] = __ldg(p.beta + cb + tid) - (float)mean * a;
+  }
+  __syncthreads();
+  // peers may still be reading this CTA's partials: arrive now, wait before leaving
+  if (p.CS > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+
+  // ---- pass D: normalise out of shared memory, 8 channels (16 bytes of bf16) per thread and step
+  {
+    const int VO = SC >> 3;
+    const int da = GNF_THREADS / VO, db = GNF_THREADS - da * VO;
+    int px = tid / VO, v = tid - px * VO;
+    const long long row0 = (long long)n * p.HW + px0;
+    while (px < npx) {
+      const float4 x0 = *reinterpret_cast<const float4*>(data + px * SC + 8 * v);
+      const float4 x1 = *reinterpret_cast<const float4*>(data + px * SC + 8 * v + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(coef + 16 * v);
+      const float4 c1 = *reinterpret_cast<const float4*>(coef + 16 * v + 4);
+      const float4 c2 = *reinterpret_cast<const float4*>(coef + 16 * v + 8);
+      const float4 c3 = *reinterpret_cast<const float4*>(coef + 16 * v + 12);
+      float y[8] = {fmaf(x0.x, c0.x, c0.y), fmaf(x0.y, c0.z, c0.w), fmaf(x0.z, c1.x, c1.y), fmaf(x0.w, c1.z, c1.w),
+                    fmaf(x1.x, c2.x, c2.y), fmaf(x1.y, c2.z, c2.w), fmaf(x1.z, c3.x, c3.y), fmaf(x1.w, c3.z, c3.w)};
+      if (p.silu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = silu_f(y[i]);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+      o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(p.out + (row0 + px) * C + cb + 8 * v) = o;
+      v += db; px += da;
+      if (v >= VO) { v -= VO; ++px; }
+    }
+  }
+  if (p.CS > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// (G, CS, PX) for the one-pass kernel, or false when no slab of the tensor fits the shared memory of a cluster.
+static bool gn_fused_plan(long long HW, int C0, int C1, int groups, int* G_, int* CS_, int* PX_, size_t* smem_) {
+  const int C = C0 + C1;
+  if (groups <= 0 || C % groups != 0 || C0 % 4 != 0 || C1 % 4 != 0 || HW <= 0 || HW > (1 << 24)) return false;
+  const int cpg = C / groups;
+  bool found = false;
+  size_t best = 0;
+  for (int G = 1; G <= groups; G <<= 1) {
+    if (groups % G != 0) break;
+    const int SC = G * cpg;
+    if (SC % 8 != 0 || SC > GNF_MAX_SC) continue;
+    if (SC < 40 && G * 2 <= groups && (G * 2 * cpg) <= GNF_MAX_SC) continue;     // 160-byte runs at least, if possible
+    for (int CS = 1; CS <= 8; CS <<= 1) {
+      const long long PX = (HW + CS - 1) / CS;
+      const size_t bytes = (size_t)PX * SC * 4 + (size_t)GNF_WARPS * SC * 8 + (size_t)SC * 8 + (size_t)G * 16 + 16;
+      if (bytes > 200 * 1024) continue;
+      // first plan at or below 84 KB (two CTAs per SM); otherwise the smallest footprint seen
+      if (!found || (best > 84 * 1024 && bytes < best)) {
+        found = true; best = bytes; *G_ = G; *CS_ = CS; *PX_ = (int)PX; *smem_ = bytes;
+      }
+      if (bytes <= 84 * 1024) return true;
+    }
+    if (found && best <= 84 * 1024) return true;
+  }
+  return found;
+}
+
 }  // namespace sdb
 
 extern "C" long long sdb_groupnorm_stats_bytes(int NB, int groups) {
@@ -440,6 +624,64 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
       x0_fp32, x1_fp32, chunks);
   return check_launch("gn_apply_kernel");
 }
+
+// 0: no plan; 1: plan with a cluster of several CTAs (measured slower than stats + apply on B200, whose second
+// read hits L2: 73 vs 46 us for 16 x 64 x 64 x 320); 2: single-CTA plan at two CTAs per SM (measured faster:
+// 14.9 vs 18.3 us for 16 x 16 x 16 x 1280) - what the engines use.
+extern "C" int sdb_groupnorm_fused_supported(long long HW, int C0, int C1, int groups) {
+  int G, CS, PX; size_t smem;
+  if (!sdb::gn_fused_plan(HW, C0, C1, groups, &G, &CS, &PX, &smem)) return 0;
+  return (CS == 1 && smem <= 84 * 1024) ? 2 : 1;
+}
+
+extern "C" int sdb_groupnorm_fused(const float* x0, const float* x1, const float* gamma, const float* beta,
+                                   void* out, int NB, long long HW, int C0, int C1, int groups, float eps,
+                                   int silu, void* stream) {
+  using namespace sdb;
+  if (!x0 || !gamma || !beta || !out || NB <= 0 || (C1 > 0 && !x1)) {
+    set_error("sdb_groupnorm_fused: bad arguments");
+    return SDB_ERR_ARG;
+  }
+  GnFusedParams p;
+  size_t smem;
+  if (!gn_fused_plan(HW, C0, C1, groups, &p.G, &p.CS, &p.PX, &smem)) {
+    set_error("sdb_groupnorm_fused: no plan for HW=%lld C=%d+%d groups=%d", HW, C0, C1, groups);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  if (((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(out)) & 15u) != 0) {
+    set_error("sdb_groupnorm_fused: pointers must be 16-byte aligned");
+    return SDB_ERR_UNSUPPORTED;
+  }
+  p.x0 = x0; p.x1 = x1; p.gamma = gamma; p.beta = beta; p.out = (__nv_bfloat16*)out;
+  p.HW = (int)HW; p.C0 = C0; p.C1 = C1; p.cpg = (C0 + C1) / groups; p.SC = p.G * p.cpg;
+  p.nslabs = groups / p.G; p.silu = silu; p.eps = eps;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((long long)NB * p.nslabs * p.CS), 1, 1);
+  cfg.blockDim = dim3(GNF_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, p);
+  if (e != cudaSuccess) {
+    set_error("gn_fused_kernel launch: %s", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return SDB_ERR_CUDA;
+  }
+  return check_launch("gn_fused_kernel");
+}
+
 
 extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out,
                              long long rows, int C, float eps, int in_fp32, int out_fp32, void* stream) {

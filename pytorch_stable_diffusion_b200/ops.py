@@ -246,9 +246,13 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
     return out
 
 
-def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
+_NO_GN_FUSED = _os.environ.get("SDB_NO_GN_FUSED") == "1"     # A/B switch: always stats + apply
+
+
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fused=None):
     """GroupNorm (+SiLU) over NHWC x0 ++ x1 (channel concat; each bf16 or fp32); returns bf16
-    [N, H, W, C0+C1]."""
+    [N, H, W, C0+C1]. fp32 inputs whose (sample, group slab) fits a cluster's shared memory take the
+    one-pass kernel (fused=None: when supported; True: required; False: never)."""
     lib = _ext.lib()
     f0 = 1 if x0.dtype == torch.float32 else 0
     f1 = 1 if (x1 is not None and x1.dtype == torch.float32) else 0
@@ -256,6 +260,17 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False):
     c0 = x0.shape[-1]
     hw = x0.numel() // (n * c0)
     c1 = x1.shape[-1] if x1 is not None else 0
+    if fused is None:
+        fused = (not _NO_GN_FUSED) and f0 == 1 and (x1 is None or f1 == 1) and \
+            lib.sdb_groupnorm_fused_supported(hw, c0, c1, groups) == 2
+    if fused:
+        out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
+        ev = _prof("groupnorm", 0.0, 4.0 * n * hw * (c0 + c1) + 2.0 * n * hw * (c0 + c1))
+        _ext.check(lib.sdb_groupnorm_fused(_p(_chk(x0, torch.float32, "x0")), _p(x1), _p(gamma), _p(beta), _p(out),
+                                           n, hw, c0, c1, groups, float(eps), 1 if silu else 0, _stream()),
+                   "sdb_groupnorm_fused")
+        _prof_end(ev)
+        return out
     stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)

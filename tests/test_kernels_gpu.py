@@ -324,6 +324,49 @@ def test_groupnorm(N, HW, C0, C1, eps, silu):
     report(f"groupnorm C={C0}+{C1} HW={HW}", out, ref, 6e-3)
 
 
+@pytest.mark.parametrize("N,HW,C0,C1,silu", [
+    (2, 4096, 320, 0, True), (2, 4096, 320, 320, True), (3, 1024, 640, 0, False), (2, 1024, 1280, 640, True),
+    (2, 1024, 640, 320, True), (2, 256, 1280, 0, True), (2, 256, 1280, 1280, True), (5, 64, 1280, 0, True),
+    (2, 64, 1280, 1280, False), (1, 4096, 512, 0, True), (2, 9216, 320, 0, True), (2, 2304, 640, 0, True),
+    (2, 144, 1280, 0, True), (2, 1000, 320, 0, True),
+])
+def test_groupnorm_fused(N, HW, C0, C1, silu):
+    """One-pass cluster GroupNorm (fp32 in, bf16 out) against F.group_norm and against the two-kernel path."""
+    ops = _ops()
+    from pytorch_stable_diffusion_b200 import _ext
+    assert _ext.lib().sdb_groupnorm_fused_supported(HW, C0, C1, 32) >= 1
+    x0 = rnd(N, HW, C0) * 2 + 0.5
+    x1 = (rnd(N, HW, C1, seed=3) - 1.0) if C1 else None
+    C = C0 + C1
+    g = rnd(C, seed=4) + 1.0
+    b = rnd(C, seed=5)
+    out = ops.groupnorm(x0, g, b, x1=x1, eps=1e-5, silu=silu, fused=True)
+    xc = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(xc.permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    report(f"groupnorm fused C={C0}+{C1} HW={HW}", out, ref, 6e-3)
+    two = ops.groupnorm(x0, g, b, x1=x1, eps=1e-5, silu=silu, fused=False)
+    report(f"groupnorm fused vs two-pass C={C0}+{C1} HW={HW}", out, two, 8e-3)
+    again = ops.groupnorm(x0, g, b, x1=x1, eps=1e-5, silu=silu, fused=True)
+    assert torch.equal(out, again)          # fixed summation order: bit-reproducible
+
+
+def test_groupnorm_fused_unsupported_shapes_fall_back():
+    ops = _ops()
+    from pytorch_stable_diffusion_b200 import _ext
+    lib = _ext.lib()
+    assert lib.sdb_groupnorm_fused_supported(4096, 640, 320, 32) == 0       # 30 channels per group at 64x64
+    assert lib.sdb_groupnorm_fused_supported(512 * 512, 128, 0, 32) == 0    # VAE full resolution
+    x0 = rnd(1, 4096, 640)
+    x1 = rnd(1, 4096, 320, seed=3)
+    g = rnd(960, seed=4) + 1.0
+    b = rnd(960, seed=5)
+    out = ops.groupnorm(x0, g, b, x1=x1, silu=True)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1], -1).permute(0, 2, 1), 32, g, b, 1e-5).permute(0, 2, 1))
+    report("groupnorm fallback 960@64", out, ref, 6e-3)
+
+
 @pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (512, 1280), (160, 768)])
 def test_layernorm(rows, C):
     ops = _ops()
