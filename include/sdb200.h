@@ -105,6 +105,9 @@ typedef struct sdb_attn_args {
                              every head is all ones: the denominator of the softmax is accumulated by the
                              P.V tensor-core product itself. No causal mask, d <= 112.                */
   int p_f16;              /* with sum_row: exponentials are taken two at a time in f16x2 and P is f16 */
+  int exp_poly;           /* two-tile kernel: every fourth exponential is a degree-3 polynomial on the FMA pipe
+                             (rel. error 7.5e-5, below the bf16 rounding of P) instead of a MUFU operation -
+                             the kernel is bound by the 16 ex2 / clk / SM. 0 = default (on), 1 = off, 2 = on */
 } sdb_attn_args;
 
 /* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),

@@ -42,12 +42,27 @@ struct AttnParams {
   int stages;    // K/V ring depth of the two-tile kernel (2 or 3)
   int tmem_cols; // one-tile kernel: TMEM columns to allocate (256 lets two CTAs share an SM)
   int o_col;     // one-tile kernel: first TMEM column of O
+  int exp_poly;  // two-tile kernel: every fourth exponential on the FMA pipe (exp2_poly)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // pure: let the compiler schedule it freely
   return y;
+}
+// 2^x without the MUFU: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (max
+// relative error 7.5e-5 - P is rounded to bf16, 2e-3, right after), 2^n by adding n to the exponent field.
+// n comes out of the magic-number addition (1.5 * 2^23 + x has round(x) in its low mantissa bits, and
+// (bits << 23) is exactly n << 23 because the constant's lowest set bit is bit 22). x >= -126 after the clamp
+// (masked scores are -inf), x <= 8 by the lazy-rescale bound.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.0551716685f, f, 0.2426111400f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 // two exponentials per MUFU operation: (lo, hi) fp32 -> f16x2 -> 2^x in f16x2
 __device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
@@ -67,6 +82,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
   const int q0 = blockIdx.x * ATT_BQ;
   const int h = blockIdx.y;
   const int n = blockIdx.z;
@@ -115,6 +131,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // nothing above touched global data (PDL: the predecessor grid may still be running)
   const uint32_t tmem_o = tmem_base + (uint32_t)p.o_col;
 
   if (warp == 0) {
@@ -305,6 +322,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
   const int q0 = blockIdx.x * (2 * ATT_BQ);
   const int h = blockIdx.y;
   const int n = blockIdx.z;
@@ -362,6 +380,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // nothing above touched global data (PDL: the predecessor grid may still be running)
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues)
@@ -554,6 +573,18 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 128; i += 2)
           pk[i >> 1] = ex2_f16x2(fmaf(__uint_as_float(sv[i]), sl2, -mb), fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+      } else if (p.sum_col >= 0 && p.exp_poly) {
+        // no row sums here (the ones row of V^T makes the P.V product accumulate them) and a quarter of the
+        // exponentials on the FMA pipe: MUFU 96 x 8 clk per warp, FMA pipe ~290 x 2 clk
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), sl2, -mb));
+          const float p3 = exp2_poly(fmaf(__uint_as_float(sv[i + 3]), sl2, -mb));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
       } else if (p.sum_col >= 0) {
 #pragma unroll
         for (int i = 0; i < 128; i += 2) {
@@ -561,6 +592,21 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
           const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
           pk[i >> 1] = pack_bf16x2(p0, p1);
         }
+      } else if (p.exp_poly) {
+        // the exponentials bound this kernel (16 MUFU ops / clk / SM): every fourth one goes to the FMA pipe
+        float lsum0 = 0.f, lsum1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sv[i + 2]), sl2, -mb));
+          const float p3 = exp2_poly(fmaf(__uint_as_float(sv[i + 3]), sl2, -mb));
+          lsum0 += p0 + p2;
+          lsum1 += p1 + p3;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        l_run += lsum0 + lsum1;
       } else {
         float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
@@ -711,6 +757,7 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   int stages2 = (227 * 1024 - 2 * q_bytes - 1024 - 256) / stage_bytes;
   if (stages2 > ATT2_MAX_STAGES) stages2 = ATT2_MAX_STAGES;
   p.stages = stages2;
+  p.exp_poly = (a->exp_poly == 1) ? 0 : 1;
   const int smem2 = stages2 >= 2 ? 2 * q_bytes + stages2 * stage_bytes + 1024 + 256 : (1 << 30);
   // a single key block (cross-attention): two light one-tile CTAs per SM beat one two-tile CTA
   const bool single_block = (a->Skv <= ATT_BKV) && dv_pad <= 128 && !a->sum_row;
@@ -720,13 +767,13 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
                         (a->variant != 1 || a->sum_row) && !(single_block && a->variant != 2);
   if (two_tile) {
     dim3 grid((unsigned)((a->S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)), (unsigned)a->heads, (unsigned)a->NB);
-    attn2_tc_kernel<<<grid, ATT2_THREADS, smem2, (cudaStream_t)stream>>>(p);
+    (void)launch_k(attn2_tc_kernel, grid, dim3(ATT2_THREADS), (size_t)smem2, (cudaStream_t)stream, 1, p);
     return check_launch("attn2_tc_kernel");
   }
   if (a->sum_row) { set_error("sdb_attention: sum_row does not fit the two-tile kernel for d = %d", a->d); return SDB_ERR_UNSUPPORTED; }
   const int smem_bytes = q_bytes + (single_block ? 1 : 2) * stage_bytes + 1024 + 256;
   if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
   dim3 grid((unsigned)((a->S + ATT_BQ - 1) / ATT_BQ), (unsigned)a->heads, (unsigned)a->NB);
-  attn_tc_kernel<<<grid, ATT_THREADS, smem_bytes, (cudaStream_t)stream>>>(p);
+  (void)launch_k(attn_tc_kernel, grid, dim3(ATT_THREADS), (size_t)smem_bytes, (cudaStream_t)stream, 1, p);
   return check_launch("attn_tc_kernel");
 }

@@ -40,6 +40,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of the denoising loop is launched with the programmatic-stream-serialization attribute
+// (host.h: launch_k): it may become resident while its predecessor drains. pdl_trigger() lets the successor be
+// scheduled once every CTA of this grid has started; pdl_wait() returns when the predecessor grid has completed
+// and its writes are visible - it must precede the first global-memory access (reads AND writes: the caching
+// allocator may hand a successor a buffer the predecessor still reads) of every thread. Both are no-ops in a
+// kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -56,6 +56,8 @@ __global__ void nhwc_to_nchw_f32_kernel(const void* __restrict__ x, float* __res
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int NB, int H,
                                   int W, int V) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = (long long)NB * Ho * Wo * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -76,6 +78,8 @@ __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __re
                                    const float* __restrict__ bias, void* __restrict__ out,
                                    __nv_bfloat16* __restrict__ out2, int NB, int H, int W, int Cin,
                                    int Cout, int out_fp32, int in_fp32) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_w[];  // [KS*KS*Cin][CoutPad]
   const int CoutPad = (Cout + 7) & ~7;
   const int K = KS * KS * Cin;
@@ -163,6 +167,8 @@ __global__ void cfg_ddpm_step_kernel(float* __restrict__ latents, const float* _
                                      int step, float cfg_scale, int do_cfg,
                                      void* __restrict__ next_in, int NB, int C, int H, int W,
                                      int eps_nchw, int next_fp32) {
+  pdl_trigger();
+  pdl_wait();
   const long long hw = (long long)H * W;
   const long long total = (long long)NB * C * hw;
   const float sb = coef[step * 5 + 0];   // sqrt(1 - abar_t)
@@ -358,7 +364,7 @@ extern "C" int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int 
     set_error("sdb_upsample2x_nhwc: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * 4 * H * W * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>((const uint4*)x, (uint4*)out, NB, H, W,
+  (void)launch_k(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, SDB_STREAM, 1, (const uint4*)x, (uint4*)out, NB, H, W,
                                                                   C / 8);
   return check_launch("upsample2x_kernel");
 }
@@ -384,10 +390,10 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (ksize == 1)
-    conv_direct_kernel<1><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
+    (void)launch_k(conv_direct_kernel<1>, dim3((unsigned)blocks), dim3(256), smem, SDB_STREAM, 1,
         x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
   else
-    conv_direct_kernel<3><<<(unsigned)blocks, 256, smem, SDB_STREAM>>>(
+    (void)launch_k(conv_direct_kernel<3>, dim3((unsigned)blocks), dim3(256), smem, SDB_STREAM, 1,
         x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
   return check_launch("conv_direct_kernel");
 }
@@ -412,7 +418,7 @@ extern "C" int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* 
     set_error("sdb_cfg_ddpm_step: bad arguments"); return SDB_ERR_ARG;
   }
   const long long total = (long long)NB * C * H * W;
-  cfg_ddpm_step_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(
+  (void)launch_k(cfg_ddpm_step_kernel, dim3(grid_for(total, 256)), dim3(256), 0, SDB_STREAM, 1,
       latents, eps, noise, coef, step, cfg_scale, do_cfg, next_in, NB, C, H, W, eps_nchw, next_fp32);
   return check_launch("cfg_ddpm_step_kernel");
 }

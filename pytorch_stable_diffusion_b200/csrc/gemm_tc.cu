@@ -204,6 +204,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
   const int trc = (blockIdx.x == 0) ? g_gemm_trace_on : 0;
   const int cta_rank = (CG == 2) ? (int)cluster_ctarank() : 0;
   const bool leader = (cta_rank == 0);
@@ -262,6 +263,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     tc_fence_after();
   }
   const uint32_t tmem_base = *tmem_slot;
+  // the prologue above touched no global data: only now wait for the predecessor grid (PDL)
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer. The whole warp walks the loop (so every value stays warp-uniform and lives
@@ -871,6 +874,8 @@ __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int ns
                                             int bias_mode, const void* __restrict__ residual,
                                             int res_fp32, long long ldr, int act,
                                             __nv_bfloat16* __restrict__ out2) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = m_total * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1240,21 +1245,8 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   const long long slots = num_sms / cg;                       // CTAs (or CTA pairs) resident at once
   const unsigned grid = (unsigned)((total_tiles < slots ? total_tiles : slots) * cg);
   {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = (size_t)smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cg;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = (cg == 2) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, p)
-                              : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, p);
+    cudaError_t e = (cg == 2) ? launch_k(gemm_tc_kernel<2>, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 2, p)
+                              : launch_k(gemm_tc_kernel<1>, dim3(grid), dim3(GEMM_THREADS), (size_t)smem_bytes, stream, 1, p);
     if (e != cudaSuccess) { set_error("gemm_tc_kernel launch: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   }
   if ((rc = check_launch("gemm_tc_kernel"))) return rc;
@@ -1262,8 +1254,8 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     const long long total = p.m_total * p.N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    gemm_splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(
-        p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias, p.bias_mode,
+    (void)launch_k(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, 1,
+        (const float*)p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias, p.bias_mode,
         p.residual, p.res_fp32, p.ldr, p.act, p.out2);
     if ((rc = check_launch("gemm_splitk_finalize_kernel"))) return rc;
   }

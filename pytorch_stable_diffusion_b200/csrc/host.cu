@@ -1,6 +1,7 @@
 // Host-side runtime glue for the C-ABI library (error reporting, TMA descriptor encoding).
 #include "host.h"
 #include <stdarg.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/sdb200.h"
 
@@ -25,6 +26,15 @@ int check_launch(const char* what) {
     return SDB_ERR_CUDA;
   }
   return SDB_OK;
+}
+
+int pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("SDB_PDL");
+    on = (ev && ev[0] == '0') ? 0 : 1;
+  }
+  return on;
 }
 
 EncodeTiledFn get_encode_tiled() {

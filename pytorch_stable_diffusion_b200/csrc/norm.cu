@@ -42,6 +42,8 @@ __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restr
                                 double* __restrict__ stats, long long HW, int C0, int C1, int groups,
                                 long long ppc, int V, int lanes, int x0_fp32, int x1_fp32) {
   extern __shared__ float s_part[];     // [lanes][ctot] sums, then [lanes][ctot] sums of squares
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int v = t % V;
@@ -107,6 +109,8 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
   extern __shared__ double s_stat[];     // [stat_chunks][groups][2] partial statistics of this sample
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.y;
   const int t = threadIdx.x;
   const int ctot = C0 + C1;
@@ -247,6 +251,8 @@ __global__ void __launch_bounds__(256)
 layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, void* __restrict__ out, long long rows, int C,
                      float eps, int out_fp32) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -407,6 +413,8 @@ constexpr int GNF_MAX_SC = 128;
 
 __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnFusedParams p) {
   extern __shared__ __align__(16) uint8_t gnf_smem[];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (p.CS > 1) ? (int)cluster_ctarank() : 0;
   const int cid = blockIdx.x / p.CS;
@@ -591,8 +599,9 @@ extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats
     set_error("sdb_groupnorm_stats: %d channels need %zu bytes of shared memory", ctot, smem);
     return SDB_ERR_UNSUPPORTED;
   }
-  gn_stats_kernel<<<dim3(chunks, NB), threads, smem, (cudaStream_t)stream>>>(
-      x0, x1, stats, HW, C0, C1, groups, ppc, V, lanes, x0_fp32, x1_fp32);
+  cudaError_t le = launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(threads), smem, (cudaStream_t)stream, 1,
+                            x0, x1, stats, HW, C0, C1, groups, ppc, V, lanes, x0_fp32, x1_fp32);
+  if (le != cudaSuccess) { set_error("gn_stats_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_stats_kernel");
 }
 
@@ -619,9 +628,10 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
                          GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double));
     apply_configured = true;
   }
-  gn_apply_kernel<<<dim3(chunks, NB), threads, smem_apply, (cudaStream_t)stream>>>(
-      x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V, lanes,
-      x0_fp32, x1_fp32, chunks);
+  cudaError_t le = launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
+                            x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
+                            lanes, x0_fp32, x1_fp32, chunks);
+  if (le != cudaSuccess) { set_error("gn_apply_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_apply_kernel");
 }
 
@@ -660,20 +670,8 @@ extern "C" int sdb_groupnorm_fused(const float* x0, const float* x1, const float
     cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)((long long)NB * p.nslabs * p.CS), 1, 1);
-  cfg.blockDim = dim3(GNF_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)p.CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, p);
+  cudaError_t e = launch_k(gn_fused_kernel, dim3((unsigned)((long long)NB * p.nslabs * p.CS)), dim3(GNF_THREADS), smem,
+                           (cudaStream_t)stream, p.CS, p);
   if (e != cudaSuccess) {
     set_error("gn_fused_kernel launch: %s", cudaGetErrorString(e));
     (void)cudaGetLastError();
@@ -700,7 +698,7 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
     if (blocks > cap) blocks = cap;
     const float* xf = reinterpret_cast<const float*>(x);
     cudaStream_t st = (cudaStream_t)stream;
-#define SDB_LN(V) layernorm_f32_kernel<V><<<(unsigned)blocks, warps * 32, 0, st>>>(xf, gamma, beta, out, rows, C, eps, out_fp32)
+#define SDB_LN(V) (void)launch_k(layernorm_f32_kernel<V>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, 1, xf, gamma, beta, out, rows, C, eps, out_fp32)
     if (vpl <= 3) SDB_LN(3);
     else if (vpl <= 5) SDB_LN(5);
     else if (vpl <= 6) SDB_LN(6);

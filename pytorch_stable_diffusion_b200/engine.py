@@ -11,6 +11,7 @@ Data layout in HBM
 Nothing here computes on the host: every tensor op below is a kernel from libsdb200.so.
 """
 import math
+import os
 from types import SimpleNamespace as NS
 
 import torch
@@ -25,6 +26,8 @@ CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
 # W = W2 . W1[:4C], b = W2 . b1[:4C] + b2 (SURVEY.md "Hard parts"; the FLOP numerator in bench.py drops
 # by the saved 179 GFLOP per image-step accordingly). Set to False to run the two GEMMs separately.
 FOLD_GEGLU = True
+# self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
+SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -104,6 +107,22 @@ def pack_unet_attn(m, dev):
     b = m.attention_1.in_proj.bias
     pk.bqk = _f32(b[:2 * c], dev) if b is not None else None
     pk.bv = _f32(b[2 * c:], dev) if b is not None else None
+    # Heads of up to 112 channels run the two-tile attention kernel with the softmax denominator accumulated by
+    # the P.V product itself: V^T gets R = round16(d + 1) rows per head, row d all ones (a zero weight row
+    # with bias 1), the rest zero. The padding is free: the tensor core pays for N = R either way.
+    d = c // pk.heads
+    pk.vt_rows = 0
+    if SUM_ROW_ATTENTION and d <= 112:
+        r = (d + 1 + 15) // 16 * 16
+        wv = torch.zeros((pk.heads, r, c), dtype=torch.float32)
+        wv[:, :d] = w[2 * c:].float().cpu().view(pk.heads, d, c)
+        bv = torch.zeros((pk.heads, r), dtype=torch.float32)
+        if b is not None:
+            bv[:, :d] = b[2 * c:].detach().float().cpu().view(pk.heads, d)
+        bv[:, d] = 1.0
+        pk.wv = _bf16(wv.view(pk.heads * r, c), dev)
+        pk.bv = _f32(bv.view(-1), dev)
+        pk.vt_rows = r
     pk.wo1, pk.bo1 = pack_linear(m.attention_1.out_proj, dev)
     pk.ln2 = pack_norm(m.layernorm_2, dev)
     pk.wq2, pk.bq2 = pack_linear(m.attention_2.q_proj, dev)
@@ -239,7 +258,7 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
     o = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
     ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
-                  ldq=2 * c, ldk=2 * c, ldo=c)
+                  ldq=2 * c, ldk=2 * c, ldo=c, sum_row=pk.vt_rows > 0)
     t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
     # cross-attention over the CLIP tokens
     l2 = ops.layernorm(t1, *pk.ln2)

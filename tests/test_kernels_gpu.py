@@ -427,6 +427,12 @@ def test_attention(N, heads, d, S, Skv, causal, amp):
     vf = v.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
     ref = ref_attention(qf, kf, vf, causal).transpose(1, 2).reshape(N * S, C)
     report(f"attention d={d} S={S} Skv={Skv} causal={causal}", out, ref, 1e-2)
+    # all exponentials on the MUFU (exp_poly=1 switches the polynomial quarter off): same answer to bf16 rounding
+    out2 = torch.empty_like(out)
+    ops.attention(q, k.view(N * Skv_pad, C), vt, out2, NB=N, heads=heads, d=d, S=S, Skv=Skv,
+                  Skv_pad=Skv_pad, ldq=C, ldk=C, ldo=C, causal=causal, exp_poly=1)
+    report(f"attention (MUFU only) d={d} S={S} Skv={Skv} causal={causal}", out2, ref, 1e-2)
+    report(f"attention poly vs MUFU d={d} S={S} Skv={Skv}", out, out2, 8e-3)
 
 
 @pytest.mark.parametrize("d,S,Skv,p_f16", [
