@@ -108,6 +108,8 @@ typedef struct sdb_attn_args {
   int exp_poly;           /* two-tile kernel: every fourth exponential is a degree-3 polynomial on the FMA pipe
                              (rel. error 7.5e-5, below the bf16 rounding of P) instead of a MUFU operation -
                              the kernel is bound by the 16 ex2 / clk / SM. 0 = default (on), 1 = off, 2 = on */
+  int q_prescaled;        /* q already carries log2(e) * scale (folded into the query projection): the scores are
+                             in log2 units and `scale` is ignored                                           */
 } sdb_attn_args;
 
 /* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),

@@ -43,6 +43,7 @@ struct AttnParams {
   int tmem_cols; // one-tile kernel: TMEM columns to allocate (256 lets two CTAs share an SM)
   int o_col;     // one-tile kernel: first TMEM column of O
   int exp_poly;  // two-tile kernel: every fourth exponential on the FMA pipe (exp2_poly)
+  int prescaled; // scale_log2 == 1: scores arrive in log2 units
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -573,9 +574,23 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
 #pragma unroll
         for (int i = 0; i < 128; i += 2)
           pk[i >> 1] = ex2_f16x2(fmaf(__uint_as_float(sv[i]), sl2, -mb), fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+      } else if (p.sum_col >= 0 && p.exp_poly && p.prescaled) {
+        // scores already in log2 units (q carries log2(e)/sqrt(d) from its projection): the argument of the
+        // exponential is a 2-register FADD instead of a 3-register FFMA. Measured (tools/micro/softmax_issue2.cu):
+        // the loop is bound by the ~1.7 clk a 3-register fp32 instruction costs per sub-partition as much as by
+        // the MUFU - 1025 -> 894 clk per 128-column row and warp.
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = ex2_approx(__uint_as_float(sv[i]) - mb);
+          const float p1 = ex2_approx(__uint_as_float(sv[i + 1]) - mb);
+          const float p2 = ex2_approx(__uint_as_float(sv[i + 2]) - mb);
+          const float p3 = exp2_poly(__uint_as_float(sv[i + 3]) - mb);
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
       } else if (p.sum_col >= 0 && p.exp_poly) {
         // no row sums here (the ones row of V^T makes the P.V product accumulate them) and a quarter of the
-        // exponentials on the FMA pipe: MUFU 96 x 8 clk per warp, FMA pipe ~290 x 2 clk
+        // exponentials on the FMA pipe
 #pragma unroll
         for (int i = 0; i < 128; i += 4) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
@@ -731,7 +746,8 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.ldo = ldo;
   p.S = a->S; p.Skv = a->Skv; p.d = a->d; p.heads = a->heads; p.NB = a->NB;
   p.causal = a->causal;
-  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.scale_log2 = a->q_prescaled ? 1.0f : a->scale * 1.4426950408889634f;
+  p.prescaled = a->q_prescaled ? 1 : 0;
   p.dchunks = (a->d + 63) / 64;
   p.dk_steps = (a->d + 15) / 16;
   p.dv_pad = dv_pad;

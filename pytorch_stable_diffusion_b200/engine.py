@@ -123,6 +123,16 @@ def pack_unet_attn(m, dev):
         pk.wv = _bf16(wv.view(pk.heads * r, c), dev)
         pk.bv = _f32(bv.view(-1), dev)
         pk.vt_rows = r
+        # ... and the queries carry log2(e)/sqrt(d) (sd/attention.py:66 divides the scores by sqrt(d_head)): the
+        # scores leave the tensor core in log2 units and the softmax argument is a subtraction, not an FFMA
+        sl2 = math.log2(math.e) / math.sqrt(d)
+        wq = w[:2 * c].detach().float().cpu().clone()
+        wq[:c] *= sl2
+        pk.wqk = _bf16(wq, dev)
+        if b is not None:
+            bq = b[:2 * c].detach().float().cpu().clone()
+            bq[:c] *= sl2
+            pk.bqk = _f32(bq, dev)
     pk.wo1, pk.bo1 = pack_linear(m.attention_1.out_proj, dev)
     pk.ln2 = pack_norm(m.layernorm_2, dev)
     pk.wq2, pk.bq2 = pack_linear(m.attention_2.q_proj, dev)
@@ -258,7 +268,7 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
     o = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
     ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
-                  ldq=2 * c, ldk=2 * c, ldo=c, sum_row=pk.vt_rows > 0)
+                  ldq=2 * c, ldk=2 * c, ldo=c, sum_row=pk.vt_rows > 0, q_prescaled=pk.vt_rows > 0)
     t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
     # cross-attention over the CLIP tokens
     l2 = ops.layernorm(t1, *pk.ln2)

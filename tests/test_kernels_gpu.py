@@ -438,6 +438,7 @@ def test_attention(N, heads, d, S, Skv, causal, amp):
 @pytest.mark.parametrize("d,S,Skv,p_f16", [
     (40, 4096, 4096, False), (40, 4096, 4096, True), (80, 1024, 1024, False), (80, 1024, 1024, True),
     (40, 1024, 77, False), (40, 1024, 77, True), (80, 576, 576, True), (40, 64, 64, True), (40, 1024, 1024, True),
+    (40, 1024, 1024, False), (40, 9216, 9216, False), (40, 1000, 1000, False), (48, 512, 512, False),
 ])
 def test_attention_sum_row(d, S, Skv, p_f16):
     """Denominator accumulated by the P.V product through a ones row in V^T; optionally f16x2 exps."""
@@ -465,6 +466,42 @@ def test_attention_sum_row(d, S, Skv, p_f16):
     vf = v.float()[:, :Skv].reshape(N, Skv, heads, d).transpose(1, 2)
     ref = ref_attention(qf, kf, vf, False).transpose(1, 2).reshape(N * S, C)
     report(f"attention sum_row d={d} S={S} Skv={Skv} p_f16={p_f16}", out, ref, 1e-2)
+    if not p_f16:
+        # queries pre-multiplied by log2(e)/sqrt(d): the kernel takes the scores as log2 units
+        qs = (q.float() * (math.log2(math.e) / math.sqrt(d))).bfloat16()
+        qsf = qs.float().view(N, S, heads, d).transpose(1, 2) * (math.sqrt(d) / math.log2(math.e))
+        ref2 = ref_attention(qsf, kf, vf, False).transpose(1, 2).reshape(N * S, C)
+        out2 = torch.empty_like(out)
+        ops.attention(qs, k.view(N * Skv_pad, C), vt, out2, NB=N, heads=heads, d=d, S=S, Skv=Skv,
+                      Skv_pad=Skv_pad, ldq=C, ldk=C, ldo=C, sum_row=True, q_prescaled=True)
+        report(f"attention sum_row prescaled d={d} S={S} Skv={Skv}", out2, ref2, 1e-2)
+
+
+def test_attention_growing_maximum():
+    """Keys whose scores grow block after block (each block raises the row maximum by far more than the 2^8
+    lazy-rescale bound): the O / denominator rescale path must give the reference softmax."""
+    ops = _ops()
+    setup_exact_fp32()
+    N, heads, d, S = 2, 8, 40, 1024
+    C = heads * d
+    R = 48
+    q = rnd(N * S, C).bfloat16()
+    k = rnd(N, S, C, seed=1)
+    ramp = torch.linspace(0.2, 6.0, S, device=DEV).view(1, S, 1)          # later key blocks: larger |scores|
+    k = (k * ramp).bfloat16()
+    v = rnd(N, S, C, seed=2).bfloat16()
+    vt = torch.zeros(heads, R, N, S, device=DEV, dtype=torch.bfloat16)
+    vt[:, :d] = v.view(N, S, heads, d).permute(2, 3, 0, 1)
+    vt[:, d] = 1.0
+    vt = vt.view(heads * R, N, S).contiguous()
+    out = torch.empty(N * S, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q, k.view(N * S, C), vt, out, NB=N, heads=heads, d=d, S=S, Skv=S, Skv_pad=S, ldq=C, ldk=C, ldo=C,
+                  sum_row=True)
+    qf = q.float().view(N, S, heads, d).transpose(1, 2)
+    kf = k.float().reshape(N, S, heads, d).transpose(1, 2)
+    vf = v.float().reshape(N, S, heads, d).transpose(1, 2)
+    ref = ref_attention(qf, kf, vf, False).transpose(1, 2).reshape(N * S, C)
+    report("attention, growing maximum", out, ref, 1e-2)
 
 
 # ------------------------------------------------------------------------------------ elementwise
