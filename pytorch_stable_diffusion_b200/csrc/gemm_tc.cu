@@ -453,88 +453,121 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
       const int cpa = p.acc_n >> 5;
       const int c1 = t.w0 + sw0, c2 = t.h0 + sh0, c3 = t.nb0 + sn0;
-      if (slab_ok) {
-        for (int ch = ch_first; ch < nchunks; ch += 2) {
-          const int col0 = t.n0 + ch * 32;
-          if (col0 >= p.N) break;
-          const int ncol = min(32, p.N - col0);
-          // stores of the chunk before the previous one have left shared memory: its slot / 16-bit buffer
-          // are free again (and the slot the prefetch below targets is the one that chunk used)
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-          if (has_res) issue_prefetch();
-          uint32_t v[32];
-          tmem_ld32(t_addr + (uint32_t)((p.n_acc == 2 && ch >= cpa) ? 256 + (ch - cpa) * 32 : ch * 32), v);
-          // bias: requested before the accumulator wait; the 32 column values reach every row-thread through a
-          // 128-byte shared-memory line (broadcast reads)
-          float rowb = 0.f, colb = 0.f;
-          if (p.bias_mode == 2) {
-            const long long m = (long long)c1 + lane;          // rank-2 outputs only (host-checked)
-            if (m < p.m_total) rowb = __ldg(p.bias + m);
-          } else if (p.bias_mode == 1) {
-            if (lane < ncol) colb = __ldg(p.bias + col0 + lane);
-          }
-          tmem_ld_wait();
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(lane * 4)), "f"(colb) : "memory");
-          __syncwarp();
-          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
-          const uint32_t srow = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES + lane * 128);
-          if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
-          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
-          uint32_t pk[16];
-          {
-            const uint32_t sx = (uint32_t)(lane & 7);
-            switch ((p.act != 0 ? 1 : 0) | (has_res ? 2 : 0) | (f32out ? 4 : 0) | (p.out_f16 ? 8 : 0)) {
-              case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 1: epi_rows<true, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 2: epi_rows<false, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 3: epi_rows<true, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 4: epi_rows<false, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 5: epi_rows<true, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-              default: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            }
-          }
-          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
-          const uint32_t hbuf = b16_base + (uint32_t)(b16 * GEMM_EPI16_BYTES);
-          if (b16out) {
-            const uint32_t hrow = hbuf + (uint32_t)(lane * 64);
-            const uint32_t hx = (uint32_t)((lane >> 1) & 3);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((((uint32_t)j) ^ hx) << 4)),
-                           "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
-                           : "memory");
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 7);
-          if (lane == 0) {
-            const uint32_t fsrc = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES);
-            if (p.a_rank == 2) {
-              if (f32out) tma_store_2d(&p.map_out, fsrc, col0, c1);
-              if (b16out) tma_store_2d(map16, hbuf, col0, c1);
-            } else {
-              if (f32out) tma_store_4d(&p.map_out, fsrc, col0, c1, c2, c3);
-              if (b16out) tma_store_4d(map16, hbuf, col0, c1, c2, c3);
-            }
-            bulk_commit();
-          }
-          if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 4);
-          if (nslot > 0 && ++slot == nslot) { slot = 0; rphase ^= 1u; }
-          b16 ^= 1;
+      // all tcgen05.ld of this accumulator have completed: hand it back to the MMA issuer (the leader's barrier;
+      // a remote arrive from the peer CTA) - before the last chunk's arithmetic and stores
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
+          else mbar_arrive(&tempty_bar[acc]);
         }
+      };
+      auto valid = [&](int c) { return c < nchunks && t.n0 + c * 32 < p.N; };
+      auto taddr = [&](int c) {
+        return t_addr + (uint32_t)((p.n_acc == 2 && c >= cpa) ? 256 + (c - cpa) * 32 : c * 32);
+      };
+      float rowb = 0.f, colb = 0.f;
+      // chunk prologue: free the buffers of the chunk before the previous one, request the next residual and
+      // this chunk's bias - everything that does not need the accumulator
+      auto pre = [&](int ch) {
+        const int col0 = t.n0 + ch * 32;
+        const int ncol = min(32, p.N - col0);
+        // stores of the chunk before the previous one have left shared memory: its slot / 16-bit buffer
+        // are free again (and the slot the prefetch below targets is the one that chunk used)
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        if (has_res) issue_prefetch();
+        // bias: requested before the accumulator wait; the 32 column values reach every row-thread through a
+        // 128-byte shared-memory line (broadcast reads)
+        rowb = 0.f; colb = 0.f;
+        if (p.bias_mode == 2) {
+          const long long m = (long long)c1 + lane;          // rank-2 outputs only (host-checked)
+          if (m < p.m_total) rowb = __ldg(p.bias + m);
+        } else if (p.bias_mode == 1) {
+          if (lane < ncol) colb = __ldg(p.bias + col0 + lane);
+        }
+      };
+      // chunk body: accumulator row in v (loaded and waited for)
+      auto post = [&](const uint32_t (&v)[32], int ch) {
+        const int col0 = t.n0 + ch * 32;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(lane * 4)), "f"(colb) : "memory");
+        __syncwarp();
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
+        const uint32_t srow = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES + lane * 128);
+        if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
+        uint32_t pk[16];
+        {
+          const uint32_t sx = (uint32_t)(lane & 7);
+          switch ((p.act != 0 ? 1 : 0) | (has_res ? 2 : 0) | (f32out ? 4 : 0) | (p.out_f16 ? 8 : 0)) {
+            case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 1: epi_rows<true, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 2: epi_rows<false, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 3: epi_rows<true, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 4: epi_rows<false, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 5: epi_rows<true, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            default: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+          }
+        }
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
+        const uint32_t hbuf = b16_base + (uint32_t)(b16 * GEMM_EPI16_BYTES);
+        if (b16out) {
+          const uint32_t hrow = hbuf + (uint32_t)(lane * 64);
+          const uint32_t hx = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((((uint32_t)j) ^ hx) << 4)),
+                         "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
+                         : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 7);
+        if (lane == 0) {
+          const uint32_t fsrc = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES);
+          if (p.a_rank == 2) {
+            if (f32out) tma_store_2d(&p.map_out, fsrc, col0, c1);
+            if (b16out) tma_store_2d(map16, hbuf, col0, c1);
+          } else {
+            if (f32out) tma_store_4d(&p.map_out, fsrc, col0, c1, c2, c3);
+            if (b16out) tma_store_4d(map16, hbuf, col0, c1, c2, c3);
+          }
+          bulk_commit();
+        }
+        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 4);
+        if (nslot > 0 && ++slot == nslot) { slot = 0; rphase ^= 1u; }
+        b16 ^= 1;
+      };
+      if (slab_ok && valid(ch_first)) {
+        // two register buffers: the accumulator chunk after this one is in flight (tcgen05.ld) while this one
+        // goes through bias / residual / staging
+        uint32_t va[32], vb[32];
+        int ch = ch_first;
+        tmem_ld32(taddr(ch), va);
+        for (;;) {
+          pre(ch);
+          tmem_ld_wait();
+          const bool n1 = valid(ch + 2);
+          if (n1) tmem_ld32(taddr(ch + 2), vb); else release_acc();
+          post(va, ch);
+          if (!n1) break;
+          ch += 2;
+          pre(ch);
+          tmem_ld_wait();
+          const bool n2 = valid(ch + 2);
+          if (n2) tmem_ld32(taddr(ch + 2), va); else release_acc();
+          post(vb, ch);
+          if (!n2) break;
+          ch += 2;
+        }
+      } else {
+        release_acc();
       }
-      if (e == 0 && lane == 0) trace_epi(trc, lt, 5);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
-        else mbar_arrive(&tempty_bar[acc]);
-        if (e == 0) trace_stamp(trc, lt, 7);
-      }
+      if (e == 0 && lane == 0) { trace_epi(trc, lt, 5); trace_stamp(trc, lt, 7); }
     }
     if (lane == 0) bulk_wait<0>();       // every store of this warp has been performed before the CTA retires
     __syncwarp();
