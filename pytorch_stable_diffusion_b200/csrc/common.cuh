@@ -189,6 +189,14 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+// Same without the release: for signals that order nothing but work already waited for (an accumulator whose
+// tcgen05.ld have completed) - the releasing form makes the thread wait for its outstanding global stores.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // TMA loads issued by either CTA of a pair; completion bytes are credited to the LEADER's barrier.
 __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0,
                                                  int c1) {

@@ -459,8 +459,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
-          else mbar_arrive(&tempty_bar[acc]);
+          if constexpr (CG == 2) mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
+          else mbar_arrive_relaxed(&tempty_bar[acc]);
         }
       };
       auto valid = [&](int c) { return c < nchunks && t.n0 + c * 32 < p.N; };
@@ -882,8 +882,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
-        else mbar_arrive(&tempty_bar[acc]);
+        if constexpr (CG == 2) mbar_arrive_cluster_relaxed(smem_u32(&tempty_bar[acc]) & PEER_BIT_MASK);
+        else mbar_arrive_relaxed(&tempty_bar[acc]);
         if (e == 0) trace_stamp(trc, lt, 7);
       }
     }
