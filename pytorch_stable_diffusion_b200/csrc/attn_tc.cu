@@ -44,6 +44,7 @@ struct AttnParams {
   int o_col;     // one-tile kernel: first TMEM column of O
   int exp_poly;  // two-tile kernel: every fourth exponential on the FMA pipe (exp2_poly)
   int prescaled; // scale_log2 == 1: scores arrive in log2 units
+  int stagger;   // two-tile kernel, separate P: clocks tile 1 starts after tile 0 (0 = fixed issue order, lock step)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -314,7 +315,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one query row per thread)
 // TMEM: S0/P0 at columns [0,128), S1/P1 at [128,256), O0 at [256,384), O1 at [384,512).
 constexpr int ATT2_THREADS = 320;
-constexpr int ATT2_MAX_STAGES = 3;
+// Warp roles of the two-tile kernel: softmax warps 0-3 (tile 0) and 4-7 (tile 1) - TMEM lane quadrant = warp % 4 -,
+// then the TMA producer and the MMA issuer (highest warp id on its sub-partition; measured neutral against the
+// issuer as warp 1).
+constexpr int ATT2_TMA_WARP = 8;
+constexpr int ATT2_MMA_WARP = 9;
+constexpr int ATT2_MAX_STAGES = 3;   // K/V ring depth (6 measured no faster)
 
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn2_tc_kernel(const __grid_constant__ AttnParams p) {
@@ -373,7 +379,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == ATT2_MMA_WARP) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -383,7 +389,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();          // nothing above touched global data (PDL: the predecessor grid may still be running)
 
-  if (warp == 0) {
+  if (warp == ATT2_TMA_WARP) {
     // ===================== TMA producer (whole warp walks the loop, one elected lane issues)
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, (uint32_t)(2 * q_bytes));
@@ -409,7 +415,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       __syncwarp();
       if (++st == nstages) { st = 0; ph ^= 1u; }
     }
-  } else if (warp == 1) {
+  } else if (warp == ATT2_MMA_WARP) {
     // ===================== MMA issuer
     const uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV);
     // p_f16 variant: P (A operand, from TMEM) and V^T (B operand) are both IEEE half (formats 0)
@@ -451,6 +457,52 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     };
     mbar_wait(&kv_full[0], 0, 23);
     tc_fence_after();
+    if (p_sep && p.stagger > 0) {
+      // EXPERIMENT, off by default (SDB_ATTN_STAGGER=<clocks> enables it): event-driven issue with tile 1 started
+      // <clocks> after tile 0. In lock step both tiles' softmax warps sit in the exponential loop at the same time
+      // (the sub-partitions are saturated) and then in the TMEM load / row maximum / P store phases at the same
+      // time (they idle); staggered, the exponential loop of a tile alone on its sub-partitions does run faster
+      // (1180 instead of 1900 clk per key block) - but tcgen05.mma issue blocks the issuing thread while the
+      // tensor pipe is busy, each tile then waits ~1500 clk for its next S, and the kernel is 10 % SLOWER
+      // (S = 4096, d = 40: 952 us against 844 us; deeper K/V ring and issuer warp id made no difference).
+      auto ready = [&](uint64_t* bar, uint32_t parity) {
+        return __shfl_sync(0xffffffffu, mbar_test_wait(bar, parity) ? 1 : 0, 0) != 0;
+      };
+      int jq[2] = {1, 0};              // next key block whose scores are to be issued, per tile
+      int jp[2] = {0, 0};              // next key block whose P.V is to be issued
+      issue_qk(0, 0);
+      const long long t_start = clock64();
+      unsigned spins = 0;
+      while (jp[0] < nkv || jp[1] < nkv) {
+        bool progress = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (jq[t] < nkv) {
+            const int stg = jq[t] % nstages;
+            const uint32_t ph = (uint32_t)((jq[t] / nstages) & 1);
+            bool ok = (jq[t] == 0) ? (clock64() - t_start >= (long long)p.stagger)
+                                   : ready(&s_free[t], (uint32_t)((jq[t] - 1) & 1));
+            if (ok && ready(&kv_full[stg], ph)) {
+              tc_fence_after();
+              issue_qk(t, stg);
+              if (t == 0 && lane == 0) ATT_STAMP(jq[0] - 1, 7);      // scores of the NEXT block issued (row of block j)
+              ++jq[t];
+              progress = true;
+            }
+          }
+          if (jp[t] < nkv && jp[t] < jq[t] && ready(&p_full[t], (uint32_t)(jp[t] & 1))) {
+            tc_fence_after();
+            // the K/V stage is released by whichever tile's product over it is issued second
+            issue_pv(t, jp[t] % nstages, jp[t] == 0, jp[1 - t] > jp[t]);
+            if (t == 0 && lane == 0) ATT_STAMP(jp[0], 6);
+            ++jp[t];
+            progress = true;
+          }
+        }
+        if (progress) spins = 0;
+        else if (++spins > (1u << 24)) { if (lane == 0) atomicCAS(&g_sdb_fault, 0u, (33u << 8) | 1u); break; }
+      }
+    } else {
     issue_qk(0, 0);
     issue_qk(1, 0);
     int st = 0;
@@ -497,9 +549,10 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       st = st_next;
       ph_kv = ph_next;
     }
+    }
   } else {
-    // ===================== softmax / correction / output: warps 2-5 tile 0, warps 6-9 tile 1
-    const int t = (warp - 2) >> 2;
+    // ===================== softmax / correction / output: warps 0-3 tile 0, warps 4-7 tile 1
+    const int t = warp >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int qrow = q0 + t * ATT_BQ + row;
@@ -686,7 +739,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == ATT2_MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace sdb
@@ -748,6 +801,11 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.causal = a->causal;
   p.scale_log2 = a->q_prescaled ? 1.0f : a->scale * 1.4426950408889634f;
   p.prescaled = a->q_prescaled ? 1 : 0;
+  {
+    static int stagger = -1;
+    if (stagger < 0) { const char* ev = getenv("SDB_ATTN_STAGGER"); stagger = ev ? atoi(ev) : 0; }
+    p.stagger = stagger;
+  }
   p.dchunks = (a->d + 63) / 64;
   p.dk_steps = (a->d + 15) / 16;
   p.dv_pad = dv_pad;
