@@ -75,7 +75,17 @@ typedef struct sdb_gemm_args {
   int out_f16;            /* 16-bit `out` is IEEE half instead of bf16 (Cout % 32 == 0, no split-K)  */
   int epi_mode;           /* epilogue: 0 = choose; 1 = per-lane global stores; 2 = TMA bulk stores whenever
                              the output geometry / alignment allows (default only for K <= 2048)          */
+  float* gn_part;         /* optional: GroupNorm partial statistics of the fp32 OUTPUT, written by the epilogue:
+                             fp32 [samples][K][Cout][2] = {sum, sum of squares} per 32-row slab and channel,
+                             K = sdb_gemm_gn_slabs(...). Needs out_fp32, no split-K, Cout % 32 == 0. The
+                             consumer reduces them with sdb_groupnorm_reduce_partials instead of reading the
+                             tensor once more for its statistics (nn.GroupNorm after nn.Conv2d:
+                             sd/diffusion.py:123-135,255). NULL = off.                                     */
+  int gn_hw;              /* LINEAR with gn_part: rows per sample (multiple of 32, divides M)              */
 } sdb_gemm_args;
+
+/* Slabs per sample (K above) for a given problem, 0 = gn_part unsupported for this geometry. */
+int sdb_gemm_gn_slabs(int kind, int NB, int HI, int WI, int M, int gn_hw);
 
 /* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,
  * 545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112,121,129,235-339;
@@ -130,7 +140,14 @@ int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, l
  * 202,738; sd/decoder.py:162,175,335); writes bf16 NHWC [NB, HW, C0 + C1]. */
 int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats, const float* gamma,
                         const float* beta, void* out, int NB, long long HW, int C0, int C1,
-                        int groups, float eps, int silu, int x0_fp32, int x1_fp32, void* stream);
+                        int groups, float eps, int silu, int x0_fp32, int x1_fp32, int stat_chunks,
+                        void* stream);
+/* Statistics without a pass over the tensor: reduces the partial sums the producing GEMM epilogues wrote
+ * (sdb_gemm_args::gn_part; part0 [NB][K0][C0][2], part1 [NB][K1][C1][2] for a channel concat or NULL) into
+ * `stats` as ONE chunk - follow with sdb_groupnorm_apply(..., stat_chunks = 1). stat_chunks = 0 above means
+ * "what sdb_groupnorm_stats wrote". */
+int sdb_groupnorm_reduce_partials(const float* part0, const float* part1, double* stats, int NB, int K0, int K1,
+                                  int C0, int C1, int groups, void* stream);
 /* One-pass GroupNorm (+SiLU) for fp32 NHWC inputs: a thread-block cluster keeps (sample, slab of groups) resident
  * in shared memory, so the tensor is read from HBM once and no statistics buffer exists. Same arithmetic
  * contract as stats + apply (fp64 combination in a fixed order). sdb_groupnorm_fused_supported(): 0 = no plan

@@ -19,7 +19,7 @@ class GemmArgs(ctypes.Structure):
         ("lda0", c_ll), ("lda1", c_ll), ("ldw", c_ll), ("ldo", c_ll), ("ldr", c_ll),
         ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
         ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int), ("out_f16", c_int),
-        ("epi_mode", c_int),
+        ("epi_mode", c_int), ("gn_part", c_void_p), ("gn_hw", c_int),
     ]
 
 
@@ -45,7 +45,10 @@ SIGNATURES = {
     "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
                             c_void_p],
     "sdb_groupnorm_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll,
-                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_void_p],
+                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p],
+    "sdb_groupnorm_reduce_partials": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p],
+    "sdb_gemm_gn_slabs": [c_int, c_int, c_int, c_int, c_int, c_int],
     "sdb_groupnorm_fused_supported": [c_ll, c_int, c_int, c_int],
     "sdb_groupnorm_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int,
                             c_float, c_int, c_void_p],

@@ -84,6 +84,13 @@ struct GemmTcParams {
   float* workspace;        // [nsplit][M_total][N] fp32 when nsplit > 1
   long long m_total;
   uint32_t fd_mul[4], fd_shr[4];   // fast division by n_tiles, m_tiles, tiles_w, tiles_h (decode_tile)
+  // GroupNorm statistics of the OUTPUT, produced by the epilogue: per (sample, 32-row slab, channel) {sum, sum of
+  // squares} of the final fp32 values -> gn_part[n][k][N][2]; a small kernel reduces them per group, so the
+  // consumer's statistics pass (one more read of the tensor) disappears. nullptr = off.
+  float* gn_part;
+  int gn_K;                // slabs per sample
+  int gn_hw;               // rank-2 outputs: rows per sample (multiple of 32)
+  int gn_spq;              // conv outputs: slabs of one sample inside a tile = min(4, bw*bh/32)
   // TMA epilogue (short reductions, where the epilogue bounds the tile time): thread = row, result staged in
   // swizzled shared memory and written with cp.async.bulk.tensor stores, fp32 residual fetched by TMA loads
   int epi_tma;
@@ -105,6 +112,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 struct TileCoord {
   int n0, w0, h0, nb0, z, kb_begin, nkb;
+  int sp;                  // index of the tile's (w, h) patch inside a sample: th * tiles_w + tw
 };
 
 // Debug timeline (sdb_debug_gemm_trace): CTA 0 records SM-clock stamps per tile, 8 slots each:
@@ -142,6 +150,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
   const int tw_i = mt - q * p.tiles_w;
   const int tn_i = fast_div(q, p.fd_mul[3], p.fd_shr[3]);
   const int th_i = q - tn_i * p.tiles_h;
+  t.sp = th_i * p.tiles_w + tw_i;
   t.w0 = tw_i * p.bw;
   t.h0 = th_i * p.bh;
   t.nb0 = tn_i * p.bn;
@@ -527,6 +536,26 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         fence_proxy_async();
         __syncwarp();
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 7);
+        if (p.gn_part != nullptr) {
+          // GroupNorm statistics of the chunk (rank-2 outputs, fp32 result resident in the slot): lane = column,
+          // 32 conflict-free reads down the swizzled rows
+          const int row0 = c1;                                    // first row of the slab
+          const int nrow = min(32, (int)p.m_total - row0);
+          const uint32_t sbase = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES) + (uint32_t)((lane & 3) * 4);
+          const uint32_t cpiece = (uint32_t)(lane >> 2);
+          float cs = 0.f, cq = 0.f;
+          for (int r = 0; r < nrow; ++r) {
+            float vv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vv)
+                         : "r"(sbase + (uint32_t)(r * 128) + ((cpiece ^ (uint32_t)(r & 7)) << 4)));
+            cs += vv;
+            cq = fmaf(vv, vv, cq);
+          }
+          const int sn = row0 / p.gn_hw;
+          const long long slab = (long long)sn * p.gn_K + (row0 - sn * p.gn_hw) / 32;
+          if (col0 + lane < p.N)
+            *reinterpret_cast<float2*>(p.gn_part + (slab * p.N + col0 + lane) * 2) = make_float2(cs, cq);
+        }
         if (lane == 0) {
           const uint32_t fsrc = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES);
           if (p.a_rank == 2) {
@@ -666,6 +695,24 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       const int ch_first = (half + lt) & 1;     // alternate so both halves get the odd chunk in turn
       int mrow[8];
       rows_for(t, mrow);
+      // (sample, slab) of this warp's 32 rows for the GroupNorm partial sums
+      bool gn_ok = false;
+      long long gn_slab = 0;
+      if (p.gn_part != nullptr) {
+        const int r0 = q * 32;
+        if (p.a_rank == 2) {
+          const int row0 = t.w0 + r0;
+          const int sn = row0 / p.gn_hw;
+          gn_ok = row0 < p.WO;
+          gn_slab = (long long)sn * p.gn_K + (row0 - sn * p.gn_hw) / 32;
+        } else {
+          const int plane = p.bw * p.bh;
+          const int dn = r0 / plane;
+          const int sn = t.nb0 + dn;
+          gn_ok = (dn < p.bn) && (sn < p.NB);
+          gn_slab = (long long)sn * p.gn_K + t.sp * p.gn_spq + (r0 - dn * plane) / 32;
+        }
+      }
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
       mbar_wait(&tfull_bar[acc], (uint32_t)(lt / nbuf) & 1u, 3);
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 6); trace_epi(trc, lt, 1); }
@@ -787,6 +834,30 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 *reinterpret_cast<uint2*>(ob + (long long)mrow[i] * p.ldo) =
                     p.out_f16 ? make_uint2(pack_f16x2(x[i].x, x[i].y), pack_f16x2(x[i].z, x[i].w))
                               : make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+          }
+          if (p.gn_part != nullptr) {
+            // GroupNorm statistics of the values just written: this lane's 4 columns over its 8 rows, then
+            // over the 4 row groups of the warp (lane bits 3-4): column sums of the 32-row slab
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mrow[i] >= 0) {
+                cs.x += x[i].x; cs.y += x[i].y; cs.z += x[i].z; cs.w += x[i].w;
+                cq.x = fmaf(x[i].x, x[i].x, cq.x); cq.y = fmaf(x[i].y, x[i].y, cq.y);
+                cq.z = fmaf(x[i].z, x[i].z, cq.z); cq.w = fmaf(x[i].w, x[i].w, cq.w);
+              }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+              cq.x += __shfl_xor_sync(0xffffffffu, cq.x, o); cq.y += __shfl_xor_sync(0xffffffffu, cq.y, o);
+              cq.z += __shfl_xor_sync(0xffffffffu, cq.z, o); cq.w += __shfl_xor_sync(0xffffffffu, cq.w, o);
+            }
+            if (sub == 0 && gn_ok) {
+              float4* dst = reinterpret_cast<float4*>(p.gn_part + (gn_slab * p.N + col0 + cl) * 2);
+              dst[0] = make_float4(cs.x, cq.x, cs.y, cq.y);
+              dst[1] = make_float4(cs.z, cq.z, cs.w, cq.w);
+            }
           }
         } else {
   #pragma unroll
@@ -995,6 +1066,25 @@ extern "C" int sdb_debug_gemm_trace(int on, long long* out_host) {
   return e == cudaSuccess ? SDB_OK : SDB_ERR_CUDA;
 }
 
+// Slabs (32 output rows of one TMEM lane quadrant) per sample for the epilogue's GroupNorm partial sums, or 0
+// when a slab could straddle two samples / the geometry is unsupported.
+extern "C" int sdb_gemm_gn_slabs(int kind, int NB, int HI, int WI, int M, int gn_hw) {
+  using namespace sdb;
+  if (kind == SDB_GEMM_LINEAR) {
+    if (gn_hw <= 0 || gn_hw % 32 != 0 || M <= 0 || M % gn_hw != 0) return 0;
+    return gn_hw / 32;
+  }
+  if (NB <= 0 || HI <= 0 || WI <= 0) return 0;
+  const bool s2 = (kind != SDB_GEMM_CONV3X3_S1);
+  const int HO = s2 ? HI / 2 : HI, WO = s2 ? WI / 2 : WI;
+  int bw = 0, bh = 0, bn = 0;
+  if (pick_tile_box(NB, HO, WO, &bw, &bh, &bn)) return 0;
+  const int plane = bw * bh;
+  if (plane % 32 != 0) return 0;
+  const int spq = plane / 32 < 4 ? plane / 32 : 4;
+  return ((WO + bw - 1) / bw) * ((HO + bh - 1) / bh) * spq;
+}
+
 extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   using namespace sdb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -1141,6 +1231,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     const bool has16 = !f32o || a->out2 != nullptr;
     const int epi_mode = a->epi_mode;            // 0 auto, 1 never, 2 whenever eligible (also long reductions)
     bool ok = !no_epi_tma && epi_mode != 1 && !want_split && (nkb_all <= 32 || epi_mode == 2);
+    if (a->gn_part != nullptr && p.a_rank == 5) ok = false;      // conv outputs: statistics in the per-lane epilogue
     ok = ok && (block_n % 32 == 0 || n_tiles == 1);
     ok = ok && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && (f32o ? (ldo_eff % 4 == 0) : (ldo_eff % 8 == 0));
     if (a->out2) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) & 15u) == 0 && (ldo_eff % 8 == 0);
@@ -1242,6 +1333,25 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.ldr = a->ldr ? a->ldr : a->Cout;
   p.act = a->act;
   p.workspace = a->workspace;
+  if (a->gn_part != nullptr) {
+    const int K = sdb_gemm_gn_slabs(kind, a->NB, a->HI, a->WI, a->M, a->gn_hw);
+    const bool aligned = (ldo_eff % 4 == 0) && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 &&
+                         (!a->out2 || (reinterpret_cast<uintptr_t>(a->out2) & 7u) == 0) &&
+                         (!a->bias || a->bias_per_row || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0) &&
+                         (!a->residual || (a->res_fp32 && (ldr_eff % 4) == 0 &&
+                                           (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0)) &&
+                         (reinterpret_cast<uintptr_t>(a->gn_part) & 15u) == 0;
+    if (K <= 0 || !a->out_fp32 || nsplit != 1 || a->Cout % 32 != 0 || block_n % 32 != 0 || !aligned) {
+      set_error("sdb_gemm_tc: gn_part needs an fp32 output, no split-K, Cout %% 32 == 0, 16-byte aligned operands and "
+                "32-row slabs inside one sample (K=%d nsplit=%d block_n=%d)", K, nsplit, block_n);
+      return SDB_ERR_UNSUPPORTED;
+    }
+    p.gn_part = a->gn_part;
+    p.gn_K = K;
+    p.gn_hw = a->gn_hw;
+    const int plane = p.bw * p.bh;
+    p.gn_spq = (p.a_rank == 5) ? (plane / 32 < 4 ? plane / 32 : 4) : 0;
+  }
 
   {
     static bool configured[64] = {false};

@@ -388,6 +388,49 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
 }
 
 
+// Per-group statistics from the per-slab, per-channel partial sums a producing GEMM epilogue left behind
+// (sdb_gemm_args::gn_part): one block per (group, sample), fixed-order fp64 sums -> the same stats layout
+// gn_apply_kernel reads, as a single "chunk". part0: [NB][K0][C0][2], part1: [NB][K1][C1][2] (channel concat).
+__global__ void __launch_bounds__(128) gn_reduce_partials_kernel(const float* __restrict__ part0,
+                                                                 const float* __restrict__ part1,
+                                                                 double* __restrict__ stats, int K0, int K1, int C0,
+                                                                 int C1, int groups) {
+  pdl_trigger();
+  pdl_wait();
+  const int g = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+  const int cpg = (C0 + C1) / groups;
+  const int cbeg = g * cpg, cend = cbeg + cpg;
+  // channels of this group in source 0: [cbeg, min(cend, C0)); in source 1: [max(cbeg, C0) - C0, cend - C0)
+  const int n0 = max(0, min(cend, C0) - cbeg), n1 = cpg - n0;
+  double ds = 0.0, dq = 0.0;
+  for (int e = t; e < K0 * n0; e += 128) {
+    const int k = e / n0, c = cbeg + (e - k * n0);
+    const float2 v = *reinterpret_cast<const float2*>(part0 + (((long long)n * K0 + k) * C0 + c) * 2);
+    ds += (double)v.x; dq += (double)v.y;
+  }
+  if (n1 > 0) {
+    const int c1beg = max(cbeg, C0) - C0;
+    for (int e = t; e < K1 * n1; e += 128) {
+      const int k = e / n1, c = c1beg + (e - k * n1);
+      const float2 v = *reinterpret_cast<const float2*>(part1 + (((long long)n * K1 + k) * C1 + c) * 2);
+      ds += (double)v.x; dq += (double)v.y;
+    }
+  }
+  __shared__ double sh[2][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if ((t & 31) == 0) { sh[0][t >> 5] = ds; sh[1][t >> 5] = dq; }
+  __syncthreads();
+  if (t == 0) {
+    double* dst = stats + ((long long)n * GN_MAX_CHUNKS * groups + g) * 2;
+    dst[0] = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
+    dst[1] = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // One-pass GroupNorm (+SiLU): the tensor is read from HBM exactly once.
 //
@@ -605,10 +648,24 @@ extern "C" int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats
   return check_launch("gn_stats_kernel");
 }
 
+extern "C" int sdb_groupnorm_reduce_partials(const float* part0, const float* part1, double* stats, int NB, int K0,
+                                            int K1, int C0, int C1, int groups, void* stream) {
+  using namespace sdb;
+  if (!part0 || !stats || NB <= 0 || K0 <= 0 || groups <= 0 || groups > 64 || (C0 + C1) % groups != 0 ||
+      (C1 > 0 && (!part1 || K1 <= 0))) {
+    set_error("sdb_groupnorm_reduce_partials: bad arguments");
+    return SDB_ERR_ARG;
+  }
+  cudaError_t le = launch_k(gn_reduce_partials_kernel, dim3(groups, NB), dim3(128), 0, (cudaStream_t)stream, 1,
+                            part0, part1, stats, K0, K1, C0, C1, groups);
+  if (le != cudaSuccess) { set_error("gn_reduce_partials_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
+  return check_launch("gn_reduce_partials_kernel");
+}
+
 extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats,
                                    const float* gamma, const float* beta, void* out, int NB,
                                    long long HW, int C0, int C1, int groups, float eps, int silu,
-                                   int x0_fp32, int x1_fp32, void* stream) {
+                                   int x0_fp32, int x1_fp32, int stat_chunks, void* stream) {
   using namespace sdb;
   const int ctot = C0 + C1;
   if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 || groups > 64 ||
@@ -630,7 +687,7 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
   }
   cudaError_t le = launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
                             x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
-                            lanes, x0_fp32, x1_fp32, chunks);
+                            lanes, x0_fp32, x1_fp32, stat_chunks > 0 ? stat_chunks : chunks);
   if (le != cudaSuccess) { set_error("gn_apply_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_apply_kernel");
 }

@@ -28,6 +28,8 @@ CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
 FOLD_GEGLU = True
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
+# GroupNorm statistics accumulated by the epilogue of the GEMM that produces the tensor (sdb_gemm_args.gn_part)
+GN_EPILOGUE_STATS = os.environ.get("SDB_NO_GN_EPI") != "1"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,10 +184,12 @@ class Stream:
     reads the stream directly as its A operand (skip 1x1 convs, down/up-sampling convs, conv_output,
     the VAE attention projections). Branch tensors (GroupNorm/LayerNorm outputs, conv hidden, Q/K/V,
     attention outputs) are bf16."""
-    __slots__ = ("f", "b")
+    __slots__ = ("f", "b", "gp")
 
-    def __init__(self, f, b=None):
-        self.f, self.b = f, b
+    def __init__(self, f, b=None, gp=None):
+        # gp: GroupNorm partial statistics of `f` written by the epilogue of the GEMM that produced it
+        # (ops.gemm(gn_samples=...)), or None - the consuming GroupNorm then runs its own statistics pass
+        self.f, self.b, self.gp = f, b, gp
 
     @property
     def shape(self):
@@ -198,10 +202,20 @@ class Stream:
 
 
 def _stream(out, shape):
-    """(fp32, bf16) pair or a lone fp32 tensor from a kernel wrapper -> Stream viewed as `shape`."""
+    """(fp32, bf16[, partials]) tuple or a lone fp32 tensor from a kernel wrapper -> Stream viewed as `shape`."""
     if isinstance(out, tuple):
-        return Stream(out[0].view(shape), out[1].view(shape))
+        return Stream(out[0].view(shape), out[1].view(shape) if out[1] is not None else None,
+                      out[2] if len(out) > 2 else None)
     return Stream(out.view(shape))
+
+
+def _gn_samples(n, hw, c):
+    """n when a GroupNorm over (hw, c) per sample wants its statistics from the producer's epilogue, else None
+    (the small levels take the one-pass kernel, which reads the tensor once anyway)."""
+    if not GN_EPILOGUE_STATS:
+        return None
+    from . import _ext
+    return n if _ext.lib().sdb_groupnorm_fused_supported(hw, c, 0, 32) != 2 else None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,10 +225,16 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
     UNET_ResidualBlock (sd/diffusion.py:145-209) / VAE_ResidualBlock (sd/decoder.py:135-189)."""
     n, h, w, c0 = x.shape
     c1 = x1.shape[-1] if x1 is not None else 0
-    a = ops.groupnorm(x.f, pk.gn1_w, pk.gn1_b, x1=x1.f if x1 is not None else None, silu=True)
+    a = ops.groupnorm(x.f, pk.gn1_w, pk.gn1_b, x1=x1.f if x1 is not None else None, silu=True,
+                      part0=x.gp, part1=x1.gp if x1 is not None else None)
+    gs = _gn_samples(n, h * w, pk.cout)
     # the hidden tensor stays fp32: it is only ever read by GroupNorm, never as a tensor-core operand
-    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b, out_fp32=True)
-    a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True)
+    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b, out_fp32=True,
+                      gn_samples=gs)
+    hid_gp = None
+    if gs is not None:
+        hid, _, hid_gp = hid
+    a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True, part0=hid_gp)
     if pk.skip_w is None:
         res = x.f.view(-1, c0)
     else:
@@ -222,9 +242,9 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
                        a1=x1.bf16().view(-1, c1) if x1 is not None else None,
                        M=n * h * w, c0=c0, c1=c1, bias=pk.skip_b, out_fp32=True)
     out = ops.conv3x3(a2, pk.conv2_w, pk.cout, bias=pk.conv2_b, residual=res, out_fp32=True,
-                      out2=True if want_b16 else None)
+                      out2=True if want_b16 else None, gn_samples=gs)
     if isinstance(out, tuple):
-        return Stream(out[0], out[1])
+        return Stream(*out)
     return Stream(out)
 
 
@@ -260,7 +280,7 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     m = n * s
     d = c // pk.heads
     dev = x.f.device
-    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False)
+    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp)
     t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=True)
     # self-attention
     l1 = ops.layernorm(t0, *pk.ln1)
@@ -286,7 +306,7 @@ def run_unet_attn(pk, x, kv, want_b16=False):
         g = ops.linear(l3, pk.wg1, bias=pk.bg1)
         t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)
     out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=x.f.view(m, c), out_fp32=True,
-                     out2=True if want_b16 else None)
+                     out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c))
     return _stream(out, (n, h, w, c))
 
 
@@ -421,12 +441,16 @@ class UNetEngine:
             elif kind == "attn":
                 x = run_unet_attn(pk, x, next(kv_iter), want_b16=want)
             elif kind == "up":
+                nn_, hh_, ww_, _ = x.shape
                 o = ops.conv3x3(ops.upsample2x(x.bf16()), pk.w, pk.cout, bias=pk.b, out_fp32=True,
-                                out2=True if want else None)
+                                out2=True if want else None, gn_samples=_gn_samples(nn_, 4 * hh_ * ww_, pk.cout))
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "conv":
+                nn_, hh_, ww_, _ = x.shape
+                s2_ = pk.kind != ops.GEMM_CONV3X3_S1
                 o = ops.conv3x3(x.bf16(), pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True,
-                                out2=True if want else None)
+                                out2=True if want else None,
+                                gn_samples=_gn_samples(nn_, (hh_ * ww_) // (4 if s2_ else 1), pk.cout))
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "direct":
                 o = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=want)

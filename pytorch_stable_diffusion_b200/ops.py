@@ -131,8 +131,13 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
 
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
-         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0):
-    """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h."""
+         lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0,
+         gn_samples=None):
+    """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h.
+
+    gn_samples=N: the output is a GroupNorm input of N samples - the epilogue also writes per-slab, per-channel
+    partial statistics and the call returns (out, out2 or None, part or None); part is None when the geometry or
+    the tiling (split-K) cannot provide them and the consumer has to run its own statistics pass."""
     lib = _ext.lib()
     _chk(a0, torch.bfloat16, "a0")
     _chk(w, torch.bfloat16, "w")
@@ -198,6 +203,14 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.cta_pair = cta_pair
     args.out_f16 = 1 if out_f16 else 0
     args.epi_mode = epi_mode
+    part = None
+    if gn_samples is not None and out_fp32 and nsplit == 1 and cout % 32 == 0 and block_n % 32 == 0 and ldo == 0:
+        hw = rows // gn_samples
+        k_slabs = lib.sdb_gemm_gn_slabs(kind, args.NB, args.HI, args.WI, args.M, hw if kind == GEMM_LINEAR else 0)
+        if k_slabs > 0 and rows % gn_samples == 0:
+            part = torch.empty((gn_samples, k_slabs, cout, 2), device=a0.device, dtype=torch.float32)
+            args.gn_part = _p(part)
+            args.gn_hw = hw
     ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
                2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size()
                + (rows * cout * residual.element_size() if residual is not None else 0)
@@ -205,6 +218,8 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
                shape=f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps}")
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
     _prof_end(ev)
+    if gn_samples is not None:
+        return out, out2, part
     return (out, out2) if out2 is not None else out
 
 
@@ -221,6 +236,8 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
     out = gemm(x, w, cout, kind=kind, bias=bias, conv_dims=(n, h, wd), c0=c, **kw)
     s2 = kind != GEMM_CONV3X3_S1
     shape = (n, h // 2 if s2 else h, wd // 2 if s2 else wd, cout)
+    if kw.get("gn_samples") is not None:
+        return out[0].view(shape), (out[1].view(shape) if out[1] is not None else None), out[2]
     if isinstance(out, tuple):
         return out[0].view(shape), out[1].view(shape)
     return out.view(shape)
@@ -249,9 +266,10 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
 
 
 _NO_GN_FUSED = _os.environ.get("SDB_NO_GN_FUSED") == "1"     # A/B switch: always stats + apply
+_NO_GN_EPI = _os.environ.get("SDB_NO_GN_EPI") == "1"         # A/B switch: ignore epilogue partial statistics
 
 
-def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fused=None):
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fused=None, part0=None, part1=None):
     """GroupNorm (+SiLU) over NHWC x0 ++ x1 (channel concat; each bf16 or fp32); returns bf16
     [N, H, W, C0+C1]. fp32 inputs whose (sample, group slab) fits a cluster's shared memory take the
     one-pass kernel (fused=None: when supported; True: required; False: never)."""
@@ -276,12 +294,20 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
-    ev = _prof("groupnorm", 0.0, 2.0 * in_bytes + 2.0 * (nel0 + nel1))
-    _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
-               "sdb_groupnorm_stats")
+    have_parts = part0 is not None and (x1 is None or part1 is not None) and not _NO_GN_EPI
+    ev = _prof("groupnorm", 0.0, (1.0 if have_parts else 2.0) * in_bytes + 2.0 * (nel0 + nel1))
+    if have_parts:
+        # statistics from the partial sums the producers' epilogues wrote: no pass over the tensor
+        _ext.check(lib.sdb_groupnorm_reduce_partials(_p(part0), _p(part1), _p(stats), n, part0.shape[1],
+                                                     part1.shape[1] if part1 is not None else 0, c0, c1, groups,
+                                                     _stream()), "sdb_groupnorm_reduce_partials")
+    else:
+        _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
+                   "sdb_groupnorm_stats")
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
     _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
-                                       c0, c1, groups, float(eps), 1 if silu else 0, f0, f1, _stream()),
+                                       c0, c1, groups, float(eps), 1 if silu else 0, f0, f1,
+                                       1 if have_parts else 0, _stream()),
                "sdb_groupnorm_apply")
     _prof_end(ev)
     return out

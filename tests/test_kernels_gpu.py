@@ -205,6 +205,65 @@ def test_conv3x3_tma_epilogue(NB, H, W, C0, C1, Cout, kind):
     assert torch.equal(got, ops.gemm(x0, pack3x3(w), Cout, epi_mode=1, **kw))
 
 
+# ------------------------------------------------------------------------------------ GN statistics in the epilogue
+def _check_partials(part, y, n, name):
+    """part [n][K][C][2] must add up (over the slabs) to the per-sample column sums / sums of squares of y."""
+    C = y.shape[-1]
+    yv = y.view(n, -1, C).double()
+    got = part.double().sum(1)
+    ref_s, ref_q = yv.sum(1), (yv * yv).sum(1)
+    report(f"{name} partial sums", got[..., 0], ref_s, 1e-5)
+    report(f"{name} partial sums of squares", got[..., 1], ref_q, 1e-5)
+
+
+@pytest.mark.parametrize("n,hw,K,N", [(2, 4096, 320, 320), (3, 1024, 640, 640), (2, 256, 2560, 1280), (4, 64, 1280, 1280)])
+def test_linear_gn_partials(n, hw, K, N):
+    """Short reductions take the TMA epilogue, K = 2560 the per-lane one: both must leave the statistics."""
+    ops = _ops()
+    setup_exact_fp32()
+    M = n * hw
+    a = rnd(M, K).bfloat16()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).bfloat16()
+    b = rnd(N, seed=2)
+    r = rnd(M, N, seed=3)
+    out, out2, part = ops.linear(a, w, bias=b, residual=r, out_fp32=True, out2=True, nsplit=1, gn_samples=n)
+    assert part is not None and part.shape == (n, hw // 32, N, 2)
+    report(f"linear gn {M}x{K}x{N}", out, a.float() @ w.float().t() + b + r, 2e-3)
+    _check_partials(part, out, n, f"linear {M}x{K}x{N}")
+    assert torch.equal(out2, out.bfloat16())
+    g = rnd(N, seed=4) + 1.0
+    be = rnd(N, seed=5)
+    y = ops.groupnorm(out.view(n, hw, N), g, be, silu=True, fused=False, part0=part)
+    ref = F.silu(F.group_norm(out.view(n, hw, N).permute(0, 2, 1), 32, g, be, 1e-5).permute(0, 2, 1))
+    report(f"groupnorm from epilogue partials {M}x{N}", y, ref, 6e-3)
+
+
+@pytest.mark.parametrize("NB,H,C0,C1,Cout", [(2, 64, 64, 0, 320), (3, 32, 128, 64, 640), (2, 16, 128, 0, 1280),
+                                             (5, 8, 64, 0, 320), (2, 96, 64, 0, 64), (2, 48, 64, 0, 64)])
+def test_conv3x3_gn_partials(NB, H, C0, C1, Cout):
+    ops = _ops()
+    setup_exact_fp32()
+    x0 = rnd(NB, H, H, C0).bfloat16()
+    x1 = rnd(NB, H, H, C1, seed=5).bfloat16() if C1 else None
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    r = rnd(NB * H * H, Cout, seed=3)
+    out, out2, part = ops.gemm(x0, pack3x3(w), Cout, kind=ops.GEMM_CONV3X3_S1, a1=x1, bias=b, residual=r,
+                               conv_dims=(NB, H, H), c0=C0, c1=C1, out_fp32=True, out2=True, nsplit=1, gn_samples=NB)
+    assert part is not None
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout) + r
+    report(f"conv gn {C0 + C1}->{Cout}@{H}", out, ref, 3e-3)
+    _check_partials(part, out, NB, f"conv {C0 + C1}->{Cout}@{H}")
+    # channel concat of two producers' partials
+    g = rnd(2 * Cout, seed=4) + 1.0
+    be = rnd(2 * Cout, seed=5)
+    o3 = out.view(NB, H * H, Cout)
+    y = ops.groupnorm(o3, g, be, x1=o3, silu=False, fused=False, part0=part, part1=part)
+    refn = F.group_norm(torch.cat([o3, o3], -1).permute(0, 2, 1), 32, g, be, 1e-5).permute(0, 2, 1)
+    report(f"groupnorm concat from partials {Cout}+{Cout}@{H}", y, refn, 6e-3)
+
+
 # ------------------------------------------------------------------------------------ conv
 def pack3x3(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()

@@ -50,14 +50,18 @@ def lin_case(M, K, Cout):
     return f"linear {M}x{K}x{Cout} +res fp32", run, 2.0 * M * K * Cout
 
 
-cases = [conv_case(16, 8, 1280, 0, 1280), conv_case(16, 8, 1280, 1280, 1280), conv_case(16, 16, 1280, 0, 1280),
+if "--big" in sys.argv:
+    cases = [conv_case(16, 64, 320, 0, 320), conv_case(16, 32, 640, 0, 640), conv_case(16, 64, 320, 320, 320),
+             conv_case(16, 32, 640, 640, 640), lin_case(65536, 320, 320)]
+else:
+  cases = [conv_case(16, 8, 1280, 0, 1280), conv_case(16, 8, 1280, 1280, 1280), conv_case(16, 16, 1280, 0, 1280),
          conv_case(16, 16, 1280, 1280, 1280), lin_case(4096, 1280, 1280), lin_case(1024, 1280, 1280),
          lin_case(16384, 640, 640)]
 for name, run, fl in cases:
     res = []
     auto = timed(lambda: run(0, 0, 0))
     for bn in (80, 128, 160, 256, 320):
-        for ns in (1, 2, 3, 4, 6, 8):
+        for ns in ((1,) if "--big" in sys.argv else (1, 2, 3, 4, 6, 8)):
             for pair in (1, 2):
                 try:
                     t = timed(lambda: run(bn, ns, pair), iters=10)
