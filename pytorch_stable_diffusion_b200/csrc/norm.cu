@@ -391,43 +391,68 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
 // Per-group statistics from the per-slab, per-channel partial sums a producing GEMM epilogue left behind
 // (sdb_gemm_args::gn_part): one block per (group, sample), fixed-order fp64 sums -> the same stats layout
 // gn_apply_kernel reads, as a single "chunk". part0: [NB][K0][C0][2], part1: [NB][K1][C1][2] (channel concat).
-__global__ void __launch_bounds__(128) gn_reduce_partials_kernel(const float* __restrict__ part0,
+__global__ void __launch_bounds__(256) gn_reduce_partials_kernel(const float* __restrict__ part0,
                                                                  const float* __restrict__ part1,
                                                                  double* __restrict__ stats, int K0, int K1, int C0,
                                                                  int C1, int groups) {
   pdl_trigger();
   pdl_wait();
-  const int g = blockIdx.x, n = blockIdx.y, t = threadIdx.x;
+  // block = (32 channel lanes, 8 slab lanes): every load is independent of the others (the kernel is a latency
+  // chain otherwise - 10 dependent L2 round trips per thread in its first form), four slabs in flight per thread
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
   const int cpg = (C0 + C1) / groups;
   const int cbeg = g * cpg, cend = cbeg + cpg;
   // channels of this group in source 0: [cbeg, min(cend, C0)); in source 1: [max(cbeg, C0) - C0, cend - C0)
   const int n0 = max(0, min(cend, C0) - cbeg), n1 = cpg - n0;
   double ds = 0.0, dq = 0.0;
-  for (int e = t; e < K0 * n0; e += 128) {
-    const int k = e / n0, c = cbeg + (e - k * n0);
-    const float2 v = *reinterpret_cast<const float2*>(part0 + (((long long)n * K0 + k) * C0 + c) * 2);
-    ds += (double)v.x; dq += (double)v.y;
-  }
-  if (n1 > 0) {
-    const int c1beg = max(cbeg, C0) - C0;
-    for (int e = t; e < K1 * n1; e += 128) {
-      const int k = e / n1, c = c1beg + (e - k * n1);
-      const float2 v = *reinterpret_cast<const float2*>(part1 + (((long long)n * K1 + k) * C1 + c) * 2);
+  for (int cc = cx; cc < n0; cc += 32) {
+    const float* base = part0 + ((long long)n * K0 * C0 + cbeg + cc) * 2;
+    int k = ky;
+    for (; k + 24 < K0; k += 32) {
+      const float2 v0 = *reinterpret_cast<const float2*>(base + (long long)k * C0 * 2);
+      const float2 v1 = *reinterpret_cast<const float2*>(base + (long long)(k + 8) * C0 * 2);
+      const float2 v2 = *reinterpret_cast<const float2*>(base + (long long)(k + 16) * C0 * 2);
+      const float2 v3 = *reinterpret_cast<const float2*>(base + (long long)(k + 24) * C0 * 2);
+      ds += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+      dq += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+    }
+    for (; k < K0; k += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(base + (long long)k * C0 * 2);
       ds += (double)v.x; dq += (double)v.y;
     }
   }
-  __shared__ double sh[2][4];
+  if (n1 > 0) {
+    const int c1beg = max(cbeg, C0) - C0;
+    for (int cc = cx; cc < n1; cc += 32) {
+      const float* base = part1 + ((long long)n * K1 * C1 + c1beg + cc) * 2;
+      int k = ky;
+      for (; k + 24 < K1; k += 32) {
+        const float2 v0 = *reinterpret_cast<const float2*>(base + (long long)k * C1 * 2);
+        const float2 v1 = *reinterpret_cast<const float2*>(base + (long long)(k + 8) * C1 * 2);
+        const float2 v2 = *reinterpret_cast<const float2*>(base + (long long)(k + 16) * C1 * 2);
+        const float2 v3 = *reinterpret_cast<const float2*>(base + (long long)(k + 24) * C1 * 2);
+        ds += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+        dq += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+      }
+      for (; k < K1; k += 8) {
+        const float2 v = *reinterpret_cast<const float2*>(base + (long long)k * C1 * 2);
+        ds += (double)v.x; dq += (double)v.y;
+      }
+    }
+  }
+  __shared__ double sh[2][8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ds += __shfl_xor_sync(0xffffffffu, ds, o);
     dq += __shfl_xor_sync(0xffffffffu, dq, o);
   }
-  if ((t & 31) == 0) { sh[0][t >> 5] = ds; sh[1][t >> 5] = dq; }
+  if (cx == 0) { sh[0][ky] = ds; sh[1][ky] = dq; }
   __syncthreads();
-  if (t == 0) {
+  if (threadIdx.x == 0) {
     double* dst = stats + ((long long)n * GN_MAX_CHUNKS * groups + g) * 2;
-    dst[0] = (sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3]);
-    dst[1] = (sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3]);
+    dst[0] = ((sh[0][0] + sh[0][1]) + (sh[0][2] + sh[0][3])) + ((sh[0][4] + sh[0][5]) + (sh[0][6] + sh[0][7]));
+    dst[1] = ((sh[1][0] + sh[1][1]) + (sh[1][2] + sh[1][3])) + ((sh[1][4] + sh[1][5]) + (sh[1][6] + sh[1][7]));
   }
 }
 
@@ -656,7 +681,7 @@ extern "C" int sdb_groupnorm_reduce_partials(const float* part0, const float* pa
     set_error("sdb_groupnorm_reduce_partials: bad arguments");
     return SDB_ERR_ARG;
   }
-  cudaError_t le = launch_k(gn_reduce_partials_kernel, dim3(groups, NB), dim3(128), 0, (cudaStream_t)stream, 1,
+  cudaError_t le = launch_k(gn_reduce_partials_kernel, dim3(groups, NB), dim3(256), 0, (cudaStream_t)stream, 1,
                             part0, part1, stats, K0, K1, C0, C1, groups);
   if (le != cudaSuccess) { set_error("gn_reduce_partials_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_reduce_partials_kernel");

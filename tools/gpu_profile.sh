@@ -14,5 +14,13 @@ for c in conv3x3_res_320_320_64 linear_proj_65536x320x320 attn_self_S4096; do
       -o gpurun_out/${TAG}_prof_$c python tools/kernel_bench.py --attn-mode 1 --only $c --iters 1 --warmup 1 \
       > gpurun_out/${TAG}_ncu_$c.log 2>&1
 done
+# HBM-bound side: GroupNorm apply (+SiLU) and LayerNorm, 2nd matching launch of the named kernel
+for pair in "groupnorm_x_320_64:gn_apply_kernel" "layernorm_65536x320:layernorm_f32_kernel"; do
+  c=${pair%%:*}; k=${pair##*:}
+  python tools/kernel_bench.py --only $c --iters 1 --warmup 1 > gpurun_out/${TAG}_plain_$c.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k "regex:^(void )?$k" -s 1 -c 1 -f \
+      -o gpurun_out/${TAG}_prof_$c python tools/kernel_bench.py --only $c --iters 1 --warmup 1 \
+      > gpurun_out/${TAG}_ncu_$c.log 2>&1
+done
 tail -3 gpurun_out/${TAG}_kernel_bench.log
 ls -la gpurun_out | tail -20
