@@ -44,6 +44,8 @@ struct AttnParams {
   int o_col;     // one-tile kernel: first TMEM column of O
   int exp_poly;  // two-tile kernel: every fourth exponential on the FMA pipe (exp2_poly)
   int prescaled; // scale_log2 == 1: scores arrive in log2 units
+  int tiles_per_cta;  // one-tile kernel, single key block, no mask: query tiles one CTA walks (K / V^T, TMEM and
+                      // barriers set up once); 1 = one tile per CTA
   int stagger;   // two-tile kernel, separate P: clocks tile 1 starts after tile 0 (0 = fixed issue order, lock step)
 };
 
@@ -96,6 +98,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint8_t* q_smem = smem;
   uint8_t* kv_smem = smem + q_bytes;
   const int kv_stages = (p.tmem_cols == 256) ? 1 : 2;      // a single key block needs one stage
+  const int T = p.tiles_per_cta;
   uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + kv_stages * stage_bytes);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
@@ -104,6 +107,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* p_full = bars + 7;    // [2]
   uint64_t* o_done = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_empty = bars + 11;  // multi-tile form: Q consumed by its Q.K^T, the next tile's Q may be loaded
+  uint64_t* o_free = bars + 12;   // O (and S/P) read out: the next tile's Q.K^T may start
 
   int nkv = (p.Skv + ATT_BKV - 1) / ATT_BKV;
   if (p.causal) {
@@ -123,6 +128,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&p_full[i], 128);
     }
     mbar_init(o_done, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 128);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -136,7 +143,137 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   pdl_wait();          // nothing above touched global data (PDL: the predecessor grid may still be running)
   const uint32_t tmem_o = tmem_base + (uint32_t)p.o_col;
 
-  if (warp == 0) {
+  if (T > 1) {
+    // ===================== multi-tile form (cross-attention over the 77 CLIP tokens): one key block, no mask.
+    // The CTA walks T query tiles of its (sample, head): K / V^T are loaded once, TMEM and the barriers are set
+    // up once, the next Q tile is loaded as soon as its predecessor's Q.K^T has completed (it has that tile's
+    // softmax, P.V and store to arrive: S / P share TMEM columns, so the next Q.K^T waits for them anyway). Per tile the chain is
+    // Q.K^T -> softmax -> P.V -> store (~3 000 clk) instead of a whole CTA life (~9 600 clk); two CTAs per SM
+    // interleave their chains as before.
+    const int tile0 = blockIdx.x * T;
+    const int ntile = min(T, (p.S + ATT_BQ - 1) / ATT_BQ - tile0);
+    if (warp == 0) {
+      if (elect_one()) {
+        uint8_t* kd = kv_smem;
+        uint8_t* vd = kd + k_bytes;
+        mbar_arrive_expect_tx(&kv_full[0], (uint32_t)stage_bytes);
+        for (int c = 0; c < p.dchunks; ++c)
+          tma_load_4d(&p.map_k, &kv_full[0], kd + c * ATT_CHUNK_BYTES, c * 64, h, 0, n);
+        for (int c = 0; c < 2; ++c)
+          tma_load_3d(&p.map_vt, &kv_full[0], vd + c * v_chunk_bytes, c * 64, n, h * p.d);
+      }
+      __syncwarp();
+      for (int i = 0; i < ntile; ++i) {
+        if (i >= 1) mbar_wait(q_empty, (uint32_t)((i - 1) & 1), 41);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
+          for (int c = 0; c < p.dchunks; ++c)
+            tma_load_4d(&p.map_q, q_full, q_smem + c * ATT_CHUNK_BYTES, c * 64, h, (tile0 + i) * ATT_BQ, n);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV);
+      const uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, (uint32_t)p.dv_pad);
+      const uint32_t k_addr = smem_u32(kv_smem);
+      const uint32_t v_addr = k_addr + (uint32_t)k_bytes;
+      mbar_wait(&kv_full[0], 0, 42);
+      for (int i = 0; i < ntile; ++i) {
+        mbar_wait(q_full, (uint32_t)(i & 1), 43);
+        if (i > 0) mbar_wait(o_free, (uint32_t)((i - 1) & 1), 44);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t q_addr = smem_u32(q_smem);
+          for (int ks = 0; ks < p.dk_steps; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * ATT_CHUNK_BYTES + (ks & 3) * 32);
+            mma_ss(tmem_base, make_kmajor_sw128_desc(q_addr + off), make_kmajor_sw128_desc(k_addr + off), idesc_qk,
+                   ks > 0 ? 1u : 0u);
+          }
+          tc_commit(&s_full[0]);
+          tc_commit(q_empty);
+        }
+        __syncwarp();
+        mbar_wait(&p_full[0], (uint32_t)(i & 1), 45);
+        tc_fence_after();
+        if (elect_one()) {
+          for (int ks = 0; ks < ATT_BKV / 16; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * v_chunk_bytes + (ks & 3) * 32);
+            mma_ts(tmem_o, tmem_base + (uint32_t)(ks * 8), make_kmajor_sw128_desc(v_addr + off), idesc_pv,
+                   ks > 0 ? 1u : 0u);
+          }
+          tc_commit(o_done);
+        }
+        __syncwarp();
+      }
+    } else {
+      const int quad = warp & 3;
+      const int row = quad * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+      const float sl2 = p.scale_log2;
+      const uint32_t s_addr = tmem_base + lane_addr;
+      for (int i = 0; i < ntile; ++i) {
+        const int qrow = (tile0 + i) * ATT_BQ + row;
+        mbar_wait(&s_full[0], (uint32_t)(i & 1), 46);
+        tc_fence_after();
+        uint32_t sv[128];
+        tmem_ld32(s_addr + 0, sv + 0);
+        tmem_ld32(s_addr + 32, sv + 32);
+        tmem_ld32(s_addr + 64, sv + 64);
+        tmem_ld32(s_addr + 96, sv + 96);
+        tmem_ld_wait();
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 128; k += 2) {
+          if (k >= p.Skv) sv[k] = 0xff800000u;
+          if (k + 1 >= p.Skv) sv[k + 1] = 0xff800000u;
+          m0 = fmaxf(m0, __uint_as_float(sv[k]));
+          m1 = fmaxf(m1, __uint_as_float(sv[k + 1]));
+        }
+        const float mx = fmaxf(m0, m1);
+        const float mb = (mx == -INFINITY) ? 0.f : mx * sl2;
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t pk[64];
+#pragma unroll
+        for (int k = 0; k < 128; k += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sl2, -mb));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sl2, -mb));
+          l0 += p0; l1 += p1;
+          pk[k >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st32(s_addr + 0, pk + 0);
+        tmem_st32(s_addr + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[0]);
+        const float lsum = l0 + l1;
+        const float inv = (lsum > 0.f) ? 1.0f / lsum : 0.f;
+        mbar_wait(o_done, (uint32_t)(i & 1), 47);
+        tc_fence_after();
+        __nv_bfloat16* orow = p.out + ((long long)n * p.S + qrow) * p.ldo + (long long)h * p.d;
+        for (int c = 0; c < p.dv_pad; c += 16) {
+          uint32_t ov[16];
+          tmem_ld16(tmem_o + lane_addr + (uint32_t)c, ov);
+          tmem_ld_wait();
+          if (qrow < p.S) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              const int col = c + g * 8;
+              if (col + 8 <= p.d) {
+                uint4 u;
+                u.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+                u.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+                u.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+                u.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + col) = u;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(o_free);
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(q_full, (uint32_t)q_bytes);
@@ -845,9 +982,18 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     return check_launch("attn2_tc_kernel");
   }
   if (a->sum_row) { set_error("sdb_attention: sum_row does not fit the two-tile kernel for d = %d", a->d); return SDB_ERR_UNSUPPORTED; }
+  // single key block, no mask (cross-attention): a CTA walks several query tiles of its (sample, head)
+  const int q_tiles = (a->S + ATT_BQ - 1) / ATT_BQ;
+  p.tiles_per_cta = 1;
+  {
+    static int multi = -1;
+    if (multi < 0) { const char* ev = getenv("SDB_ATTN_MULTI_TILE"); multi = (ev && ev[0] == '0') ? 0 : 1; }
+    if (multi && single_block && !a->causal && q_tiles >= 2)
+      p.tiles_per_cta = q_tiles >= 16 ? 8 : (q_tiles >= 8 ? 4 : 2);
+  }
   const int smem_bytes = q_bytes + (single_block ? 1 : 2) * stage_bytes + 1024 + 256;
   if (smem_bytes > 227 * 1024) { set_error("sdb_attention: shared memory %d too large", smem_bytes); return SDB_ERR_UNSUPPORTED; }
-  dim3 grid((unsigned)((a->S + ATT_BQ - 1) / ATT_BQ), (unsigned)a->heads, (unsigned)a->NB);
+  dim3 grid((unsigned)((q_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta), (unsigned)a->heads, (unsigned)a->NB);
   (void)launch_k(attn_tc_kernel, grid, dim3(ATT_THREADS), (size_t)smem_bytes, (cudaStream_t)stream, 1, p);
   return check_launch("attn_tc_kernel");
 }

@@ -464,6 +464,11 @@ def ref_attention(q, k, v, causal):
     (2, 8, 160, 64, 64, False, 1.0),
     (2, 8, 40, 4096, 77, False, 1.0),     # cross-attention over the 77 CLIP tokens
     (2, 8, 160, 64, 77, False, 1.0),
+    (2, 8, 80, 1024, 77, False, 1.0),     # multi-tile form of the one-tile kernel: 4 tiles per CTA
+    (2, 8, 40, 1000, 77, False, 1.0),     # ... ragged last tile
+    (3, 8, 40, 256, 77, False, 1.0),      # ... 2 tiles per CTA
+    (2, 8, 40, 640, 100, False, 2.0),     # ... 5 tiles, 2 per CTA: the last CTA walks one
+    (2, 8, 160, 256, 77, False, 1.0),     # d = 160: two key stages, one tile per CTA
     (2, 12, 64, 77, 77, True, 1.0),       # CLIP causal self-attention
     (2, 8, 40, 1024, 1024, False, 6.0),   # peaky logits: exercises the lazy O rescale
     (2, 8, 80, 576, 576, False, 1.0),     # 768^2 levels (ragged tiles)
