@@ -624,6 +624,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                        (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 7u) == 0))
                     : ((reinterpret_cast<uintptr_t>(p.out) & 7u) == 0)) &&
         (p.bias_mode != 1 || (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0);
+    const bool split_fast = (p.nsplit > 1) && (p.N % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.workspace) & 15u) == 0);
     const uint32_t ring_addr = smem_u32(epi_smem + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES +
                                         e * (GEMM_RES_RING * GEMM_EPI_STAGE_BYTES));
     // (dw, dh, dn) of the 8 tile rows this lane touches in phase 2 (local rows sub + 4*i): fixed for the
@@ -771,7 +772,20 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
         // phase 2
         const uint32_t rslot = ring_addr + (uint32_t)(rd_slot * GEMM_EPI_STAGE_BYTES);
-        if (fast_ok && ncol == 32) {
+        if (split_fast && ncol == 32) {
+          // split-K partial sums: raw fp32 accumulator rows into this slice of the workspace, 16 bytes per lane
+          float* wb = p.workspace + (long long)t.z * p.m_total * p.N + col0 + cl;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int lr = i * 4 + sub;
+            const uint32_t swz = (uint32_t)(lr * 128 + ((c4 ^ (lr & 7)) << 4));
+            float4 x;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                         : "r"(stg_addr + swz));
+            if (mrow[i] >= 0) *reinterpret_cast<float4*>(wb + (long long)mrow[i] * p.N) = x;
+          }
+        } else if (fast_ok && ncol == 32) {
           // fast path (full chunk, aligned pointers): all shared-memory reads first, then the math,
           // then the stores - eight independent chains per lane, no per-element guards
           float4 x[8];
@@ -968,6 +982,48 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   } else {
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// Split-K finalize, four columns per thread (N % 4 == 0, 16-byte aligned fp32 operands, per-column bias or none):
+// the scalar form below spent its time in one 64-bit division per element.
+__global__ void gemm_splitk_finalize4_kernel(const float* __restrict__ ws, int nsplit, long long m_total, int N,
+                                             void* out, long long ldo, int out_fp32, const float* __restrict__ bias,
+                                             const float* __restrict__ residual, long long ldr, int act,
+                                             __nv_bfloat16* __restrict__ out2) {
+  pdl_trigger();
+  pdl_wait();
+  const int nv = N >> 2;
+  const long long totalv = m_total * nv;
+  const long long total = m_total * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < totalv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nv;
+    const int n = (int)(i - m * nv) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(ws + m * N + n);
+    for (int z = 1; z < nsplit; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (long long)z * total + m * N + n);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (bias != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    }
+    if (act != 0) {
+      acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act);
+      acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act);
+    }
+    if (residual != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(residual + m * ldr + n);
+      acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+    }
+    const uint2 h = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    if (out_fp32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * ldo + n) = acc;
+      if (out2) *reinterpret_cast<uint2*>(out2 + m * ldo + n) = h;
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + m * ldo + n) = h;
+    }
   }
 }
 
@@ -1397,6 +1453,22 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     const long long total = p.m_total * p.N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    const bool vec4 = (p.N % 4 == 0) && (p.ldo % 4 == 0) && p.bias_mode != 2 &&
+                      (p.residual == nullptr || (p.res_fp32 && p.ldr % 4 == 0 &&
+                                                 (reinterpret_cast<uintptr_t>(p.residual) & 15u) == 0)) &&
+                      (reinterpret_cast<uintptr_t>(p.workspace) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 &&
+                      (p.out2 == nullptr || (reinterpret_cast<uintptr_t>(p.out2) & 7u) == 0) &&
+                      (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0);
+    if (vec4) {
+      int blocks4 = (int)((total / 4 + 255) / 256);
+      if (blocks4 > 148 * 8) blocks4 = 148 * 8;
+      (void)launch_k(gemm_splitk_finalize4_kernel, dim3(blocks4), dim3(256), 0, stream, 1,
+                     (const float*)p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias,
+                     reinterpret_cast<const float*>(p.residual), p.ldr, p.act, p.out2);
+      if ((rc = check_launch("gemm_splitk_finalize4_kernel"))) return rc;
+      return SDB_OK;
+    }
     (void)launch_k(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, 1,
         (const float*)p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias, p.bias_mode,
         p.residual, p.res_fp32, p.ldr, p.act, p.out2);
