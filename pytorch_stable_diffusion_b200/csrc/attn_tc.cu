@@ -641,6 +641,15 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       }
     } else {
     issue_qk(0, 0);
+    if (p.stagger < 0) {
+      // Fixed issue order, tile 1 started -stagger clocks after tile 0. In lock step both tiles' softmax warps sit
+      // in the exponential loop at the same time (the sub-partitions saturated) and then in the TMEM load / row
+      // maximum / P store phases at the same time (idle); nothing in the protocol re-synchronises the tiles, so an
+      // initial offset of about half a period persists and the phases of one tile fill the gaps of the other
+      // (period 3 060 -> 2 800 clk).
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)(-p.stagger)) { }
+    }
     issue_qk(1, 0);
     int st = 0;
     uint32_t ph_kv = 0;                 // phase of kv_full[next stage]
@@ -939,9 +948,12 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.scale_log2 = a->q_prescaled ? 1.0f : a->scale * 1.4426950408889634f;
   p.prescaled = a->q_prescaled ? 1 : 0;
   {
-    static int stagger = -1;
-    if (stagger < 0) { const char* ev = getenv("SDB_ATTN_STAGGER"); stagger = ev ? atoi(ev) : 0; }
-    p.stagger = stagger;
+    static int stagger = 0;
+    static bool stagger_set = false;
+    if (!stagger_set) { const char* ev = getenv("SDB_ATTN_STAGGER"); stagger = ev ? atoi(ev) : -1300; stagger_set = true; }
+    // default: fixed issue order, tile 1 started 1 300 clocks after tile 0 when there are enough key blocks for
+    // the offset to pay (S = 4096, d = 40: 843 -> 783 us; 1 100 / 1 500 / 1 900 clocks: 800 / 791 / 797 us)
+    p.stagger = (stagger < 0 && (a->Skv + ATT_BKV - 1) / ATT_BKV < 8) ? 0 : stagger;
   }
   p.dchunks = (a->d + 63) / 64;
   p.dk_steps = (a->d + 15) / 16;
