@@ -26,6 +26,8 @@ CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
 # W = W2 . W1[:4C], b = W2 . b1[:4C] + b2 (SURVEY.md "Hard parts"; the FLOP numerator in bench.py drops
 # by the saved 179 GFLOP per image-step accordingly). Set to False to run the two GEMMs separately.
 FOLD_GEGLU = True
+# ... and conv_output composed with it (see pack_unet_attn): one dual-source GEMM per attention block
+FOLD_FF_OUT = os.environ.get("SDB_NO_FOLD_FF_OUT") != "1"
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 # GroupNorm statistics accumulated by the epilogue of the GEMM that produces the tensor (sdb_gemm_args.gn_part)
@@ -151,6 +153,16 @@ def pack_unet_attn(m, dev):
         pk.wg = (w2 @ w1).to(torch.bfloat16).contiguous()
         pk.bg = (w2 @ b1 + b2).to(torch.float32).contiguous()
         pk.wg1 = None
+        pk.w_ffout = None
+        if FOLD_FF_OUT:
+            # conv_output is a 1x1 convolution of (feed-forward + its residual t2): one more affine map, so
+            #   conv_output(W_g l3 + b_g + t2) = [W_o W_g | W_o] . [l3 ; t2] + (W_o b_g + b_o)
+            # - ONE dual-source GEMM over the LayerNorm output and the bf16 shadow of the token stream instead of
+            # two GEMMs with a bf16 round trip of t3 in between (sd/diffusion.py:355-381)
+            wo = m.conv_output.weight.detach().to(device=dev, dtype=torch.float64).reshape(c, c)
+            bo = m.conv_output.bias.detach().to(device=dev, dtype=torch.float64)
+            pk.w_ffout = torch.cat([wo @ (w2 @ w1), wo], dim=1).to(torch.bfloat16).contiguous()
+            pk.b_ffout = (wo @ (w2 @ b1 + b2) + bo).to(torch.float32).contiguous()
     else:
         pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev)
         pk.bg1 = _f32(m.linear_geglu_1.bias[:4 * c], dev)
@@ -297,8 +309,15 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     o2 = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
     ops.attention(q, k2, vt2, o2, NB=n, heads=pk.heads, d=d, S=s, Skv=77, Skv_pad=CTX_PAD,
                   ldq=c, ldk=c, ldo=c)
-    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True)
+    ff_out = pk.wg1 is None and pk.w_ffout is not None
+    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True, out2=True if ff_out else None)
     # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
+    if ff_out:
+        t2, t2_b = t2
+        l3 = ops.layernorm(t2, *pk.ln3)
+        out = ops.gemm(l3, pk.w_ffout, c, a1=t2_b, M=m, c0=c, c1=c, bias=pk.b_ffout, residual=x.f.view(m, c),
+                       out_fp32=True, out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c))
+        return _stream(out, (n, h, w, c))
     l3 = ops.layernorm(t2, *pk.ln3)
     if pk.wg1 is None:
         t3 = ops.linear(l3, pk.wg, bias=pk.bg, residual=t2)       # folded affine map; only conv_output reads it: bf16
