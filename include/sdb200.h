@@ -82,6 +82,10 @@ typedef struct sdb_gemm_args {
                              tensor once more for its statistics (nn.GroupNorm after nn.Conv2d:
                              sd/diffusion.py:123-135,255). NULL = off.                                     */
   int gn_hw;              /* LINEAR with gn_part: rows per sample (multiple of 32, divides M)              */
+  const void* ax0;        /* CONV3X3_S1 only: extra 1x1 source accumulated into the same output tile - the    */
+  const void* ax1;        /* resblock's skip convolution (sd/diffusion.py:138-143,208): bf16 NHWC             */
+  int Cx0, Cx1;           /* [NB, HI, WI, Cx0] (++ [.., Cx1]); w rows then hold 9*(C0+C1) + Cx0 + Cx1 values,  */
+                          /* the 1x1 weights last; multiples of 64. NULL = off.                               */
 } sdb_gemm_args;
 
 /* Slabs per sample (K above) for a given problem, 0 = gn_part unsupported for this geometry. */

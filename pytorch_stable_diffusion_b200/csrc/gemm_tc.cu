@@ -49,10 +49,17 @@ struct GemmTcParams {
   int cblocks0, cblocks;   // 64-channel blocks in source 0 / in both sources
   int ntaps;
   int ktot;                // row length of W = ntaps * (C0 + C1)
-  int8_t tap_dc_sel[9];    // 0/1: add tap_dc_unit to the channel coordinate (stride-2 fold)
-  int8_t tap_dw[9];
-  int8_t tap_d2[9];
-  int8_t tap_dh[9];
+  int8_t tap_dc_sel[10];   // 0/1: add tap_dc_unit to the channel coordinate (stride-2 fold); entry 9 = centre tap
+  int8_t tap_dw[10];
+  int8_t tap_d2[10];
+  int8_t tap_dh[10];
+  // extra 1x1 source behind the nine taps of a stride-1 3x3 conv (the resblock's skip convolution accumulated into
+  // the same TMEM tile: sd/diffusion.py:138-143,208): channels Cx0 (+ Cx1 from a second tensor), W columns
+  // [9 * (C0 + C1), +Cx0 + Cx1)
+  CUtensorMap map_x0;
+  CUtensorMap map_x1;
+  int cblocks_x0, cblocks_x;
+  int nkb_total;           // ntaps * cblocks + cblocks_x
   int tap_dc_unit;
   // epilogue
   int N;                   // valid output columns (Cout)
@@ -155,9 +162,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
   t.h0 = th_i * p.bh;
   t.nb0 = tn_i * p.bn;
   t.n0 = n_tile * p.block_n;
-  const int nkb_total = p.ntaps * p.cblocks;
   t.kb_begin = t.z * p.per_split;
-  t.nkb = min(nkb_total, t.kb_begin + p.per_split) - t.kb_begin;
+  t.nkb = min(p.nkb_total, t.kb_begin + p.per_split) - t.kb_begin;
   return t;
 }
 
@@ -289,14 +295,17 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       trace_stamp(trc, ltp, 0);
       int tap = t.kb_begin / p.cblocks;
       int cb = t.kb_begin - tap * p.cblocks;
+      if (tap >= p.ntaps) { tap = p.ntaps; cb = t.kb_begin - p.ntaps * p.cblocks; }    // inside the extra 1x1 source
       const int wn = t.n0 + cta_rank * b_rows;
       for (int i = 0; i < t.nkb; ++i) {
         mbar_wait(&empty_bar[s], ph, 1);
         uint8_t* a_dst = smem + s * stage_bytes;
         uint8_t* b_dst = a_dst + GEMM_A_STAGE_BYTES;
-        const bool second = cb >= p.cblocks0;
-        const CUtensorMap* ma = second ? &p.map_a1 : &p.map_a0;
-        const int c = (second ? (cb - p.cblocks0) : cb) * GEMM_BK;
+        const bool extra = (tap == p.ntaps);                   // k-blocks of the extra 1x1 source (centre tap)
+        const int cbl0 = extra ? p.cblocks_x0 : p.cblocks0;
+        const bool second = cb >= cbl0;
+        const CUtensorMap* ma = extra ? (second ? &p.map_x1 : &p.map_x0) : (second ? &p.map_a1 : &p.map_a0);
+        const int c = (second ? (cb - cbl0) : cb) * GEMM_BK;
         const int wk = tap * ctot + cb * GEMM_BK;
         const int ca = c + p.tap_dc_sel[tap] * p.tap_dc_unit;
         const int cw = t.w0 + p.tap_dw[tap];
@@ -318,7 +327,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           }
         }
         __syncwarp();
-        if (++cb == p.cblocks) { cb = 0; ++tap; }
+        if (++cb == (extra ? p.cblocks_x : p.cblocks)) { cb = 0; ++tap; }
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       trace_stamp(trc, ltp, 1);
@@ -1237,6 +1246,29 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   const long long m_tiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
   p.m_total = (long long)p.NB * p.HO * p.WO;
   p.ktot = p.ntaps * ctot;
+  if (a->ax0 != nullptr) {
+    if (kind != SDB_GEMM_CONV3X3_S1 || a->Cx0 <= 0 || a->Cx0 % 64 != 0 || a->Cx1 % 64 != 0 || (a->Cx1 > 0 && !a->ax1) ||
+        a->C0 % 64 != 0 || a->C1 % 64 != 0) {
+      set_error("sdb_gemm_tc: the extra 1x1 source needs a stride-1 3x3 conv and channel counts that are multiples of 64");
+      return SDB_ERR_UNSUPPORTED;
+    }
+    p.cblocks_x0 = a->Cx0 / 64;
+    p.cblocks_x = p.cblocks_x0 + a->Cx1 / 64;
+    p.ktot += a->Cx0 + a->Cx1;
+    uint32_t box[5] = {64, (uint32_t)p.bw, 1, (uint32_t)p.bh, (uint32_t)p.bn};
+    const uint64_t WI = (uint64_t)a->WI, HI = (uint64_t)a->HI;
+    const uint64_t c0b = (uint64_t)a->Cx0 * 2;
+    uint64_t dims[5] = {(uint64_t)a->Cx0, WI, 1, HI, (uint64_t)a->NB};
+    uint64_t str[4] = {c0b, c0b * WI, c0b * WI, c0b * WI * HI};
+    if ((rc = make_tmap_bf16(&p.map_x0, a->ax0, 5, dims, str, box, "conv extra source 0"))) return rc;
+    if (a->Cx1 > 0) {
+      const uint64_t c1b = (uint64_t)a->Cx1 * 2;
+      uint64_t dims1[5] = {(uint64_t)a->Cx1, WI, 1, HI, (uint64_t)a->NB};
+      uint64_t str1[4] = {c1b, c1b * WI, c1b * WI, c1b * WI * HI};
+      if ((rc = make_tmap_bf16(&p.map_x1, a->ax1, 5, dims1, str1, box, "conv extra source 1"))) return rc;
+    }
+  }
+  p.nkb_total = p.ntaps * p.cblocks + p.cblocks_x;
 
   // ---- N tiling
   int block_n = a->block_n;
@@ -1274,7 +1306,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
   const long long ldo_eff = a->ldo ? a->ldo : a->Cout;
   const int want_split = a->nsplit > 1;
-  const int nkb_all = p.ntaps * p.cblocks;
+  const int nkb_all = p.nkb_total;
   const int smem_budget = (a->smem_budget > 0 && a->smem_budget < 227 * 1024) ? a->smem_budget : 227 * 1024;
   int fixed_bytes = 0;
   int stages = 0;
@@ -1361,7 +1393,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.epi_bytes = fixed_bytes - 1024 - GEMM_BAR_BYTES;
   if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
   if (stages < 2) { set_error("sdb_gemm_tc: shared-memory budget too small"); return SDB_ERR_ARG; }
-  const int nkb_total = p.ntaps * p.cblocks;
+  const int nkb_total = p.nkb_total;
   int nsplit = a->nsplit > 0 ? a->nsplit : 1;
   if (nsplit > nkb_total) nsplit = nkb_total;
   p.per_split = (nkb_total + nsplit - 1) / nsplit;

@@ -28,6 +28,8 @@ CTX_PAD = 80  # 77 CLIP tokens padded to a multiple of 8 (TMA stride alignment)
 FOLD_GEGLU = True
 # ... and conv_output composed with it (see pack_unet_attn): one dual-source GEMM per attention block
 FOLD_FF_OUT = os.environ.get("SDB_NO_FOLD_FF_OUT") != "1"
+# channel-changing resblocks: the 1x1 skip convolution rides in conv_merged's GEMM as extra k-blocks
+FUSE_SKIP_CONV = os.environ.get("SDB_NO_FUSE_SKIP") != "1"
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 # GroupNorm statistics accumulated by the epilogue of the GEMM that produces the tensor (sdb_gemm_args.gn_part)
@@ -87,8 +89,14 @@ def pack_resblock(m, dev, time=True):
     pk.gn2_w, pk.gn2_b = pack_norm(gn2, dev)
     pk.conv2_w, pk.conv2_b = pack_conv3x3(conv2, dev)
     pk.cin, pk.cout = conv1.in_channels, conv1.out_channels
+    pk.conv2x_w = None
     if isinstance(m.residual_layer, torch.nn.Conv2d):
         pk.skip_w, pk.skip_b = pack_conv1x1(m.residual_layer, dev)
+        # the 1x1 skip convolution as extra k-blocks of conv_merged: its weights behind the 9 * Cout columns of the
+        # 3x3 filter, the two biases added - one GEMM, no fp32 round trip of the skip branch (FUSE_SKIP_CONV)
+        if FUSE_SKIP_CONV and pk.cin % 64 == 0 and pk.cout % 64 == 0:
+            pk.conv2x_w = torch.cat([pk.conv2_w, pk.skip_w], dim=1).contiguous()
+            pk.conv2x_b = (pk.conv2_b + pk.skip_b).contiguous()
     else:
         pk.skip_w = pk.skip_b = None
     if time:
@@ -247,6 +255,12 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
     if gs is not None:
         hid, _, hid_gp = hid
     a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True, part0=hid_gp)
+    if pk.conv2x_w is not None and c0 % 64 == 0 and c1 % 64 == 0:
+        out = ops.conv3x3(a2, pk.conv2x_w, pk.cout, bias=pk.conv2x_b, out_fp32=True, out2=True if want_b16 else None,
+                          gn_samples=gs, ax0=x.bf16(), ax1=x1.bf16() if x1 is not None else None)
+        if isinstance(out, tuple):
+            return Stream(*out)
+        return Stream(out)
     if pk.skip_w is None:
         res = x.f.view(-1, c0)
     else:

@@ -132,7 +132,7 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
          lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0,
-         gn_samples=None):
+         gn_samples=None, ax0=None, ax1=None):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h.
 
     gn_samples=N: the output is a GroupNorm input of N samples - the epilogue also writes per-slab, per-channel
@@ -184,6 +184,13 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.bias_per_row = 1 if bias_per_row else 0
     args.act = act
     nkb = ntaps * ((c0 + 63) // 64 + (c1 + 63) // 64)
+    cx0 = cx1 = 0
+    if ax0 is not None:        # extra 1x1 source (resblock skip conv) accumulated behind the nine taps
+        cx0 = ax0.shape[-1]
+        cx1 = ax1.shape[-1] if ax1 is not None else 0
+        args.ax0, args.ax1 = _p(_chk(ax0, torch.bfloat16, "ax0")), _p(ax1)
+        args.Cx0, args.Cx1 = cx0, cx1
+        nkb += (cx0 + cx1) // 64
     if block_n == 0 or nsplit == 0:
         ob = (4 if out_fp32 else 2) + (2 if out2 is not None else 0)
         rb = 0 if residual is None else residual.element_size()
@@ -211,8 +218,10 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
             part = torch.empty((gn_samples, k_slabs, cout, 2), device=a0.device, dtype=torch.float32)
             args.gn_part = _p(part)
             args.gn_hw = hw
-    ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear", 2.0 * rows * cout * ntaps * (c0 + c1),
-               2.0 * (rows * (c0 + c1) + cout * ntaps * (c0 + c1)) + out.numel() * out.element_size()
+    ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear",
+               2.0 * rows * cout * (ntaps * (c0 + c1) + cx0 + cx1),
+               2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * (ntaps * (c0 + c1) + cx0 + cx1))
+               + out.numel() * out.element_size()
                + (rows * cout * residual.element_size() if residual is not None else 0)
                + (rows * cout * 2 if out2 is not None else 0),
                shape=f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps}")

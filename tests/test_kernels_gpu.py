@@ -264,6 +264,33 @@ def test_conv3x3_gn_partials(NB, H, C0, C1, Cout):
     report(f"groupnorm concat from partials {Cout}+{Cout}@{H}", y, refn, 6e-3)
 
 
+@pytest.mark.parametrize("N,H,C,Cx0,Cx1,Cout,nsplit", [(2, 64, 320, 640, 320, 320, 1), (2, 32, 640, 320, 0, 640, 1),
+                                                       (2, 16, 1280, 1280, 640, 1280, 1), (2, 8, 1280, 1280, 1280, 1280, 3),
+                                                       (3, 16, 128, 64, 0, 128, 1)])
+def test_conv3x3_extra_1x1_source(N, H, C, Cx0, Cx1, Cout, nsplit):
+    """conv3x3(a) + conv1x1(x0 ++ x1) in ONE GEMM (the resblock's skip convolution as extra k-blocks)."""
+    ops = _ops()
+    setup_exact_fp32()
+    a = rnd(N, H, H, C).bfloat16()
+    x0 = rnd(N, H, H, Cx0, seed=6).bfloat16()
+    x1 = rnd(N, H, H, Cx1, seed=7).bfloat16() if Cx1 else None
+    w3 = rnd(Cout, C, 3, 3, scale=(9 * C) ** -0.5, seed=1).bfloat16()
+    w1 = rnd(Cout, Cx0 + Cx1, scale=(Cx0 + Cx1) ** -0.5, seed=8).bfloat16()
+    b = rnd(Cout, seed=2)
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = (F.conv2d(a.float().permute(0, 3, 1, 2), w3.float(), b, padding=1) +
+           F.conv2d(xin.permute(0, 3, 1, 2), w1.float()[:, :, None, None])).permute(0, 2, 3, 1).reshape(-1, Cout)
+    wcat = torch.cat([pack3x3(w3), w1], dim=1).contiguous()
+    out = ops.gemm(a, wcat, Cout, kind=ops.GEMM_CONV3X3_S1, bias=b, conv_dims=(N, H, H), c0=C, out_fp32=True,
+                   nsplit=nsplit, ax0=x0, ax1=x1)
+    report(f"conv3x3 + 1x1 source {C}+{Cx0 + Cx1}->{Cout}@{H} nsplit={nsplit}", out, ref, 3e-3)
+    out, out2, part = ops.gemm(a, wcat, Cout, kind=ops.GEMM_CONV3X3_S1, bias=b, conv_dims=(N, H, H), c0=C,
+                               out_fp32=True, out2=True, nsplit=1, ax0=x0, ax1=x1, gn_samples=N)
+    report(f"conv3x3 + 1x1 source, gn partials {C}+{Cx0 + Cx1}->{Cout}@{H}", out, ref, 3e-3)
+    if part is not None:
+        _check_partials(part, out, N, "conv3x3 + 1x1 source")
+
+
 # ------------------------------------------------------------------------------------ conv
 def pack3x3(w):
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
