@@ -123,6 +123,21 @@ __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __re
       }
     }
     const long long obase = (((long long)n * H + ho) * W + wo) * Cout + g * 8;
+    if ((Cout & 7) == 0) {
+      // eight channels per thread, vector stores: consecutive threads write consecutive 32 (16) bytes - the scalar
+      // form below took 258 us for the UNet stem (16 x 64 x 64 x 4 -> 320), 13 x its memory time
+      const uint4 h = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                 pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      if (out_fp32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        if (out2 != nullptr) *reinterpret_cast<uint4*>(out2 + obase) = h;
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase) = h;
+      }
+      continue;
+    }
     for (int j = 0; j < 8; ++j) {
       if (g * 8 + j < Cout) {
         if (out_fp32) {
@@ -131,6 +146,93 @@ __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __re
         } else {
           reinterpret_cast<__nv_bfloat16*>(out)[obase + j] = __float2bfloat16_rn(acc[j]);
         }
+      }
+    }
+  }
+}
+
+// Same convolution, 4 adjacent output pixels x 8 output channels per thread (W % 4 == 0, Cout % 8 == 0): the
+// shared-memory weight reads bound the one-pixel form (two LDS.128 with a 2-way bank conflict per 8 FMAs:
+// 258 us for the UNet stem, 13 x its memory time); here every weight vector feeds 32 FMAs.
+template <int KS>
+__global__ void __launch_bounds__(256) conv_direct4_kernel(const void* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, void* __restrict__ out,
+                                                           __nv_bfloat16* __restrict__ out2, int NB, int H, int W,
+                                                           int Cin, int Cout, int out_fp32, int in_fp32) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float s_w[];  // [KS*KS*Cin][Cout]
+  const int K = KS * KS * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;
+    s_w[i] = w[(long long)co * K + k];
+  }
+  __syncthreads();
+  const int G = Cout >> 3;
+  const int W4 = W >> 2;
+  const long long total = (long long)NB * H * W4 * G;
+  constexpr int PAD = (KS - 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    long long r = i / G;
+    const int wq = (int)(r % W4); r /= W4;
+    const int ho = (int)(r % H);
+    const int n = (int)(r / H);
+    const int wo0 = wq * 4;
+    float acc[4][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float b = (bias != nullptr) ? bias[g * 8 + j] : 0.f;
+#pragma unroll
+      for (int px = 0; px < 4; ++px) acc[px][j] = b;
+    }
+    for (int ky = 0; ky < KS; ++ky) {
+      const int hi = ho + ky - PAD;
+      if (hi < 0 || hi >= H) continue;
+      const long long rowoff = ((long long)n * H + hi) * W;
+      for (int ci = 0; ci < Cin; ++ci) {
+        // the KS + 3 input values of this row / channel that the 4 pixels touch
+        float a[KS + 3];
+#pragma unroll
+        for (int t = 0; t < KS + 3; ++t) {
+          const int wi = wo0 + t - PAD;
+          float v = 0.f;
+          if (wi >= 0 && wi < W) {
+            const long long off = (rowoff + wi) * Cin + ci;
+            v = in_fp32 ? reinterpret_cast<const float*>(x)[off]
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[off]);
+          }
+          a[t] = v;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const float* wk = s_w + (long long)((ky * KS + kx) * Cin + ci) * Cout + g * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wk);
+          const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float av = a[px + kx];
+            acc[px][0] = fmaf(av, w0.x, acc[px][0]); acc[px][1] = fmaf(av, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(av, w0.z, acc[px][2]); acc[px][3] = fmaf(av, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(av, w1.x, acc[px][4]); acc[px][5] = fmaf(av, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(av, w1.z, acc[px][6]); acc[px][7] = fmaf(av, w1.w, acc[px][7]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const long long obase = (((long long)n * H + ho) * W + wo0 + px) * Cout + g * 8;
+      const uint4 h = make_uint4(pack_bf16x2(acc[px][0], acc[px][1]), pack_bf16x2(acc[px][2], acc[px][3]),
+                                 pack_bf16x2(acc[px][4], acc[px][5]), pack_bf16x2(acc[px][6], acc[px][7]));
+      if (out_fp32) {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
+        o[0] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
+        o[1] = make_float4(acc[px][4], acc[px][5], acc[px][6], acc[px][7]);
+        if (out2 != nullptr) *reinterpret_cast<uint4*>(out2 + obase) = h;
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + obase) = h;
       }
     }
   }
@@ -385,10 +487,25 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
   if (!configured) {
     cudaFuncSetAttribute(conv_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(conv_direct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(conv_direct4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(conv_direct4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     configured = true;
   }
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
+  if ((W & 3) == 0 && (Cout & 7) == 0) {
+    const long long total4 = (long long)NB * H * (W / 4) * (Cout / 8);
+    long long blocks4 = (total4 + 255) / 256;
+    if (blocks4 > 148 * 4) blocks4 = 148 * 4;
+    const size_t smem4 = (size_t)ksize * ksize * Cin * Cout * sizeof(float);
+    if (ksize == 1)
+      (void)launch_k(conv_direct4_kernel<1>, dim3((unsigned)blocks4), dim3(256), smem4, SDB_STREAM, 1,
+          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+    else
+      (void)launch_k(conv_direct4_kernel<3>, dim3((unsigned)blocks4), dim3(256), smem4, SDB_STREAM, 1,
+          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+    return check_launch("conv_direct4_kernel");
+  }
   if (ksize == 1)
     (void)launch_k(conv_direct_kernel<1>, dim3((unsigned)blocks), dim3(256), smem, SDB_STREAM, 1,
         x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);

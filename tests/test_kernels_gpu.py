@@ -390,6 +390,20 @@ def test_conv_direct(Cin, Cout, k):
     report(f"conv_direct fp32 in {Cin}->{Cout} k{k}", out, ref, 1e-4)
 
 
+def test_conv_direct_odd_width_takes_the_one_pixel_kernel():
+    ops = _ops()
+    setup_exact_fp32()
+    N, H, W, Cin, Cout, k = 2, 18, 30, 4, 320, 3
+    x = rnd(N, H, W, Cin)
+    w = rnd(Cout, Cin, k, k, scale=(k * k * Cin) ** -0.5, seed=1)
+    b = rnd(Cout, seed=2)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous()
+    out, shadow = ops.conv_direct(x, wp, b, Cout, k, out_fp32=True, out2=True)
+    report("conv_direct W=30", out, ref, 1e-4)
+    assert torch.equal(shadow, out.bfloat16())
+
+
 # ------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("N,HW,C0,C1,eps,silu", [
     (2, 4096, 320, 0, 1e-5, True), (2, 64, 1280, 1280, 1e-5, True), (2, 1024, 640, 320, 1e-5, True),
