@@ -19,3 +19,27 @@ for name,fn in cases.items():
     e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     print(f"{name:50s} {1e3*e0.elapsed_time(e1)/20:8.1f} us")
+
+# GroupNorm statistics from epilogue partials: the reduce kernel alone, then reduce + apply, vs stats + apply
+import ctypes
+from pytorch_stable_diffusion_b200 import _ext
+lib = _ext.lib()
+for (n, hw, c) in ((16, 4096, 320), (16, 1024, 640)):
+    xg = torch.randn(n, hw, c, device=dev)
+    gam = torch.randn(c, device=dev); bet = torch.randn(c, device=dev)
+    part = torch.randn(n, hw // 32, c, 2, device=dev)
+    stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, 32) // 8,), device=dev, dtype=torch.float64)
+    st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cases2 = {f"gn reduce_partials only {n}x{hw}x{c}": lambda: lib.sdb_groupnorm_reduce_partials(
+                  ctypes.c_void_p(part.data_ptr()), None, ctypes.c_void_p(stats.data_ptr()), n, hw // 32, 0, c, 0, 32, st()),
+              f"gn reduce + apply {n}x{hw}x{c}": lambda: ops.groupnorm(xg, gam, bet, silu=True, fused=False, part0=part),
+              f"gn stats + apply {n}x{hw}x{c}": lambda: ops.groupnorm(xg, gam, bet, silu=True, fused=False)}
+    for name, fn in cases2.items():
+        fn(); torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(20): fn()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        print(f"{name:50s} {1e3*e0.elapsed_time(e1)/20:8.1f} us")
