@@ -124,6 +124,12 @@ typedef struct sdb_attn_args {
                              the kernel is bound by the 16 ex2 / clk / SM. 0 = default (on), 1 = off, 2 = on */
   int q_prescaled;        /* q already carries log2(e) * scale (folded into the query projection): the scores are
                              in log2 units and `scale` is ignored                                           */
+  int qk_cols;            /* columns stored per head in q and k (head h at column h * qk_cols; all of them enter the
+                             reduction); 0 = d                                                                */
+  int qk_fold;            /* with sum_row + q_prescaled, qk_cols > d: column d of k is all ones, column d of q is
+                             zero - the kernel writes -round(row maximum of the first key block) there (in its
+                             shared-memory copy), so later score blocks arrive relative to the row's reference and
+                             the softmax needs no subtraction                                                  */
 } sdb_attn_args;
 
 /* Flash-style softmax(Q K^T * scale) V with S in TMEM; replaces sd/attention.py:55-76 (self),

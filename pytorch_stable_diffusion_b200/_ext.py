@@ -29,7 +29,7 @@ class AttnArgs(ctypes.Structure):
         ("q", c_void_p), ("k", c_void_p), ("vt", c_void_p), ("out", c_void_p), ("NB", c_int),
         ("heads", c_int), ("d", c_int), ("S", c_int), ("Skv", c_int), ("Skv_pad", c_int), ("vt_ld", c_int),
         ("ldq", c_ll), ("ldk", c_ll), ("ldo", c_ll), ("causal", c_int), ("scale", c_float), ("variant", c_int), ("sum_row", c_int), ("p_f16", c_int),
-        ("exp_poly", c_int), ("q_prescaled", c_int),
+        ("exp_poly", c_int), ("q_prescaled", c_int), ("qk_cols", c_int), ("qk_fold", c_int),
     ]
 
 

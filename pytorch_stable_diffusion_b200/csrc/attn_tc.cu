@@ -46,6 +46,8 @@ struct AttnParams {
   int prescaled; // scale_log2 == 1: scores arrive in log2 units
   int tiles_per_cta;  // one-tile kernel, single key block, no mask: query tiles one CTA walks (K / V^T, TMEM and
                       // barriers set up once); 1 = one tile per CTA
+  int qk_fold;   // two-tile kernel: the row offset of the softmax rides in Q.K^T (column d of K is all ones, column d
+                 // of the Q tile in shared memory gets -round(row maximum of key block 0)), see the softmax loop
   int stagger;   // two-tile kernel, separate P: clocks tile 1 starts after tile 0 (0 = fixed issue order, lock step)
 };
 
@@ -487,6 +489,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
   uint64_t* o_done = p_full + 2;                 // [2]
   uint64_t* s_free = o_done + 2;                 // [2] softmax has S_t in registers (separate-P layout)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* q_ready = s_free + 3;                // [2] qk_fold: the rows' offsets are in the Q tile
   // TMEM columns. Narrow heads (dv_pad <= 64) keep P apart from S, so Q.K^T of the next key block can
   // overwrite S_t while the softmax of the current one is still computing and P_t waits for its P.V:
   //   separate:  S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
@@ -513,6 +516,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_init(&p_full[i], 128);
       mbar_init(&o_done[i], 1);
       mbar_init(&s_free[i], 128);
+      mbar_init(&q_ready[i], 128);
     }
     fence_mbar_init();
   }
@@ -664,9 +668,11 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
         if (more) {
           mbar_wait(&kv_full[st_next], ph_next, 25);
           mbar_wait(&s_free[0], par, 30);
+          if (p.qk_fold && j == 0) mbar_wait(&q_ready[0], 0, 34);     // tile 0's row offsets are in its Q tile
           tc_fence_after();
           issue_qk(0, st_next);
           mbar_wait(&s_free[1], par, 31);
+          if (p.qk_fold && j == 0) mbar_wait(&q_ready[1], 0, 35);
           tc_fence_after();
           issue_qk(1, st_next);
         }
@@ -710,6 +716,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     float l_run = 0.f;
     const float sl2 = p.scale_log2;
     const bool tr0 = (t == 0 && quad == 2 && lane == 0);
+    const bool fold = p.qk_fold != 0;
     for (int j = 0; j < nkv; ++j) {
       if (tr0) ATT_STAMP(j, 0);
       mbar_wait(&s_full[t], (uint32_t)(j & 1), 27);
@@ -765,10 +772,37 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
         l_run *= factor;
       }
       if (need) m_ref = m_new;
+      if (fold && j == 0) {
+        // qk_fold: from the second key block on, the scores leave the tensor core already relative to this row's
+        // reference. Column d of K is all ones; column d of this row of the Q tile (shared memory, 128B-swizzled:
+        // 16-byte chunk (d/8) ^ (row & 7)) gets -m, m = the row maximum of block 0 rounded to an integer (exact in
+        // bf16 up to 256; scores are in log2 units, so 2^-m is an exact factor and the ones-row denominator sees the
+        // same P). The issuer waits for q_ready before the second block's Q.K^T.
+        float mi = (m_ref == -INFINITY) ? 0.f : rintf(m_ref);
+        mi = fminf(fmaxf(mi, -256.f), 256.f);
+        m_ref = mi;
+        const uint32_t qrow_addr = smem_u32(q_smem) + (uint32_t)(t * q_bytes + ((p.d >> 6) * ATT_CHUNK_BYTES)) +
+                                   (uint32_t)(row * 128) + (uint32_t)(((((p.d & 63) >> 3) ^ (row & 7)) << 4) + (p.d & 7) * 2);
+        const __nv_bfloat16 hv = __float2bfloat16_rn(-mi);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(qrow_addr), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+        fence_proxy_async();
+        mbar_arrive(&q_ready[t]);
+      }
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
       if (tr0) ATT_STAMP(j, 3);
       uint32_t pk[64];
-      if (p.p_f16) {
+      if (fold && j > 0 && __all_sync(0xffffffffu, mb == 0.f)) {
+        // scores already relative to the row's reference (see above): no subtraction, a quarter on the FMA pipe
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = ex2_approx(__uint_as_float(sv[i]));
+          const float p1 = ex2_approx(__uint_as_float(sv[i + 1]));
+          const float p2 = ex2_approx(__uint_as_float(sv[i + 2]));
+          const float p3 = exp2_poly(__uint_as_float(sv[i + 3]));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+      } else if (p.p_f16) {
         // denominator comes from the V^T ones row (sum_col >= 0 is required with p_f16)
 #pragma unroll
         for (int i = 0; i < 128; i += 2)
@@ -843,6 +877,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      if (fold && j == 0) m_ref = 0.f;       // from here on the scores arrive relative to the baked reference
       if (tr0) ATT_STAMP(j, 5);
     }
     // ---- epilogue: O / l -> bf16
@@ -914,15 +949,19 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   AttnParams p;
   memset(&p, 0, sizeof(p));
   int rc;
+  // columns stored per head in q and k (>= d; the extra ones are part of the reduction: zeros, or the ones / offset
+  // column of qk_fold)
+  const int dqk = a->qk_cols > 0 ? a->qk_cols : a->d;
+  if (dqk < a->d || dqk % 8 != 0 || dqk > 160) { set_error("sdb_attention: qk_cols %d invalid", dqk); return SDB_ERR_ARG; }
   {
-    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->S, (uint64_t)a->NB};
-    uint64_t str[3] = {(uint64_t)a->d * 2, (uint64_t)ldq * 2, (uint64_t)ldq * 2 * a->S};
+    uint64_t dims[4] = {(uint64_t)dqk, (uint64_t)a->heads, (uint64_t)a->S, (uint64_t)a->NB};
+    uint64_t str[3] = {(uint64_t)dqk * 2, (uint64_t)ldq * 2, (uint64_t)ldq * 2 * a->S};
     uint32_t box[4] = {64, 1, 128, 1};
     if ((rc = make_tmap_bf16(&p.map_q, a->q, 4, dims, str, box, "attention Q"))) return rc;
   }
   {
-    uint64_t dims[4] = {(uint64_t)a->d, (uint64_t)a->heads, (uint64_t)a->Skv_pad, (uint64_t)a->NB};
-    uint64_t str[3] = {(uint64_t)a->d * 2, (uint64_t)ldk * 2, (uint64_t)ldk * 2 * a->Skv_pad};
+    uint64_t dims[4] = {(uint64_t)dqk, (uint64_t)a->heads, (uint64_t)a->Skv_pad, (uint64_t)a->NB};
+    uint64_t str[3] = {(uint64_t)dqk * 2, (uint64_t)ldk * 2, (uint64_t)ldk * 2 * a->Skv_pad};
     uint32_t box[4] = {64, 1, 128, 1};
     if ((rc = make_tmap_bf16(&p.map_k, a->k, 4, dims, str, box, "attention K"))) return rc;
   }
@@ -955,8 +994,8 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     // the offset to pay (S = 4096, d = 40: 843 -> 783 us; 1 100 / 1 500 / 1 900 clocks: 800 / 791 / 797 us)
     p.stagger = (stagger < 0 && (a->Skv + ATT_BKV - 1) / ATT_BKV < 8) ? 0 : stagger;
   }
-  p.dchunks = (a->d + 63) / 64;
-  p.dk_steps = (a->d + 15) / 16;
+  p.dchunks = (dqk + 63) / 64;
+  p.dk_steps = (dqk + 15) / 16;
   p.dv_pad = dv_pad;
   p.vt_rows = vt_rows;
   p.sum_col = a->sum_row ? a->d : -1;
@@ -988,6 +1027,15 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
   p.o_col = single_block ? 128 : 256;
   const bool two_tile = !a->causal && a->d <= 128 && (a->S > ATT_BQ || a->sum_row) && smem2 <= 227 * 1024 &&
                         (a->variant != 1 || a->sum_row) && !(single_block && a->variant != 2);
+  if (a->qk_fold) {
+    if (!two_tile || !a->sum_row || !a->q_prescaled || !p.exp_poly || a->p_f16 || dv_pad > 64 || dqk < a->d + 1 ||
+        (a->d >> 6) != ((dqk - 1) >> 6)) {
+      set_error("sdb_attention: qk_fold needs the two-tile kernel with sum_row, q_prescaled, the polynomial quarter, "
+                "V^T rows per head <= 64 and qk_cols > d in the same 64-column chunk");
+      return SDB_ERR_UNSUPPORTED;
+    }
+    p.qk_fold = 1;
+  }
   if (two_tile) {
     dim3 grid((unsigned)((a->S + 2 * ATT_BQ - 1) / (2 * ATT_BQ)), (unsigned)a->heads, (unsigned)a->NB);
     (void)launch_k(attn2_tc_kernel, grid, dim3(ATT2_THREADS), (size_t)smem2, (cudaStream_t)stream, 1, p);

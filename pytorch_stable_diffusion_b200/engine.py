@@ -32,6 +32,8 @@ FOLD_FF_OUT = os.environ.get("SDB_NO_FOLD_FF_OUT") != "1"
 FUSE_SKIP_CONV = os.environ.get("SDB_NO_FUSE_SKIP") != "1"
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
+# ... and the softmax row offset folded into Q.K^T through a ones column of k (heads padded to R columns)
+QK_OFFSET_FOLD = os.environ.get("SDB_NO_QK_FOLD") != "1"
 # GroupNorm statistics accumulated by the epilogue of the GEMM that produces the tensor (sdb_gemm_args.gn_part)
 GN_EPILOGUE_STATS = os.environ.get("SDB_NO_GN_EPI") != "1"
 
@@ -124,6 +126,7 @@ def pack_unet_attn(m, dev):
     # with bias 1), the rest zero. The padding is free: the tensor core pays for N = R either way.
     d = c // pk.heads
     pk.vt_rows = 0
+    pk.qk_cols = 0
     if SUM_ROW_ATTENTION and d <= 112:
         r = (d + 1 + 15) // 16 * 16
         wv = torch.zeros((pk.heads, r, c), dtype=torch.float32)
@@ -140,10 +143,25 @@ def pack_unet_attn(m, dev):
         sl2 = math.log2(math.e) / math.sqrt(d)
         wq = w[:2 * c].detach().float().cpu().clone()
         wq[:c] *= sl2
-        pk.wqk = _bf16(wq, dev)
+        bq = None
         if b is not None:
             bq = b[:2 * c].detach().float().cpu().clone()
             bq[:c] *= sl2
+        pk.qk_cols = 0
+        if QK_OFFSET_FOLD and r <= 64 and d % 8 == 0:
+            # ... and the heads of q and k are padded to the same R columns: column d of k is all ones (zero weight
+            # row, bias 1), column d of q is zero - the attention kernel writes each row's -round(max) there and the
+            # scores of every later key block leave the tensor core relative to the row's reference (qk_fold)
+            wp = torch.zeros((2, pk.heads, r, c), dtype=torch.float32)
+            wp[:, :, :d] = wq.view(2, pk.heads, d, c)
+            bp = torch.zeros((2, pk.heads, r), dtype=torch.float32)
+            if bq is not None:
+                bp[:, :, :d] = bq.view(2, pk.heads, d)
+            bp[1, :, d] = 1.0
+            wq, bq = wp.view(2 * pk.heads * r, c), bp.view(-1)
+            pk.qk_cols = r
+        pk.wqk = _bf16(wq, dev)
+        if bq is not None:
             pk.bqk = _f32(bq, dev)
     pk.wo1, pk.bo1 = pack_linear(m.attention_1.out_proj, dev)
     pk.ln2 = pack_norm(m.layernorm_2, dev)
@@ -313,8 +331,11 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     qk = ops.linear(l1, pk.wqk, bias=pk.bqk)
     vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
     o = torch.empty((m, c), device=dev, dtype=torch.bfloat16)
-    ops.attention(qk, qk[:, c:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
-                  ldq=2 * c, ldk=2 * c, ldo=c, sum_row=pk.vt_rows > 0, q_prescaled=pk.vt_rows > 0)
+    cq = pk.heads * pk.qk_cols if pk.qk_cols else c          # columns of the q (and k) part of qk
+    fold = pk.qk_cols > 0 and s % 8 == 0 and s > 128
+    ops.attention(qk, qk[:, cq:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
+                  ldq=2 * cq, ldk=2 * cq, ldo=c, sum_row=pk.vt_rows > 0, q_prescaled=pk.vt_rows > 0,
+                  qk_cols=pk.qk_cols, qk_fold=fold)
     t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
     # cross-attention over the CLIP tokens
     l2 = ops.layernorm(t1, *pk.ln2)

@@ -253,7 +253,7 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
 
 
 def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0,
-              variant=0, sum_row=False, p_f16=False, exp_poly=0, q_prescaled=False):
+              variant=0, sum_row=False, p_f16=False, exp_poly=0, q_prescaled=False, qk_cols=0, qk_fold=False):
     lib = _ext.lib()
     a = AttnArgs()
     a.q, a.k, a.vt, a.out = _p(_chk(q, torch.bfloat16, "q")), _p(_chk(k, torch.bfloat16, "k")), \
@@ -267,6 +267,8 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
     a.p_f16 = 1 if p_f16 else 0
     a.exp_poly = exp_poly
     a.q_prescaled = 1 if q_prescaled else 0
+    a.qk_cols = qk_cols
+    a.qk_fold = 1 if qk_fold else 0
     ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
                2.0 * NB * heads * d * (2 * S + 2 * Skv))
     _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")

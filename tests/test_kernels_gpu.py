@@ -266,7 +266,9 @@ def test_conv3x3_gn_partials(NB, H, C0, C1, Cout):
 
 @pytest.mark.parametrize("N,H,C,Cx0,Cx1,Cout,nsplit", [(2, 64, 320, 640, 320, 320, 1), (2, 32, 640, 320, 0, 640, 1),
                                                        (2, 16, 1280, 1280, 640, 1280, 1), (2, 8, 1280, 1280, 1280, 1280, 3),
-                                                       (3, 16, 128, 64, 0, 128, 1)])
+                                                       (3, 16, 128, 64, 0, 128, 1), (2, 24, 128, 128, 64, 128, 1),
+                                                       (2, 12, 128, 64, 64, 128, 1), (2, 48, 64, 128, 0, 64, 1),
+                                                       (2, 96, 64, 64, 0, 64, 1), (2, 24, 1280, 1280, 640, 1280, 1)])
 def test_conv3x3_extra_1x1_source(N, H, C, Cx0, Cx1, Cout, nsplit):
     """conv3x3(a) + conv1x1(x0 ++ x1) in ONE GEMM (the resblock's skip convolution as extra k-blocks)."""
     ops = _ops()
@@ -607,6 +609,47 @@ def test_attention_growing_maximum():
     vf = v.float().reshape(N, S, heads, d).transpose(1, 2)
     ref = ref_attention(qf, kf, vf, False).transpose(1, 2).reshape(N * S, C)
     report("attention, growing maximum", out, ref, 1e-2)
+
+
+@pytest.mark.parametrize("S,amp,ramp", [(4096, 1.0, False), (1024, 3.0, False), (1024, 1.0, True), (1000, 2.0, False),
+                                        (256, 1.0, False)])
+def test_attention_qk_fold(S, amp, ramp):
+    """Row offset of the softmax folded into Q.K^T (ones column in K, offset column written into the Q tile by the
+    kernel): padded 48-column heads, pre-scaled queries, ones-row denominator."""
+    ops = _ops()
+    setup_exact_fp32()
+    N, heads, d, R = 2, 8, 40, 48
+    C = heads * d
+    sl2 = math.log2(math.e) / math.sqrt(d)
+    qf = rnd(N * S, heads, d) * amp
+    kf = rnd(N * S, heads, d, seed=1) * amp
+    if ramp:
+        kf = kf * torch.linspace(0.2, 6.0, S, device=DEV).repeat(N).view(N * S, 1, 1)
+    vf = rnd(N * S, heads, d, seed=2)
+    q = torch.zeros(N * S, heads, R, device=DEV, dtype=torch.bfloat16)
+    k = torch.zeros(N * S, heads, R, device=DEV, dtype=torch.bfloat16)
+    q[:, :, :d] = (qf * sl2).bfloat16()
+    k[:, :, :d] = kf.bfloat16()
+    k[:, :, d] = 1.0
+    vt = torch.zeros(heads, R, N, S, device=DEV, dtype=torch.bfloat16)
+    vt[:, :d] = vf.bfloat16().view(N, S, heads, d).permute(2, 3, 0, 1)
+    vt[:, d] = 1.0
+    vt = vt.view(heads * R, N, S).contiguous()
+    out = torch.empty(N * S, C, device=DEV, dtype=torch.bfloat16)
+    ops.attention(q.view(N * S, heads * R), k.view(N * S, heads * R), vt, out, NB=N, heads=heads, d=d, S=S, Skv=S,
+                  Skv_pad=S, ldq=heads * R, ldk=heads * R, ldo=C, sum_row=True, q_prescaled=True, qk_cols=R, qk_fold=True)
+    qr = (q[:, :, :d].float() / sl2).view(N, S, heads, d).transpose(1, 2)
+    kr = k[:, :, :d].float().view(N, S, heads, d).transpose(1, 2)
+    vr = vf.bfloat16().float().view(N, S, heads, d).transpose(1, 2)
+    ref = ref_attention(qr, kr, vr, False).transpose(1, 2).reshape(N * S, C)
+    report(f"attention qk_fold S={S} amp={amp} ramp={ramp}", out, ref, 1e-2)
+    # same inputs without the fold: the two must agree to bf16 rounding of P
+    out2 = torch.empty_like(out)
+    k2 = k.clone()
+    k2[:, :, d] = 0.0
+    ops.attention(q.view(N * S, heads * R), k2.view(N * S, heads * R), vt, out2, NB=N, heads=heads, d=d, S=S, Skv=S,
+                  Skv_pad=S, ldq=heads * R, ldk=heads * R, ldo=C, sum_row=True, q_prescaled=True, qk_cols=R)
+    report(f"attention qk_fold vs plain S={S}", out, out2, 8e-3)
 
 
 # ------------------------------------------------------------------------------------ elementwise

@@ -4,14 +4,14 @@
 set -u
 TAG=${1:-r01}
 K='regex:^(gemm_|attn2?_tc|gn_|layernorm|softmax_rows|fill_zero|nchw_f32|nhwc_to|upsample2x|conv_direct|small_linear|cfg_ddpm|vae_|f32_to_bf16|axpby|image_to|uint8_to|clip_embed)'
-python tools/kernel_bench.py --graph --attn-mode 1 --json gpurun_out/${TAG}_kernel_bench.json > gpurun_out/${TAG}_kernel_bench.log 2>&1
+python tools/kernel_bench.py --graph --attn-mode 3 --json gpurun_out/${TAG}_kernel_bench.json > gpurun_out/${TAG}_kernel_bench.log 2>&1
 python bench.py --profile-only > gpurun_out/${TAG}_po.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --profile-only > gpurun_out/${TAG}_ncu_launches.log 2>&1
 for c in conv3x3_res_320_320_64 linear_proj_65536x320x320 attn_self_S4096; do
-  python tools/kernel_bench.py --attn-mode 1 --only $c --iters 1 --warmup 1 > gpurun_out/${TAG}_plain_$c.log 2>&1 &&
+  python tools/kernel_bench.py --attn-mode 3 --only $c --iters 1 --warmup 1 > gpurun_out/${TAG}_plain_$c.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k 'regex:^(gemm_tc|attn2?_tc)' -s 1 -c 1 -f \
-      -o gpurun_out/${TAG}_prof_$c python tools/kernel_bench.py --attn-mode 1 --only $c --iters 1 --warmup 1 \
+      -o gpurun_out/${TAG}_prof_$c python tools/kernel_bench.py --attn-mode 3 --only $c --iters 1 --warmup 1 \
       > gpurun_out/${TAG}_ncu_$c.log 2>&1
 done
 # HBM-bound side: GroupNorm apply (+SiLU) and LayerNorm, 2nd matching launch of the named kernel

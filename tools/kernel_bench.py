@@ -60,13 +60,28 @@ def cases(B):
         sr = ATTN_MODE > 0 and d <= 112
         rows = heads * ((d + 16) // 16 * 16) if sr else c
         vt = bf(rows, N * skv_pad)
-        if sr and ATTN_MODE > 1:
+        if sr and ATTN_MODE == 2:
             vt = vt.to(torch.float16)
         o = torch.empty(N * S, c, device=DEV, dtype=torch.bfloat16)
         fl = 4.0 * N * heads * S * Skv * d
+        if ATTN_MODE == 3 and sr and d <= 47 and Skv == S:
+            # what the UNet's 64x64 self-attention runs: 48-column heads, pre-scaled q, ones column in k (qk_fold)
+            R = 48
+            qp = torch.zeros(N * S, heads, R, device=DEV, dtype=torch.bfloat16)
+            kp = torch.zeros(N * S, heads, R, device=DEV, dtype=torch.bfloat16)
+            qp[:, :, :d] = (q.view(N * S, heads, d).float() * (1.4427 / d ** 0.5)).bfloat16()
+            kp[:, :, :d] = k.view(N * S, heads, d)
+            kp[:, :, d] = 1.0
+            vb = vt.to(torch.bfloat16)
+            out.append((f"attn_{name}_S{S}_kv{Skv}_d{d}", count, fl,
+                        lambda: ops.attention(qp.view(N * S, heads * R), kp.view(N * S, heads * R), vb, o, NB=N,
+                                              heads=heads, d=d, S=S, Skv=Skv, Skv_pad=skv_pad, ldq=heads * R,
+                                              ldk=heads * R, ldo=c, sum_row=True, q_prescaled=True, qk_cols=R,
+                                              qk_fold=True)))
+            return
         out.append((f"attn_{name}_S{S}_kv{Skv}_d{d}", count, fl,
                     lambda: ops.attention(q, k, vt, o, NB=N, heads=heads, d=d, S=S, Skv=Skv, Skv_pad=skv_pad,
-                                          ldq=c, ldk=c, ldo=c, sum_row=sr, p_f16=sr and ATTN_MODE > 1)))
+                                          ldq=c, ldk=c, ldo=c, sum_row=sr, p_f16=sr and ATTN_MODE == 2)))
 
     def gnorm(name, Hh, C0, C1, count, fp32=True):
         x0 = torch.randn(N, Hh, Hh, C0, device=DEV)
@@ -137,7 +152,7 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--pair", type=int, default=0, help="0 auto, 1 single-CTA tiles, 2 CTA pairs")
     ap.add_argument("--graph", action="store_true", help="time a CUDA-graph replay of the launches")
-    ap.add_argument("--attn-mode", type=int, default=0, help="0 plain, 1 ones-row denominator, 2 + f16x2 exps")
+    ap.add_argument("--attn-mode", type=int, default=0, help="0 plain, 1 ones-row denominator, 2 + f16x2 exps, 3 ones-row + pre-scaled q + qk_fold")
     args = ap.parse_args()
     global PAIR, ATTN_MODE
     PAIR = args.pair
