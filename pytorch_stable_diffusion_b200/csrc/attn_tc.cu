@@ -734,6 +734,55 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       if (tr0) ATT_STAMP(j, 2);
       const int visible = p.Skv - j * ATT_BKV;          // keys [0, visible) of this block are real
+      if (fold && j > 0 && visible >= 128 && __all_sync(0xffffffffu, m_ref == 0.f)) {
+        // qk_fold, no row-maximum pass: the scores arrive relative to (row maximum of block 0) + 7, i.e. every
+        // probability carries 2^-7 (so does the denominator column of O: it cancels exactly). "This block raised
+        // the row maximum by 2^8 or more" is then "some probability >= 2.0" = bit 14 of a bf16 pattern: OR the packed
+        // words (32 LOP3 instead of 64 FMNMX3) and test that bit in both halves.
+        uint32_t pk[64];
+        uint32_t orv = 0;
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          const float p0 = ex2_approx(__uint_as_float(sv[i]));
+          const float p1 = ex2_approx(__uint_as_float(sv[i + 1]));
+          const float p2 = ex2_approx(__uint_as_float(sv[i + 2]));
+          const float p3 = exp2_poly(__uint_as_float(sv[i + 3]));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          orv |= pk[i >> 1] | pk[(i >> 1) + 1];
+        }
+        if (tr0) ATT_STAMP(j, 4);
+        mbar_wait(&o_done[t], (uint32_t)((j - 1) & 1), 32);     // P_t of the previous block consumed by its P.V
+        tc_fence_after();
+        const bool grow = (orv & 0x40004000u) != 0u;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare: rescale O (denominator column included) and this block's P by an exact power of two and carry
+          // the shift as the row's relative reference - those rows take the subtracting path from here on
+          float pmax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 64; ++i) pmax = fmaxf(pmax, fmaxf(bf16lo(pk[i]), bf16hi(pk[i])));
+          const float e = grow ? floorf(log2f(pmax)) + 7.0f : 0.f;
+          const float factor = grow ? ex2_approx(-e) : 1.0f;
+          for (int c = 0; c < p.dv_pad; c += 16) {
+            uint32_t ov[16];
+            tmem_ld16(o_addr + (uint32_t)c, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * factor);
+            tmem_st16(o_addr + (uint32_t)c, ov);
+          }
+#pragma unroll
+          for (int i = 0; i < 64; ++i) pk[i] = pack_bf16x2(bf16lo(pk[i]) * factor, bf16hi(pk[i]) * factor);
+          if (grow) m_ref = e;
+        }
+        tmem_st32(p_addr + 0, pk + 0);
+        tmem_st32(p_addr + 32, pk + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[t]);
+        if (tr0) ATT_STAMP(j, 5);
+        continue;
+      }
       float mloc = -INFINITY;
       if (visible < 128) {
 #pragma unroll
@@ -778,7 +827,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
         // 16-byte chunk (d/8) ^ (row & 7)) gets -m, m = the row maximum of block 0 rounded to an integer (exact in
         // bf16 up to 256; scores are in log2 units, so 2^-m is an exact factor and the ones-row denominator sees the
         // same P). The issuer waits for q_ready before the second block's Q.K^T.
-        float mi = (m_ref == -INFINITY) ? 0.f : rintf(m_ref);
+        float mi = (m_ref == -INFINITY) ? 0.f : rintf(m_ref) + 7.0f;   // + 7: see the no-max-pass path below
         mi = fminf(fmaxf(mi, -256.f), 256.f);
         m_ref = mi;
         const uint32_t qrow_addr = smem_u32(q_smem) + (uint32_t)(t * q_bytes + ((p.d >> 6) * ATT_CHUNK_BYTES)) +
@@ -791,18 +840,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       const float mb = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
       if (tr0) ATT_STAMP(j, 3);
       uint32_t pk[64];
-      if (fold && j > 0 && __all_sync(0xffffffffu, mb == 0.f)) {
-        // scores already relative to the row's reference (see above): no subtraction, a quarter on the FMA pipe
-#pragma unroll
-        for (int i = 0; i < 128; i += 4) {
-          const float p0 = ex2_approx(__uint_as_float(sv[i]));
-          const float p1 = ex2_approx(__uint_as_float(sv[i + 1]));
-          const float p2 = ex2_approx(__uint_as_float(sv[i + 2]));
-          const float p3 = exp2_poly(__uint_as_float(sv[i + 3]));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-        }
-      } else if (p.p_f16) {
+      if (p.p_f16) {
         // denominator comes from the V^T ones row (sum_col >= 0 is required with p_f16)
 #pragma unroll
         for (int i = 0; i < 128; i += 2)
