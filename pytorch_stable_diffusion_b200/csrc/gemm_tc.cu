@@ -1429,7 +1429,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
                          (!a->residual || (a->res_fp32 && (ldr_eff % 4) == 0 &&
                                            (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0)) &&
                          (reinterpret_cast<uintptr_t>(a->gn_part) & 15u) == 0;
-    if (K <= 0 || !a->out_fp32 || nsplit != 1 || a->Cout % 32 != 0 || block_n % 32 != 0 || !aligned) {
+    if (K <= 0 || (!a->out_fp32 && p.epi_tma) || nsplit != 1 || a->Cout % 32 != 0 || block_n % 32 != 0 || !aligned) {
       set_error("sdb_gemm_tc: gn_part needs an fp32 output, no split-K, Cout %% 32 == 0, 16-byte aligned operands and "
                 "32-row slabs inside one sample (K=%d nsplit=%d block_n=%d)", K, nsplit, block_n);
       return SDB_ERR_UNSUPPORTED;

@@ -30,6 +30,9 @@ FOLD_GEGLU = True
 FOLD_FF_OUT = os.environ.get("SDB_NO_FOLD_FF_OUT") != "1"
 # channel-changing resblocks: the 1x1 skip convolution rides in conv_merged's GEMM as extra k-blocks
 FUSE_SKIP_CONV = os.environ.get("SDB_NO_FUSE_SKIP") != "1"
+# EXPERIMENT: the resblock's hidden tensor stored as bf16 where its GroupNorm statistics come from the fp32 values in
+# conv_feature's epilogue anyway (only the normalised value sees the rounding)
+HID_BF16 = os.environ.get("SDB_HID_BF16") == "1"
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 # ... and the softmax row offset folded into Q.K^T through a ones column of k (heads padded to R columns)
@@ -267,8 +270,8 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
                       part0=x.gp, part1=x1.gp if x1 is not None else None)
     gs = _gn_samples(n, h * w, pk.cout)
     # the hidden tensor stays fp32: it is only ever read by GroupNorm, never as a tensor-core operand
-    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b, out_fp32=True,
-                      gn_samples=gs)
+    hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b,
+                      out_fp32=not (HID_BF16 and gs is not None), gn_samples=gs)
     hid_gp = None
     if gs is not None:
         hid, _, hid_gp = hid

@@ -211,7 +211,8 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.out_f16 = 1 if out_f16 else 0
     args.epi_mode = epi_mode
     part = None
-    if gn_samples is not None and out_fp32 and nsplit == 1 and cout % 32 == 0 and block_n % 32 == 0 and ldo == 0:
+    if gn_samples is not None and (out_fp32 or kind != GEMM_LINEAR) and nsplit == 1 and cout % 32 == 0 \
+            and block_n % 32 == 0 and ldo == 0:
         hw = rows // gn_samples
         k_slabs = lib.sdb_gemm_gn_slabs(kind, args.NB, args.HI, args.WI, args.M, hw if kind == GEMM_LINEAR else 0)
         if k_slabs > 0 and rows % gn_samples == 0:

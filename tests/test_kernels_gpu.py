@@ -268,7 +268,12 @@ def test_conv3x3_gn_partials(NB, H, C0, C1, Cout):
                                                        (2, 16, 1280, 1280, 640, 1280, 1), (2, 8, 1280, 1280, 1280, 1280, 3),
                                                        (3, 16, 128, 64, 0, 128, 1), (2, 24, 128, 128, 64, 128, 1),
                                                        (2, 12, 128, 64, 64, 128, 1), (2, 48, 64, 128, 0, 64, 1),
-                                                       (2, 96, 64, 64, 0, 64, 1), (2, 24, 1280, 1280, 640, 1280, 1)])
+                                                       (2, 96, 64, 64, 0, 64, 1), (2, 24, 1280, 1280, 640, 1280, 1),
+                                                       (2, 12, 1280, 1280, 1280, 1280, 8), (2, 12, 1280, 1280, 1280, 1280, 6),
+                                                       (2, 12, 1280, 1280, 1280, 1280, 0), (2, 24, 1280, 1280, 1280, 1280, 0),
+                                                       (2, 24, 1280, 1280, 640, 1280, 4), (2, 8, 1280, 1280, 1280, 1280, 8),
+                                                       (2, 48, 640, 1280, 640, 640, 0), (2, 48, 640, 320, 0, 640, 0),
+                                                       (2, 96, 320, 640, 320, 320, 0)])
 def test_conv3x3_extra_1x1_source(N, H, C, Cx0, Cx1, Cout, nsplit):
     """conv3x3(a) + conv1x1(x0 ++ x1) in ONE GEMM (the resblock's skip convolution as extra k-blocks)."""
     ops = _ops()

@@ -19,7 +19,9 @@ models = synthetic.build_models(dev, which=("diffusion",))
 sd = synthetic.state_dicts(models)["diffusion"]
 g = torch.Generator().manual_seed(11)
 ctx = torch.randn(2, 77, 768, generator=g).to(dev)
-for hw, t in ((32, 980), (64, 980), (64, 500), (64, 20), (96, 980)):
+CASES = ((96, 980), (96, 500), (96, 20), (96, 740), (48, 980)) if "--96" in sys.argv else \
+    ((32, 980), (64, 980), (64, 500), (64, 20), (96, 980))
+for hw, t in CASES:
     lat = torch.randn(1, 4, hw, hw, generator=g).to(dev).repeat(2, 1, 1, 1)
     temb = pipeline.get_time_embedding(t).to(dev)
     with torch.no_grad():
