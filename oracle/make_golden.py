@@ -65,6 +65,9 @@ def build_reference_models(ref):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also run the 50-step txt2img and img2img references")
+    ap.add_argument("--img2img50", action="store_true",
+                    help="only config 3 as written: img2img on dog.jpg, strength 0.8, 50 nominal steps (40 UNet "
+                         "evaluations) -> tests/golden/img2img_50.pt")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_grad_enabled(False)
@@ -95,6 +98,29 @@ def main():
 
     cond, uncond = canonical_tokens()
     out = {"weights_digest": digest, "cond_tokens": cond, "uncond_tokens": uncond}
+
+    if args.img2img50:
+        # ---- config 3 as BASELINE.json words it: strength 0.8, 50 nominal DDPM steps = 40 UNet evaluations (t = 780 .. 0)
+        from PIL import Image
+        tok = StubTokenizer({"a": cond.tolist(), "b": uncond.tolist()})
+        dog = Image.open("/root/reference/images/dog.jpg")
+        dec_in = {}
+        def grab(mod, inp):                 # must return None: a returned tensor would replace the input
+            dec_in.setdefault("z", inp[0].clone())
+
+        hd = models["decoder"].register_forward_pre_hook(grab)
+        t0 = time.time()
+        image = ref["pipeline"].generate(prompt="a", uncond_prompt="b", input_image=dog, strength=0.8, do_cfg=True,
+                                         cfg_scale=7.5, sampler_name="ddpm", n_inference_steps=50, models=models,
+                                         seed=42, device="cpu", idle_device=None, tokenizer=tok)
+        dt = time.time() - t0
+        hd.remove()
+        print(f"reference img2img 50 nominal steps on CPU: {dt:.1f}s", flush=True)
+        torch.save({"image": torch.from_numpy(image.copy()), "final_latents": dec_in["z"], "cpu_seconds": dt,
+                    "threads": torch.get_num_threads(), "input_from": "img2img_5.pt['input'] (dog.jpg resized to 512x512)"},
+                   os.path.join(GOLDEN, "img2img_50.pt"))
+        print("img2img_50.pt written", flush=True)
+        return
 
     # ---- small-block goldens (fast to re-check in the CPU suite)
     g = torch.Generator().manual_seed(123)

@@ -378,10 +378,9 @@ __global__ void image_to_uint8_kernel(const float* __restrict__ x, unsigned char
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     // rescale (-1,1) -> (0,255) in the reference's operation order: x -= -1; x *= 255/2; x += 0
-    float v = x[i];
-    v -= -1.0f;
-    v *= 127.5f;
-    v += 0.0f;
+    // (explicit round-to-nearest intrinsics: no FMA contraction, bit-identical to the three torch ops)
+    float v = __fmul_rn(__fsub_rn(x[i], -1.0f), 127.5f);
+    v = __fadd_rn(v, 0.0f);
     v = fminf(fmaxf(v, 0.f), 255.f);
     out[i] = (unsigned char)v;  // truncation, as torch's float -> uint8 cast
   }
@@ -391,10 +390,8 @@ __global__ void uint8_to_image_kernel(const unsigned char* __restrict__ x, void*
                                       long long n, int out_fp32) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    float v = (float)x[i];
-    v -= 0.0f;
-    v *= (2.0f / 255.0f);
-    v += -1.0f;
+    // x -= 0; x *= 2/255; x += -1 (sd/pipeline.py:295-301) as three separately rounded fp32 operations
+    float v = __fadd_rn(__fmul_rn((float)x[i], 2.0f / 255.0f), -1.0f);
     if (out_fp32) reinterpret_cast<float*>(out)[i] = v;
     else reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
   }

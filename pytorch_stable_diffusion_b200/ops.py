@@ -27,18 +27,20 @@ class LaunchProfiler:
     def __init__(self):
         self.records = []
 
-    def begin(self, name, flops=0.0, nbytes=0.0, shape=None):
+    def begin(self, name, flops=0.0, nbytes=0.0, shape=None, relaunch=None):
+        """relaunch: optional zero-argument callable that issues the identical launch again (same device
+        buffers, same arguments) - bench.py re-times the dominant launch inside a CUDA graph with it."""
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        self.records.append([name, float(flops), float(nbytes), e0, e1, shape])
+        self.records.append([name, float(flops), float(nbytes), e0, e1, shape, relaunch])
         return e1
 
     def summary(self, by_shape=False):
         """{name (or (name, shape)): launches, ms, flops, bytes} over the recorded launches."""
         torch.cuda.synchronize()
         out = {}
-        for name, flops, nbytes, e0, e1, shape in self.records:
+        for name, flops, nbytes, e0, e1, shape, relaunch in self.records:
             key = (name, shape) if by_shape else name
             d = out.setdefault(key, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
@@ -51,8 +53,8 @@ class LaunchProfiler:
 PROFILER = None
 
 
-def _prof(name, flops=0.0, nbytes=0.0, shape=None):
-    return PROFILER.begin(name, flops, nbytes, shape) if PROFILER is not None else None
+def _prof(name, flops=0.0, nbytes=0.0, shape=None, relaunch=None):
+    return PROFILER.begin(name, flops, nbytes, shape, relaunch) if PROFILER is not None else None
 
 
 def _prof_end(ev):
@@ -219,13 +221,22 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
             part = torch.empty((gn_samples, k_slabs, cout, 2), device=a0.device, dtype=torch.float32)
             args.gn_part = _p(part)
             args.gn_hw = hw
-    ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear",
-               2.0 * rows * cout * (ntaps * (c0 + c1) + cx0 + cx1),
-               2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * (ntaps * (c0 + c1) + cx0 + cx1))
-               + out.numel() * out.element_size()
-               + (rows * cout * residual.element_size() if residual is not None else 0)
-               + (rows * cout * 2 if out2 is not None else 0),
-               shape=f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps}")
+    ev = None
+    if PROFILER is not None:
+        # one key per launch VARIANT: everything that changes the FLOPs or the bytes of the launch is in it, so the
+        # per-shape averages bench.py reports are averages over identical launches
+        k_total = ntaps * (c0 + c1) + cx0 + cx1
+        res_b = residual.element_size() if residual is not None else 0
+        shape = (f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps} cx={cx0 + cx1} "
+                 f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={('f32', 'bf16')[res_b == 2] if res_b else 'none'} "
+                 f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit}")
+        keep = (a0, a1, w, bias, residual, out, out2, ws, part, ax0, ax1)     # the relaunch closure owns its operands
+        ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear",
+                   2.0 * rows * cout * k_total,
+                   2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * k_total) + out.numel() * out.element_size()
+                   + rows * cout * res_b + (rows * cout * 2 if out2 is not None else 0),
+                   shape=shape,
+                   relaunch=lambda: (keep, _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc"))[1])
     _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc")
     _prof_end(ev)
     if gn_samples is not None:
@@ -270,8 +281,14 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
     a.q_prescaled = 1 if q_prescaled else 0
     a.qk_cols = qk_cols
     a.qk_fold = 1 if qk_fold else 0
-    ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
-               2.0 * NB * heads * d * (2 * S + 2 * Skv))
+    ev = None
+    if PROFILER is not None:
+        keep = (q, k, vt, out)
+        # algorithmic bytes: Q and O once, K and V once per sample and head (re-reads by the query tiles hit L2)
+        ev = _prof("attention", 4.0 * NB * heads * S * Skv * d * (0.5 if causal else 1.0),
+                   2.0 * NB * heads * d * (2 * S + 2 * Skv),
+                   shape=f"NB={NB} heads={heads} d={d} S={S} Skv={Skv} causal={int(causal)} fold={int(qk_fold)}",
+                   relaunch=lambda: (keep, _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention"))[1])
     _ext.check(lib.sdb_attention(ctypes.byref(a), _stream()), "sdb_attention")
     _prof_end(ev)
     return out
@@ -295,32 +312,37 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     if fused is None:
         fused = (not _NO_GN_FUSED) and f0 == 1 and (x1 is None or f1 == 1) and \
             lib.sdb_groupnorm_fused_supported(hw, c0, c1, groups) == 2
-    if fused:
-        out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
-        ev = _prof("groupnorm", 0.0, 4.0 * n * hw * (c0 + c1) + 2.0 * n * hw * (c0 + c1))
-        _ext.check(lib.sdb_groupnorm_fused(_p(_chk(x0, torch.float32, "x0")), _p(x1), _p(gamma), _p(beta), _p(out),
-                                           n, hw, c0, c1, groups, float(eps), 1 if silu else 0, _stream()),
-                   "sdb_groupnorm_fused")
-        _prof_end(ev)
-        return out
-    stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
+    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
-    have_parts = part0 is not None and (x1 is None or part1 is not None) and not _NO_GN_EPI
-    ev = _prof("groupnorm", 0.0, (1.0 if have_parts else 2.0) * in_bytes + 2.0 * (nel0 + nel1))
-    if have_parts:
-        # statistics from the partial sums the producers' epilogues wrote: no pass over the tensor
-        _ext.check(lib.sdb_groupnorm_reduce_partials(_p(part0), _p(part1), _p(stats), n, part0.shape[1],
-                                                     part1.shape[1] if part1 is not None else 0, c0, c1, groups,
-                                                     _stream()), "sdb_groupnorm_reduce_partials")
+    if fused:
+        _chk(x0, torch.float32, "x0")
+
+        def launch():
+            _ext.check(lib.sdb_groupnorm_fused(_p(x0), _p(x1), _p(gamma), _p(beta), _p(out), n, hw, c0, c1, groups,
+                                               float(eps), 1 if silu else 0, _stream()), "sdb_groupnorm_fused")
+        passes, form = 1.0, "one-pass"
     else:
-        _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
-                   "sdb_groupnorm_stats")
-    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
-    _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
-                                       c0, c1, groups, float(eps), 1 if silu else 0, f0, f1,
-                                       1 if have_parts else 0, _stream()),
-               "sdb_groupnorm_apply")
+        stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
+        have_parts = part0 is not None and (x1 is None or part1 is not None) and not _NO_GN_EPI
+
+        def launch():
+            if have_parts:
+                # statistics from the partial sums the producers' epilogues wrote: no pass over the tensor
+                _ext.check(lib.sdb_groupnorm_reduce_partials(_p(part0), _p(part1), _p(stats), n, part0.shape[1],
+                                                             part1.shape[1] if part1 is not None else 0, c0, c1,
+                                                             groups, _stream()), "sdb_groupnorm_reduce_partials")
+            else:
+                _ext.check(lib.sdb_groupnorm_stats(_p(x0), _p(x1), _p(stats), n, hw, c0, c1, groups, f0, f1, _stream()),
+                           "sdb_groupnorm_stats")
+            _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
+                                               c0, c1, groups, float(eps), 1 if silu else 0, f0, f1,
+                                               1 if have_parts else 0, _stream()), "sdb_groupnorm_apply")
+        passes, form = (1.0, "epilogue-stats+apply") if have_parts else (2.0, "stats+apply")
+    ev = _prof("groupnorm", 0.0, passes * in_bytes + 2.0 * (nel0 + nel1),
+               shape=f"n={n} hw={hw} c0={c0} c1={c1} in={'f32' if f0 else 'bf16'} silu={int(silu)} {form}",
+               relaunch=launch)
+    launch()
     _prof_end(ev)
     return out
 
@@ -330,10 +352,15 @@ def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False):
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    ev = _prof("layernorm", 0.0, x.numel() * x.element_size() + out.numel() * out.element_size())
-    _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
-                                 1 if x.dtype == torch.float32 else 0, 1 if out_fp32 else 0, _stream()),
-               "sdb_layernorm")
+
+    def launch():
+        _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
+                                     1 if x.dtype == torch.float32 else 0, 1 if out_fp32 else 0, _stream()),
+                   "sdb_layernorm")
+    ev = _prof("layernorm", 0.0, x.numel() * x.element_size() + out.numel() * out.element_size(),
+               shape=f"rows={rows} c={c} in={'f32' if x.dtype == torch.float32 else 'bf16'} "
+                     f"out={'f32' if out_fp32 else 'bf16'}", relaunch=launch)
+    launch()
     _prof_end(ev)
     return out
 
