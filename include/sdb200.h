@@ -34,6 +34,9 @@ const char* sdb_last_error(void);
 /* Number of kernels this library has launched in this process (a launch recorded during CUDA-graph
  * capture counts once, at capture time). */
 unsigned long long sdb_launch_count(void);
+/* sizeof(sdb_gemm_args) (which = 0) / sizeof(sdb_attn_args) (which = 1) in this build of the library; a binding
+ * checks it against its own struct layout before the first call. */
+int sdb_args_size(int which);
 /* Reads and clears the device watchdog word (non-zero = an mbarrier wait timed out inside a
  * kernel: (site << 8) | kind). Synchronises the device; for tests and smoke runs only. */
 int sdb_read_fault(unsigned int* out_host);
@@ -227,6 +230,12 @@ int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, int out_f
  * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out fp32 [NB, T_pad, D]. */
 int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,
                    int T, int T_pad, int D, int vocab, void* stream);
+
+/* Pack-time helper (model load, not the sampling loop): C[M, N] = A[M, K] . B[K, N], row-major, A / B fp32 (or fp64
+ * when a_f64 / b_f64), C fp64, accumulated in fp64 on the CUDA cores. Composes the reference's feed-forward
+ * linear_geglu_2 . linear_geglu_1[:4C] (no non-linearity in between: the GEGLU gate is dead, sd/diffusion.py:359-363)
+ * and conv_output (:371-381) into one matrix per attention block. */
+int sdb_matmul_f64(const void* A, int a_f64, const void* B, int b_f64, double* C, int M, int N, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ SIGNATURES = {
     "sdb_abi_version": [],
     "sdb_last_error": [],
     "sdb_launch_count": [],
+    "sdb_args_size": [c_int],
     "sdb_read_fault": [ctypes.POINTER(ctypes.c_uint)],
     "sdb_gemm_tc": [ctypes.POINTER(GemmArgs), c_void_p],
     "sdb_debug_gemm_trace": [c_int, ctypes.POINTER(ctypes.c_longlong)],
@@ -71,6 +72,7 @@ SIGNATURES = {
     "sdb_image_to_uint8": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "sdb_matmul_f64": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong,
              "sdb_groupnorm_stats_bytes": ctypes.c_longlong}
@@ -95,6 +97,10 @@ def lib():
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = _RESTYPES.get(name, c_int)
+        for which, struct in ((0, GemmArgs), (1, AttnArgs)):
+            if l.sdb_args_size(which) != ctypes.sizeof(struct):
+                raise SdbError(f"{LIB_PATH}: sizeof({struct.__name__}) is {l.sdb_args_size(which)} in the library but "
+                               f"{ctypes.sizeof(struct)} in _ext.py - rebuild the library (stale .so?)")
         _lib = l
     return _lib
 

@@ -417,6 +417,49 @@ __global__ void clip_embed_kernel(const long long* __restrict__ tokens, const fl
   }
 }
 
+// Pack-time composition of affine maps in double precision: C[M, N] = A[M, K] . B[K, N] (row-major, A / B fp32 or
+// fp64, C fp64). Used once per model load to fold linear_geglu_2 . linear_geglu_1[:4C] and conv_output into one
+// matrix (sd/diffusion.py:355-381 has no non-linearity between them); products of two fp32 values are exact in fp64.
+// 64 x 64 tile per block, 4 x 4 outputs per thread, K walked 16 at a time through shared memory.
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256) matmul_f64_kernel(const TA* __restrict__ A, const TB* __restrict__ B,
+                                                         double* __restrict__ C, int M, int N, int K) {
+  __shared__ double sa[16][64 + 1];
+  __shared__ double sb[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  double acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, kk = i & 15;          // A tile: 64 rows x 16 k
+      const int gm = m0 + r, gk = k0 + kk;
+      sa[kk][r] = (gm < M && gk < K) ? (double)A[(long long)gm * K + gk] : 0.0;
+      const int kb = i >> 6, c = i & 63;          // B tile: 16 k x 64 columns
+      const int gk2 = k0 + kb, gn = n0 + c;
+      sb[kb][c] = (gk2 < K && gn < N) ? (double)B[(long long)gk2 * N + gn] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sa[kk][ty * 4 + i]; b[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gm < M && gn < N) C[(long long)gm * N + gn] = acc[i][j];
+    }
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -480,13 +523,13 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
   const size_t smem = (size_t)ksize * ksize * Cin * CoutPad * sizeof(float);
   if (smem > 160 * 1024) { set_error("sdb_conv_direct: weights too large"); return SDB_ERR_UNSUPPORTED; }
   const long long total = (long long)NB * H * W * (CoutPad / 8);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(conv_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(conv_direct_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(conv_direct4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(conv_direct4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    configured = true;
+  static PerDeviceOnce direct_once = {};
+  if (first_use_on_device(direct_once)) {
+    int rc = set_max_smem(conv_direct_kernel<1>, 160 * 1024, "sdb_conv_direct");
+    if (!rc) rc = set_max_smem(conv_direct_kernel<3>, 160 * 1024, "sdb_conv_direct");
+    if (!rc) rc = set_max_smem(conv_direct4_kernel<1>, 160 * 1024, "sdb_conv_direct");
+    if (!rc) rc = set_max_smem(conv_direct4_kernel<3>, 160 * 1024, "sdb_conv_direct");
+    if (rc) return rc;
   }
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -592,4 +635,16 @@ extern "C" int sdb_clip_embed(const long long* tokens, const float* table, const
   clip_embed_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(tokens, table, pos, (float*)out, NB,
                                                                   T, T_pad, D, vocab);
   return check_launch("clip_embed_kernel");
+}
+
+extern "C" int sdb_matmul_f64(const void* A, int a_f64, const void* B, int b_f64, double* C, int M, int N, int K,
+                              void* stream) {
+  using namespace sdb;
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) { set_error("sdb_matmul_f64: bad arguments"); return SDB_ERR_ARG; }
+  const dim3 grid((N + 63) / 64, (M + 63) / 64);
+  if (a_f64 && b_f64) matmul_f64_kernel<double, double><<<grid, 256, 0, SDB_STREAM>>>((const double*)A, (const double*)B, C, M, N, K);
+  else if (a_f64) matmul_f64_kernel<double, float><<<grid, 256, 0, SDB_STREAM>>>((const double*)A, (const float*)B, C, M, N, K);
+  else if (b_f64) matmul_f64_kernel<float, double><<<grid, 256, 0, SDB_STREAM>>>((const float*)A, (const double*)B, C, M, N, K);
+  else matmul_f64_kernel<float, float><<<grid, 256, 0, SDB_STREAM>>>((const float*)A, (const float*)B, C, M, N, K);
+  return check_launch("matmul_f64_kernel");
 }

@@ -1,6 +1,7 @@
 // Host-side runtime glue for the C-ABI library (error reporting, TMA descriptor encoding).
 #include "host.h"
 #include <stdarg.h>
+#include <atomic>
 #include <stdlib.h>
 #include "common.cuh"
 #include "../../include/sdb200.h"
@@ -16,10 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static unsigned long long g_launches = 0;
+static std::atomic<unsigned long long> g_launches{0};   // entry points may be called from one thread per GPU
 
 int check_launch(const char* what) {
-  ++g_launches;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -113,7 +114,15 @@ int sdb_abi_version(void) { return SDB_ABI_VERSION; }
 
 // Kernels launched by this library in this process so far (launches recorded into a CUDA graph
 // count once, at capture).
-unsigned long long sdb_launch_count(void) { return sdb::g_launches; }
+unsigned long long sdb_launch_count(void) { return sdb::g_launches.load(std::memory_order_relaxed); }
+
+// sizeof() of the argument structs as THIS build sees them: a binding compares it with its own struct size
+// before the first call (a short struct would make the entry point read past its end).
+int sdb_args_size(int which) {
+  if (which == 0) return (int)sizeof(sdb_gemm_args);
+  if (which == 1) return (int)sizeof(sdb_attn_args);
+  return SDB_ERR_ARG;
+}
 
 // Reads and clears the device fault word (mbarrier watchdog). Synchronises the device.
 int sdb_read_fault(unsigned int* out) {

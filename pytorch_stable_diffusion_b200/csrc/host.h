@@ -63,6 +63,28 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: every entry point that needs more than
+// 48 KiB of dynamic shared memory configures its kernels once per device (one process or thread per GPU).
+struct PerDeviceOnce { bool done[64]; };
+// true when the calling entry point still has to configure the current device (and marks it configured)
+inline bool first_use_on_device(PerDeviceOnce& o) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (o.done[dev]) return false;
+  o.done[dev] = true;
+  return true;
+}
+template <typename K>
+inline int set_max_smem(K kernel, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d): %s", what, bytes, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return SDB_ERR_CUDA;
+  }
+  return SDB_OK;
+}
+
 // General form: elem_bytes 2 (16-bit) or 4 (fp32); swizzle_bytes 0 / 32 / 64 / 128.
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank,
               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, const char* what);

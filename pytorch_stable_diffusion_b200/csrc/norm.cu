@@ -704,11 +704,10 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
     return SDB_ERR_UNSUPPORTED;
   }
   const size_t smem_apply = (size_t)chunks * groups * 2 * sizeof(double);
-  static bool apply_configured = false;
-  if (!apply_configured) {
-    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double));
-    apply_configured = true;
+  static PerDeviceOnce apply_once = {};
+  if (first_use_on_device(apply_once)) {
+    int rc = set_max_smem(gn_apply_kernel, GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double), "sdb_groupnorm_apply");
+    if (rc) return rc;
   }
   cudaError_t le = launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
                             x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
@@ -747,10 +746,10 @@ extern "C" int sdb_groupnorm_fused(const float* x0, const float* x1, const float
   p.x0 = x0; p.x1 = x1; p.gamma = gamma; p.beta = beta; p.out = (__nv_bfloat16*)out;
   p.HW = (int)HW; p.C0 = C0; p.C1 = C1; p.cpg = (C0 + C1) / groups; p.SC = p.G * p.cpg;
   p.nslabs = groups / p.G; p.silu = silu; p.eps = eps;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
+  static PerDeviceOnce fused_once = {};
+  if (first_use_on_device(fused_once)) {
+    int rc = set_max_smem(gn_fused_kernel, 200 * 1024, "sdb_groupnorm_fused");
+    if (rc) return rc;
   }
   cudaError_t e = launch_k(gn_fused_kernel, dim3((unsigned)((long long)NB * p.nslabs * p.CS)), dim3(GNF_THREADS), smem,
                            (cudaStream_t)stream, p.CS, p);
@@ -797,14 +796,19 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
 extern "C" int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols,
                                 float scale, void* stream) {
   using namespace sdb;
-  if (!scores || !probs || rows <= 0 || cols <= 0 || cols > 24576) {
+  if (!scores || !probs || rows <= 0 || cols <= 0) {
     set_error("sdb_softmax_rows: bad arguments");
     return SDB_ERR_ARG;
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(softmax_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    configured = true;
+  if (cols > 24576) {
+    set_error("sdb_softmax_rows: %d columns exceed the 24576 a row can hold in shared memory "
+              "(VAE attention above 1248 x 1248 pixels)", cols);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  static PerDeviceOnce softmax_once = {};
+  if (first_use_on_device(softmax_once)) {
+    int rc = set_max_smem(softmax_rows_kernel, 100 * 1024, "sdb_softmax_rows");
+    if (rc) return rc;
   }
   softmax_rows_kernel<<<(unsigned)rows, 256, cols * sizeof(float), (cudaStream_t)stream>>>(
       scores, (__nv_bfloat16*)probs, cols, scale * 1.4426950408889634f);

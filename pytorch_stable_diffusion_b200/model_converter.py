@@ -212,12 +212,25 @@ def convert_state_dict(original_model):
     return converted
 
 
-def load_from_standard_weights(input_file: str, device: str) -> dict:
+def load_from_standard_weights(input_file: str, device: str, allow_unsafe_pickle: bool = None) -> dict:
     """Reads a CompVis .ckpt and returns {'diffusion','encoder','decoder','clip'} state_dicts
-    (sd/model_converter.py:3). The file is unpickled with weights_only=True first; legacy
-    checkpoints that need arbitrary pickled classes fall back to the reference's behaviour."""
+    (sd/model_converter.py:3).
+
+    The file is unpickled with weights_only=True. The reference loads with weights_only=False
+    (sd/model_converter.py:5), which executes whatever the pickle contains; that behaviour is opt-in here:
+    allow_unsafe_pickle=True, or SDB_ALLOW_UNSAFE_PICKLE=1 in the environment, for legacy checkpoints that pickle
+    arbitrary classes - only for files you trust."""
+    import os
+    import pickle
+    if allow_unsafe_pickle is None:
+        allow_unsafe_pickle = os.environ.get("SDB_ALLOW_UNSAFE_PICKLE") == "1"
     try:
         ckpt = torch.load(input_file, map_location=device, weights_only=True)
-    except Exception:
+    except pickle.UnpicklingError as e:
+        if not allow_unsafe_pickle:
+            raise pickle.UnpicklingError(
+                f"{input_file} cannot be read with weights_only=True ({e}). If you trust the file, pass "
+                "allow_unsafe_pickle=True (or set SDB_ALLOW_UNSAFE_PICKLE=1) to unpickle it the way the reference "
+                "does - this executes code stored in the checkpoint.") from e
         ckpt = torch.load(input_file, map_location=device, weights_only=False)
     return convert_state_dict(ckpt["state_dict"])

@@ -512,3 +512,19 @@ def clip_embed(tokens, table, pos, t_pad):
     _ext.check(lib.sdb_clip_embed(_p(tokens), _p(table), _p(pos), _p(out), nb, t, t_pad, d, vocab, _stream()),
                "sdb_clip_embed")
     return out
+
+
+def matmul_f64(a, b):
+    """Pack-time fp64 product of row-major matrices (fp32 or fp64 in, fp64 out) on the CUDA cores - no library GEMM."""
+    lib = _ext.lib()
+    for t, nm in ((a, "a"), (b, "b")):
+        if not t.is_cuda or t.dtype not in (torch.float32, torch.float64) or not t.is_contiguous():
+            raise ValueError(f"{nm} must be a contiguous fp32/fp64 CUDA tensor")
+    m, k = a.shape
+    k2, n = b.shape
+    if k != k2:
+        raise ValueError("inner dimensions differ")
+    out = torch.empty((m, n), device=a.device, dtype=torch.float64)
+    _ext.check(lib.sdb_matmul_f64(_p(a), 1 if a.dtype == torch.float64 else 0, _p(b), 1 if b.dtype == torch.float64 else 0,
+                                  _p(out), m, n, k, _stream()), "sdb_matmul_f64")
+    return out

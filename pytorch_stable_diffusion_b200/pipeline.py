@@ -7,6 +7,8 @@ Extensions are keyword-only and default to the reference's behaviour (one 512x51
 from torch.Generator(device)): batch_size, height/width, per-sample seeds, injected noise,
 return_all, use_cuda_graph, trace.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -18,7 +20,11 @@ HEIGHT = 512
 LATENTS_WIDTH = WIDTH // 8
 LATENTS_HEIGHT = HEIGHT // 8
 
-_GRAPH_CACHE = {}
+# Captured denoising loops, least recently used first. Each entry pins its static buffers and its graph's memory
+# pool (a few GB at batch 8), so only the GRAPH_CACHE_SIZE most recently used configurations stay resident:
+# alternating txt2img (50 steps) and img2img (40 steps), or two batch sizes, does not re-capture.
+GRAPH_CACHE_SIZE = 3
+_GRAPH_CACHE = collections.OrderedDict()
 
 
 def rescale(x, old_range, new_range, clamp=False):
@@ -242,9 +248,18 @@ def generate(
         images = sample_on_device(diffusion, decoder, context, latents, step_noise, coef, temb,
                                   do_cfg=do_cfg, cfg_scale=cfg_scale, use_cuda_graph=use_cuda_graph,
                                   trace=trace, timesteps=timesteps)
+        images = images.to("cpu").numpy()
+        check_device_fault("pipeline.generate")
+        if idle_device:
+            # idle_device means "give the GPU memory back" (sd/pipeline.py:80-85): besides the fp32 parameters that
+            # is the packed bf16 engines and the captured loop, which would otherwise keep everything resident.
+            # The next call repacks and re-captures.
+            drop_cached_graphs(diffusion.__dict__.get("_sdb_engine", (None, None))[1])
+            for m in (clip, diffusion, decoder) + ((models["encoder"],) if input_image else ()):
+                m.invalidate_packed()
+            diffusion.__dict__.pop("_sdb_ctx", None)
         to_idle(diffusion)
         to_idle(decoder)
-        images = images.to("cpu").numpy()
         return images if return_all else images[0]
 
 
@@ -267,8 +282,11 @@ def sample_on_device(diffusion, decoder, context, latents, step_noise, coef, tem
     loop = _GRAPH_CACHE.get(key)
     if loop is None:
         loop = _Loop(eng, B, lh, lw, n_steps, bool(do_cfg), float(cfg_scale), device)
-        _GRAPH_CACHE.clear()          # one resident configuration; graphs pin their memory pool
         _GRAPH_CACHE[key] = loop
+        while len(_GRAPH_CACHE) > GRAPH_CACHE_SIZE:
+            _GRAPH_CACHE.popitem(last=False)
+    else:
+        _GRAPH_CACHE.move_to_end(key)
     loop.set_inputs(latents, step_noise, coef, tvecs, kvs)
     if trace is not None or not use_cuda_graph:
         loop.run_steps(trace=trace, timesteps=timesteps)
@@ -279,3 +297,18 @@ def sample_on_device(diffusion, decoder, context, latents, step_noise, coef, tem
         loop.replay()
     images = decoder.decode_nhwc(loop.latents)           # fp32 NHWC in ~[-1, 1]
     return ops.image_to_uint8(images)
+
+
+def drop_cached_graphs(engine=None):
+    """Releases the captured loops (all, or those of one UNet engine) and the memory their graphs pin."""
+    for key in [k for k, lp in _GRAPH_CACHE.items() if engine is None or lp.eng is engine]:
+        del _GRAPH_CACHE[key]
+
+
+def check_device_fault(what):
+    """Raises if a kernel's mbarrier watchdog tripped since the last check (a wait that timed out lets the kernel run
+    on with data that was not ready: every result since then is suspect). Synchronises the device."""
+    fault = _ext.read_fault()
+    if fault:
+        raise _ext.SdbError(f"{what}: device watchdog fault 0x{fault:x} (mbarrier wait timed out at site {fault >> 8}); "
+                            "the results of this call are invalid - the fault word has been cleared, retry the call")

@@ -50,14 +50,22 @@ def gather_images(local_images, n_total, group=None):
 
 def generate_sharded(prompt, uncond_prompt, seeds, gather=True, **kw):
     """pipeline.generate over `seeds`, sharded across the ranks of the default process group. Every
-    rank returns all images when gather=True, else only its own shard."""
+    rank returns all images when gather=True, else only its own shard. A rank whose shard is empty (more ranks
+    than seeds) generates nothing and still takes part in the gather."""
+    import numpy as np
     from . import pipeline
     mine = shard_seeds(seeds)
-    images = pipeline.generate(prompt, uncond_prompt, seeds=mine, batch_size=len(mine), return_all=True, **kw)
+    h = kw.get("height") or pipeline.HEIGHT
+    w = kw.get("width") or pipeline.WIDTH
+    if mine:
+        images = pipeline.generate(prompt, uncond_prompt, seeds=mine, batch_size=len(mine), return_all=True, **kw)
+    else:
+        images = np.zeros((0, h, w, 3), dtype=np.uint8)
     if not gather:
         return images
-    dev = kw.get("device")
     t = torch.from_numpy(images)
     if dist.is_initialized() and dist.get_backend() == "nccl":
-        t = t.to(dev)
-    return gather_images(t, len(seeds)).cpu().numpy()
+        dev = kw.get("device")
+        t = t.to(torch.device("cuda", torch.cuda.current_device()) if dev is None else dev)
+    out = gather_images(t, len(seeds))
+    return out.cpu().numpy() if torch.is_tensor(out) else out

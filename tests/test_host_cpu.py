@@ -34,6 +34,32 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_ext.GemmArgs) > 0 and ctypes.sizeof(_ext.AttnArgs) > 0
 
 
+def test_argument_structs_match_the_library_and_the_header_and_the_docs():
+    """ctypes structs == sizeof() in the built library == field order of include/sdb200.h == INTEGRATION.md."""
+    import subprocess
+    from pytorch_stable_diffusion_b200 import _ext
+    lib = _ext.lib()
+    assert lib.sdb_args_size(0) == ctypes.sizeof(_ext.GemmArgs)
+    assert lib.sdb_args_size(1) == ctypes.sizeof(_ext.AttnArgs)
+    assert lib.sdb_args_size(7) == -1
+    header = open(os.path.join(ROOT, "include", "sdb200.h")).read()
+    for struct, c_name in ((_ext.GemmArgs, "sdb_gemm_args"), (_ext.AttnArgs, "sdb_attn_args")):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (c_name, c_name), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            first, *rest = decl.split(",")
+            names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", first)[-1])
+            names += [r.strip().lstrip("*").strip() for r in rest]
+        assert names == [f[0] for f in struct._fields_], f"{c_name}: header and _ext.py disagree"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_integration.py"), "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_c_abi_reports_bad_arguments_without_a_gpu():
     from pytorch_stable_diffusion_b200 import _ext
     lib = _ext.lib()
@@ -54,6 +80,28 @@ def test_product_path_has_no_cpu_fallback():
         pipeline.generate("a", "b", strength=1.5, models={}, tokenizer=StubTokenizer(), device="cpu")
     with pytest.raises(ValueError):
         pipeline.generate("a", "b", sampler_name="ddim", models={}, tokenizer=StubTokenizer(), device="cpu")
+
+
+def test_unsafe_pickle_is_opt_in(tmp_path, monkeypatch):
+    """A checkpoint that needs arbitrary unpickling is refused unless the caller opts in (the reference's
+    weights_only=False, sd/model_converter.py:5, executes whatever the file contains)."""
+    import pickle
+    from pytorch_stable_diffusion_b200 import model_converter
+
+    import fractions                   # any class outside torch's allow-list: weights_only=True rejects it
+    path = str(tmp_path / "legacy.ckpt")
+    torch.save({"state_dict": {}, "extra": fractions.Fraction(1, 3)}, path)
+    monkeypatch.delenv("SDB_ALLOW_UNSAFE_PICKLE", raising=False)
+    with pytest.raises(pickle.UnpicklingError, match="allow_unsafe_pickle"):
+        model_converter.load_from_standard_weights(path, "cpu")
+    with pytest.raises(KeyError):      # opted in: the file is read (and then found to hold no SD weights)
+        model_converter.load_from_standard_weights(path, "cpu", allow_unsafe_pickle=True)
+
+
+def test_graph_cache_is_a_small_lru():
+    from pytorch_stable_diffusion_b200 import pipeline
+    assert 2 <= pipeline.GRAPH_CACHE_SIZE <= 4
+    assert isinstance(pipeline._GRAPH_CACHE, __import__("collections").OrderedDict)
 
 
 # ------------------------------------------------------------------------------------ sampler

@@ -751,3 +751,17 @@ def test_vae_scramble_tail_uint8_embed():
     assert float(e[:, 77:].abs().max()) == 0.0
     a, b = rnd(1000), rnd(1000, seed=4)
     report("axpby", ops.axpby(a, b, 0.3, 0.7), 0.3 * a + 0.7 * b, 1e-6)
+
+
+def test_matmul_f64_pack_time_composition():
+    """ops.matmul_f64 (the GEGLU / conv_output fold at pack time) against torch's fp64 matmul."""
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for m, k, n, da, db in ((320, 1280, 320, torch.float32, torch.float32), (130, 77, 65, torch.float32, torch.float64),
+                            (64, 2560, 1, torch.float32, torch.float32), (100, 33, 7, torch.float64, torch.float32)):
+        a = torch.randn(m, k, device=DEV, generator=g, dtype=torch.float32).to(da)
+        b = torch.randn(k, n, device=DEV, generator=g, dtype=torch.float32).to(db)
+        got = ops.matmul_f64(a, b)
+        ref = a.double() @ b.double()
+        assert got.dtype == torch.float64 and got.shape == (m, n)
+        assert float((got - ref).abs().max() / ref.abs().max()) < 1e-13

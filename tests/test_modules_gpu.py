@@ -342,3 +342,26 @@ def test_generate_errors(models):
         pipeline.generate("a", "b", sampler_name="ddim", models=models, tokenizer=StubTokenizer(), device=DEV)
     with pytest.raises(RuntimeError):
         pipeline.generate("a", "b", models=models, tokenizer=StubTokenizer(), device="cpu")
+
+
+# ------------------------------------------------------------------------------------------ loader
+def test_checkpoint_load_path_on_gpu(models, tmp_path):
+    """A full-size synthetic CompVis checkpoint (the canonical weights laid out under the original SD-1.5 key names)
+    goes through model_loader.preload_models_from_standard_weights(path, "cuda") - converter rules, strict
+    load_state_dict, weights_only=True - and the loaded models generate the same bytes as the canonical ones."""
+    from canon import compvis_checkpoint_from
+    from pytorch_stable_diffusion_b200 import model_loader, pipeline
+    path = str(tmp_path / "synthetic-v1-5.ckpt")
+    torch.save(compvis_checkpoint_from(state_dicts(models)), path)
+    loaded = model_loader.preload_models_from_standard_weights(path, DEV)
+    os.remove(path)
+    assert set(loaded) == {"clip", "encoder", "decoder", "diffusion"}
+    for k in loaded:
+        a, b = loaded[k].state_dict(), models[k].state_dict()
+        assert list(a) == list(b)
+        bad = [n for n in a if not torch.equal(a[n], b[n])]
+        assert not bad, f"{k}: {bad[:4]} differ after the checkpoint round trip"
+    kw = dict(seeds=[42], n_inference_steps=2, device=DEV, tokenizer=StubTokenizer())
+    img_loaded = pipeline.generate("a", "b", models=loaded, **kw)
+    img_canon = pipeline.generate("a", "b", models=models, **kw)
+    assert (img_loaded == img_canon).all()
