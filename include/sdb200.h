@@ -75,7 +75,8 @@ typedef struct sdb_gemm_args {
   int nsplit;             /* split-K factor, 0/1 = none                                          */
   int smem_budget;        /* bytes of shared memory for the pipeline, 0 = choose                 */
   int cta_pair;           /* 0 = choose; 1 = one CTA per tile (128 rows); 2 = CTA pairs (256 rows) */
-  int out_f16;            /* 16-bit `out` is IEEE half instead of bf16 (Cout % 32 == 0, no split-K)  */
+  int out_f16;            /* the 16-bit tensor written - `out`, or `out2` next to an fp32 `out` - is IEEE half instead
+                             of bf16 (saturating conversion: +-65504, never inf)                                  */
   int epi_mode;           /* epilogue: 0 = choose; 1 = per-lane global stores; 2 = TMA bulk stores whenever
                              the output geometry / alignment allows (default only for K <= 2048)          */
   float* gn_part;         /* optional: GroupNorm partial statistics of the fp32 OUTPUT, written by the epilogue:
@@ -89,10 +90,18 @@ typedef struct sdb_gemm_args {
   const void* ax1;        /* resblock's skip convolution (sd/diffusion.py:138-143,208): bf16 NHWC             */
   int Cx0, Cx1;           /* [NB, HI, WI, Cx0] (++ [.., Cx1]); w rows then hold 9*(C0+C1) + Cx0 + Cx1 values,  */
                           /* the 1x1 weights last; multiples of 64. NULL = off.                               */
+  int ab_f16;             /* every 16-bit operand (a0, a1, ax0, ax1, w) is IEEE half instead of bf16: 11 instead of 8
+                             significand bits at the same width and tensor-core rate (tcgen05 kind::f16 takes either),
+                             fp32 accumulation unchanged. The UNet's full-resolution level runs this way: it carries
+                             76 % of the squared bf16-rounding error of a UNet evaluation (tools/diag_layer_budget.py) */
 } sdb_gemm_args;
 
 /* Slabs per sample (K above) for a given problem, 0 = gn_part unsupported for this geometry. */
 int sdb_gemm_gn_slabs(int kind, int NB, int HI, int WI, int M, int gn_hw);
+
+/* Tile-chooser aid: bytes of activations one pipeline stage fetches per three k-blocks (one filter column) when a
+ * stride-1 3x3 conv over [NB, HI, WI] runs with filter-column staging, 0 when it cannot (classic: 3 x 16 KiB). */
+int sdb_gemm_conv_a3_bytes(int NB, int HI, int WI);
 
 /* Replaces nn.Conv2d / nn.Linear: sd/diffusion.py:38,42,125,129,135,143,256,266,267,269,410,
  * 545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112,121,129,235-339;
@@ -145,7 +154,8 @@ int sdb_attention(const sdb_attn_args* args, void* stream);
  * (fp64) into `stats`, a caller-provided buffer of sdb_groupnorm_stats_bytes(NB, groups) bytes that
  * needs no initialisation; sdb_groupnorm_apply (same NB, HW, C0, C1, groups) adds the partials in a
  * fixed order. nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;
- * sd/encoder.py:86. */
+ * sd/encoder.py:86. Wherever a normalisation / conversion entry point below takes `out_f16` (or out kind 2), the
+ * 16-bit output is IEEE half instead of bf16 (the operand type of sdb_gemm_args::ab_f16 consumers). */
 long long sdb_groupnorm_stats_bytes(int NB, int groups);
 int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, long long HW,
                         int C0, int C1, int groups, int x0_fp32, int x1_fp32, void* stream);
@@ -154,7 +164,7 @@ int sdb_groupnorm_stats(const void* x0, const void* x1, double* stats, int NB, l
 int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats, const float* gamma,
                         const float* beta, void* out, int NB, long long HW, int C0, int C1,
                         int groups, float eps, int silu, int x0_fp32, int x1_fp32, int stat_chunks,
-                        void* stream);
+                        int out_f16, void* stream);
 /* Statistics without a pass over the tensor: reduces the partial sums the producing GEMM epilogues wrote
  * (sdb_gemm_args::gn_part; part0 [NB][K0][C0][2], part1 [NB][K1][C1][2] for a channel concat or NULL) into
  * `stats` as ONE chunk - follow with sdb_groupnorm_apply(..., stat_chunks = 1). stat_chunks = 0 above means
@@ -168,11 +178,12 @@ int sdb_groupnorm_reduce_partials(const float* part0, const float* part1, double
  * read hits L2), 2 = single-CTA plan (faster; the small UNet levels). */
 int sdb_groupnorm_fused_supported(long long HW, int C0, int C1, int groups);
 int sdb_groupnorm_fused(const float* x0, const float* x1, const float* gamma, const float* beta, void* out,
-                        int NB, long long HW, int C0, int C1, int groups, float eps, int silu, void* stream);
+                        int NB, long long HW, int C0, int C1, int groups, float eps, int silu, int out_f16,
+                        void* stream);
 /* nn.LayerNorm over the last axis (sd/diffusion.py:258,261,264; sd/clip.py:105,113,225).
- * x bf16 (fp32 when in_fp32) [rows, C] -> out bf16 (or fp32 when out_fp32). */
+ * x bf16 (fp32 when in_fp32) [rows, C] -> out bf16 (out_kind 0), fp32 (1) or IEEE half (2). */
 int sdb_layernorm(const void* x, const float* gamma, const float* beta, void* out, long long rows,
-                  int C, float eps, int in_fp32, int out_fp32, void* stream);
+                  int C, float eps, int in_fp32, int out_kind, void* stream);
 /* Row softmax of fp32 scores * scale -> bf16 probabilities (VAE attention, sd/attention.py:66-71). */
 int sdb_softmax_rows(const float* scores, void* probs, long long rows, int cols, float scale,
                      void* stream);
@@ -193,7 +204,8 @@ int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int W, int C, v
  * optional bf16 copy next to an fp32 out (or NULL). sd/diffusion.py:545; sd/decoder.py:235,239;
  * sd/encoder.py:56,92. */
 int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2, int NB,
-                    int H, int W, int Cin, int Cout, int ksize, int out_fp32, int in_fp32, void* stream);
+                    int H, int W, int Cin, int Cout, int ksize, int out_fp32, int in_fp32, int out2_f16,
+                    void* stream);
 /* y[r, n] = act_out( sum_k act_in(x[r, k]) * W[n, k] + bias[n] ), fp32 activations, bf16 weights.
  * The time path: TimeEmbedding (sd/diffusion.py:64-76) and SiLU+linear_time (:184-187). */
 int sdb_small_linear(const float* x, const void* w, const float* bias, float* out, int R, int K,
@@ -212,8 +224,8 @@ int sdb_cfg_ddpm_step(float* latents, const float* eps, const float* noise, cons
  * out[n, p, c] = y_flat[n][c*HW + p] + res[n, p, c]. */
 int sdb_vae_attn_scramble_add(const void* y, const float* res, float* out, void* out2, int NB,
                               long long HW, int C, void* stream);
-/* fp32 -> bf16 copy (bf16 shadow of an fp32 residual-stream tensor). */
-int sdb_f32_to_bf16(const float* x, void* out, long long n, void* stream);
+/* fp32 -> 16-bit copy (bf16, or IEEE half when f16: the 16-bit shadow of an fp32 residual-stream tensor). */
+int sdb_f32_to_bf16(const float* x, void* out, long long n, int f16, void* stream);
 /* VAE encoder tail (sd/encoder.py:127-152): moments fp32 NHWC [NB, H, W, 8] + noise fp32 NCHW
  * [NB, 4, H, W] -> latents fp32 NCHW: (mean + exp(clamp(logvar,-30,20))^0.5 * noise) * 0.18215. */
 int sdb_vae_encode_tail(const float* moments, const float* noise, float* out, int NB, int H, int W,
@@ -226,6 +238,13 @@ int sdb_axpby(const float* x, const float* y, float* out, float a, float b, long
 int sdb_image_to_uint8(const float* x, unsigned char* out, long long n, void* stream);
 /* Pre-processing (sd/pipeline.py:162-173): uint8 HWC -> NHWC in [-1,1], bf16 or (out_fp32) fp32. */
 int sdb_uint8_to_image(const unsigned char* x, void* out, long long n, int out_fp32, void* stream);
+/* One pass of Pillow's 8-bit separable resampler over uint8 NHWC [NB, H, W, C] along W (axis 0) or H (axis 1) -> out_size
+ * samples: PIL.Image.resize as the reference calls it on the input image (sd/pipeline.py:156; bicubic with antialiasing).
+ * bounds int32 [out_size][2] = {first source index, tap count}, coef int32 [out_size][ksize] = taps with 22 fractional
+ * bits (host-computed, pytorch_stable_diffusion_b200/imageio.py). img (optional fp32, same shape as dst) receives
+ * dst * (2/255) - 1, the reference's rescale (sd/pipeline.py:162-173). Byte-exact against Pillow. */
+int sdb_resample_u8(const unsigned char* src, unsigned char* dst, float* img, int NB, int H, int W, int C, int out_size,
+                    int axis, const int* bounds, const int* coef, int ksize, void* stream);
 /* CLIPEmbedding (sd/clip.py:58-63): out[b, t, :] = table[tokens[b, t]] + pos[t]; rows
  * t >= T (up to T_pad) are zero. tokens int64 [NB, T]; table/pos fp32; out fp32 [NB, T_pad, D]. */
 int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,

@@ -20,7 +20,7 @@ class GemmArgs(ctypes.Structure):
         ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
         ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int), ("out_f16", c_int),
         ("epi_mode", c_int), ("gn_part", c_void_p), ("gn_hw", c_int),
-        ("ax0", c_void_p), ("ax1", c_void_p), ("Cx0", c_int), ("Cx1", c_int),
+        ("ax0", c_void_p), ("ax1", c_void_p), ("Cx0", c_int), ("Cx1", c_int), ("ab_f16", c_int),
     ]
 
 
@@ -47,13 +47,14 @@ SIGNATURES = {
     "sdb_groupnorm_stats": [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int,
                             c_void_p],
     "sdb_groupnorm_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll,
-                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_void_p],
+                            c_int, c_int, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_groupnorm_reduce_partials": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_void_p],
     "sdb_gemm_gn_slabs": [c_int, c_int, c_int, c_int, c_int, c_int],
+    "sdb_gemm_conv_a3_bytes": [c_int, c_int, c_int],
     "sdb_groupnorm_fused_supported": [c_ll, c_int, c_int, c_int],
     "sdb_groupnorm_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_int,
-                            c_float, c_int, c_void_p],
+                            c_float, c_int, c_int, c_void_p],
     "sdb_layernorm": [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p],
     "sdb_softmax_rows": [c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p],
     "sdb_fill_zero": [c_void_p, c_ll, c_void_p],
@@ -61,17 +62,19 @@ SIGNATURES = {
     "sdb_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_upsample2x_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_conv_direct": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                        c_int, c_int, c_int, c_void_p],
+                        c_int, c_int, c_int, c_int, c_void_p],
     "sdb_small_linear": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_cfg_ddpm_step": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_int,
                           c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_vae_attn_scramble_add": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_void_p],
-    "sdb_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_void_p],
+    "sdb_f32_to_bf16": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "sdb_vae_encode_tail": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "sdb_axpby": [c_void_p, c_void_p, c_void_p, c_float, c_float, c_ll, c_void_p],
     "sdb_image_to_uint8": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_uint8_to_image": [c_void_p, c_void_p, c_ll, c_int, c_void_p],
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "sdb_resample_u8": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                        c_void_p],
     "sdb_matmul_f64": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong,

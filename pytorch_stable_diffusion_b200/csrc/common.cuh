@@ -320,6 +320,11 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// kind::f16 instruction descriptor with fp32 accumulation: A / B formats bf16 (1) or IEEE half (0)
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(uint32_t m, uint32_t n, int f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 // Shared-memory matrix descriptor for a K-major tile stored as rows of 128 bytes with the
 // 128-byte TMA swizzle (8-row / 1024-byte atoms): start>>4 | SBO(1024)>>4 at [32,46) |
 // version 1 at [46,48) | layout SWIZZLE_128B (2) at [61,64).
@@ -392,6 +397,19 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t h;
   asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
   return h;
+}
+// Two fp32 values -> one 32-bit word of the 16-bit operand type: bf16, or IEEE half when f16 (saturating: values
+// beyond +-65504 become +-65504, never inf - the fp32 master tensor keeps the true value).
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t h;
+  asm volatile("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  return h;
+}
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ unsigned short cvt16(float v, int f16) {
+  return (unsigned short)(pack16x2(v, 0.f, f16) & 0xFFFFu);
 }
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }

@@ -77,7 +77,7 @@ template <int KS>
 __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                    const float* __restrict__ bias, void* __restrict__ out,
                                    __nv_bfloat16* __restrict__ out2, int NB, int H, int W, int Cin,
-                                   int Cout, int out_fp32, int in_fp32) {
+                                   int Cout, int out_fp32, int in_fp32, int out2_f16) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_w[];  // [KS*KS*Cin][CoutPad]
@@ -126,8 +126,9 @@ __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __re
     if ((Cout & 7) == 0) {
       // eight channels per thread, vector stores: consecutive threads write consecutive 32 (16) bytes - the scalar
       // form below took 258 us for the UNet stem (16 x 64 x 64 x 4 -> 320), 13 x its memory time
-      const uint4 h = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                 pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      const int h16 = out_fp32 ? out2_f16 : 0;        // the 16-bit shadow may be IEEE half; a 16-bit `out` is bf16
+      const uint4 h = make_uint4(pack16x2(acc[0], acc[1], h16), pack16x2(acc[2], acc[3], h16),
+                                 pack16x2(acc[4], acc[5], h16), pack16x2(acc[6], acc[7], h16));
       if (out_fp32) {
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -142,7 +143,7 @@ __global__ void conv_direct_kernel(const void* __restrict__ x, const float* __re
       if (g * 8 + j < Cout) {
         if (out_fp32) {
           reinterpret_cast<float*>(out)[obase + j] = acc[j];
-          if (out2 != nullptr) out2[obase + j] = __float2bfloat16_rn(acc[j]);
+          if (out2 != nullptr) reinterpret_cast<unsigned short*>(out2)[obase + j] = cvt16(acc[j], out2_f16);
         } else {
           reinterpret_cast<__nv_bfloat16*>(out)[obase + j] = __float2bfloat16_rn(acc[j]);
         }
@@ -158,7 +159,7 @@ template <int KS>
 __global__ void __launch_bounds__(256) conv_direct4_kernel(const void* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, void* __restrict__ out,
                                                            __nv_bfloat16* __restrict__ out2, int NB, int H, int W,
-                                                           int Cin, int Cout, int out_fp32, int in_fp32) {
+                                                           int Cin, int Cout, int out_fp32, int in_fp32, int out2_f16) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float s_w[];  // [KS*KS*Cin][Cout]
@@ -224,8 +225,9 @@ __global__ void __launch_bounds__(256) conv_direct4_kernel(const void* __restric
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       const long long obase = (((long long)n * H + ho) * W + wo0 + px) * Cout + g * 8;
-      const uint4 h = make_uint4(pack_bf16x2(acc[px][0], acc[px][1]), pack_bf16x2(acc[px][2], acc[px][3]),
-                                 pack_bf16x2(acc[px][4], acc[px][5]), pack_bf16x2(acc[px][6], acc[px][7]));
+      const int h16 = out_fp32 ? out2_f16 : 0;
+      const uint4 h = make_uint4(pack16x2(acc[px][0], acc[px][1], h16), pack16x2(acc[px][2], acc[px][3], h16),
+                                 pack16x2(acc[px][4], acc[px][5], h16), pack16x2(acc[px][6], acc[px][7], h16));
       if (out_fp32) {
         float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
         o[0] = make_float4(acc[px][0], acc[px][1], acc[px][2], acc[px][3]);
@@ -360,10 +362,17 @@ __global__ void vae_encode_tail_kernel(const float* __restrict__ moments, const 
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(x[i]);
+// fp32 -> 16-bit shadow (bf16, or IEEE half when f16), four elements per thread when n % 4 == 0
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, unsigned short* __restrict__ out, long long n, int f16) {
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, step = (long long)gridDim.x * blockDim.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    for (long long i = i0; i < (n >> 2); i += step) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      reinterpret_cast<uint2*>(out)[i] = make_uint2(pack16x2(v.x, v.y, f16), pack16x2(v.z, v.w, f16));
+    }
+    return;
+  }
+  for (long long i = i0; i < n; i += step) out[i] = cvt16(x[i], f16);
 }
 
 __global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y,
@@ -460,6 +469,41 @@ __global__ void __launch_bounds__(256) matmul_f64_kernel(const TA* __restrict__ 
     }
 }
 
+// One pass of Pillow's 8-bit separable resampler (ImagingResampleHorizontal_8bpc / Vertical_8bpc, what
+// PIL.Image.resize runs for the reference's input_image.resize((WIDTH, HEIGHT)), sd/pipeline.py:156) over uint8 NHWC:
+// out[.., o, ..] = clip8((2^21 + sum_k src[.., lo_o + k, ..] * coef[o][k]) >> 22) with the host-computed fixed-point
+// taps (22 fractional bits) and windows [lo_o, lo_o + cnt_o). axis 0 = along W, 1 = along H. With `img` non-null the
+// pass also writes the pre-processed fp32 value x * (2/255) - 1 (sd/pipeline.py:162-173), so resize + rescale of the
+// last pass is one kernel. Bit-exact against Pillow (tests/test_kernels_gpu.py).
+__global__ void resample_u8_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst,
+                                   float* __restrict__ img, int NB, int H, int W, int C, int out_size, int axis,
+                                   const int* __restrict__ bounds, const int* __restrict__ coef, int ksize) {
+  const int HO = axis ? out_size : H, WO = axis ? W : out_size;
+  const long long total = (long long)NB * HO * WO * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int x = (int)((i / C) % WO);
+    const int y = (int)((i / ((long long)C * WO)) % HO);
+    const int n = (int)(i / ((long long)C * WO * HO));
+    const int o = axis ? y : x;
+    const int lo = bounds[2 * o], cnt = bounds[2 * o + 1];
+    const int* k = coef + (long long)o * ksize;
+    int acc = 1 << 21;
+    if (axis) {
+      const unsigned char* p = src + (((long long)n * H + lo) * W + x) * C + c;
+      for (int j = 0; j < cnt; ++j) acc += (int)p[(long long)j * W * C] * k[j];
+    } else {
+      const unsigned char* p = src + (((long long)n * H + y) * W + lo) * C + c;
+      for (int j = 0; j < cnt; ++j) acc += (int)p[(long long)j * C] * k[j];
+    }
+    acc >>= 22;
+    const unsigned char v = (unsigned char)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+    dst[i] = v;
+    if (img != nullptr) img[i] = __fadd_rn(__fmul_rn((float)v, 2.0f / 255.0f), -1.0f);
+  }
+}
+
 }  // namespace sdb
 
 using namespace sdb;
@@ -513,7 +557,7 @@ extern "C" int sdb_upsample2x_nhwc(const void* x, void* out, int NB, int H, int 
 
 extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias, void* out, void* out2,
                                int NB, int H, int W, int Cin, int Cout, int ksize, int out_fp32,
-                               int in_fp32, void* stream) {
+                               int in_fp32, int out2_f16, void* stream) {
   if (!x || !w || !out || NB <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin > 8 || Cout <= 0 ||
       (ksize != 1 && ksize != 3) || (out2 && !out_fp32)) {
     set_error("sdb_conv_direct: bad arguments (Cin=%d Cout=%d k=%d)", Cin, Cout, ksize);
@@ -540,18 +584,18 @@ extern "C" int sdb_conv_direct(const void* x, const float* w, const float* bias,
     const size_t smem4 = (size_t)ksize * ksize * Cin * Cout * sizeof(float);
     if (ksize == 1)
       (void)launch_k(conv_direct4_kernel<1>, dim3((unsigned)blocks4), dim3(256), smem4, SDB_STREAM, 1,
-          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32, out2_f16);
     else
       (void)launch_k(conv_direct4_kernel<3>, dim3((unsigned)blocks4), dim3(256), smem4, SDB_STREAM, 1,
-          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+          x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32, out2_f16);
     return check_launch("conv_direct4_kernel");
   }
   if (ksize == 1)
     (void)launch_k(conv_direct_kernel<1>, dim3((unsigned)blocks), dim3(256), smem, SDB_STREAM, 1,
-        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32, out2_f16);
   else
     (void)launch_k(conv_direct_kernel<3>, dim3((unsigned)blocks), dim3(256), smem, SDB_STREAM, 1,
-        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32);
+        x, w, bias, out, (__nv_bfloat16*)out2, NB, H, W, Cin, Cout, out_fp32, in_fp32, out2_f16);
   return check_launch("conv_direct_kernel");
 }
 
@@ -601,9 +645,9 @@ extern "C" int sdb_vae_encode_tail(const float* moments, const float* noise, flo
   return check_launch("vae_encode_tail_kernel");
 }
 
-extern "C" int sdb_f32_to_bf16(const float* x, void* out, long long n, void* stream) {
+extern "C" int sdb_f32_to_bf16(const float* x, void* out, long long n, int f16, void* stream) {
   if (!x || !out || n <= 0) { set_error("sdb_f32_to_bf16: bad arguments"); return SDB_ERR_ARG; }
-  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, SDB_STREAM>>>(x, (__nv_bfloat16*)out, n);
+  f32_to_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, SDB_STREAM>>>(x, (unsigned short*)out, n, f16);
   return check_launch("f32_to_bf16_kernel");
 }
 
@@ -647,4 +691,18 @@ extern "C" int sdb_matmul_f64(const void* A, int a_f64, const void* B, int b_f64
   else if (b_f64) matmul_f64_kernel<float, double><<<grid, 256, 0, SDB_STREAM>>>((const float*)A, (const double*)B, C, M, N, K);
   else matmul_f64_kernel<float, float><<<grid, 256, 0, SDB_STREAM>>>((const float*)A, (const float*)B, C, M, N, K);
   return check_launch("matmul_f64_kernel");
+}
+
+extern "C" int sdb_resample_u8(const unsigned char* src, unsigned char* dst, float* img, int NB, int H, int W, int C,
+                               int out_size, int axis, const int* bounds, const int* coef, int ksize, void* stream) {
+  using namespace sdb;
+  if (!src || !dst || !bounds || !coef || NB <= 0 || H <= 0 || W <= 0 || C <= 0 || out_size <= 0 || ksize <= 0 ||
+      (axis != 0 && axis != 1)) {
+    set_error("sdb_resample_u8: bad arguments");
+    return SDB_ERR_ARG;
+  }
+  const long long total = (long long)NB * (axis ? out_size : H) * (axis ? W : out_size) * C;
+  resample_u8_kernel<<<grid_for(total, 256), 256, 0, SDB_STREAM>>>(src, dst, img, NB, H, W, C, out_size, axis, bounds,
+                                                                    coef, ksize);
+  return check_launch("resample_u8_kernel");
 }

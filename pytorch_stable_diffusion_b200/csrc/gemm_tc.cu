@@ -61,6 +61,17 @@ struct GemmTcParams {
   int cblocks_x0, cblocks_x;
   int nkb_total;           // ntaps * cblocks + cblocks_x
   int tap_dc_unit;
+  // "Filter-column" staging (a3) of a stride-1 3x3 conv whose tile is a bw x bh patch of ONE sample: a pipeline
+  // stage holds the A box of one filter column kx WITH its two halo rows - (bh + 2) x bw pixels x 64 channels,
+  // fetched once at (w0 + kx - 1, h0 - 1), zero padding = TMA out-of-bounds fill - plus the three W sub-tiles
+  // (ky = 0, 1, 2) of that column. Tap (ky, kx) is then the SAME shared-memory box viewed ky * bw rows further
+  // down (ky * bw * 128 bytes: a multiple of the 1024-byte swizzle atom for bw % 8 == 0, so the UMMA descriptor
+  // only moves its start address). 3 boxes instead of 9 per channel block: (bh + 2) / (3 bh) of the A bytes leave
+  // L2 (0.42 for 16 x 8 patches) - the narrow pair tiles were bound by exactly that L2 -> SM traffic - and the
+  // producer / issuer hand-shake runs once per three k-blocks.
+  int a3;                  // 0 = one tap per stage (classic), 1 = filter-column staging
+  int a3_box_bytes;        // (bh + 2) * bw * 128
+  int a3_iters;            // pipeline stages consumed per tile: 3 * cblocks + cblocks_x
   // epilogue
   int N;                   // valid output columns (Cout)
   int block_n;             // UMMA N (multiple of 16, <= 256)
@@ -78,7 +89,8 @@ struct GemmTcParams {
   void* out;
   long long ldo;
   int out_fp32;
-  int out_f16;             // 16-bit output is IEEE half instead of bf16 (V^T for the f16 attention variant)
+  int out_f16;             // the 16-bit tensor written (out, or out2 next to an fp32 out) is IEEE half instead of bf16
+  int ab_f16;              // A and W are IEEE half (kind::f16 with f16 operand formats); accumulation stays fp32
   const float* bias;
   int bias_mode;           // 0 none, 1 per column, 2 per row
   const void* residual;    // bf16, or fp32 when res_fp32
@@ -197,7 +209,7 @@ __device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], uint32_t (&pk)
     if (F32)
       asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(piece), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
                    : "memory");
-    if (F16) { pk[2 * j] = pack_f16x2(x.x, x.y); pk[2 * j + 1] = pack_f16x2(x.z, x.w); }
+    if (F16) { pk[2 * j] = pack_f16x2_sat(x.x, x.y); pk[2 * j + 1] = pack_f16x2_sat(x.z, x.w); }
     else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
   }
 }
@@ -228,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const int b_rows = p.acc_n / CG;                       // W rows this CTA stages per k-block and accumulator
   const int b_sub_bytes = b_rows * GEMM_BK * 2;
   const int b_stage_bytes = p.n_acc * b_sub_bytes;
-  const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
+  const int stage_bytes = p.a3 ? (p.a3_box_bytes + 3 * b_stage_bytes) : (GEMM_A_STAGE_BYTES + b_stage_bytes);
   const int nbuf = (p.n_acc == 2) ? 1 : 2;               // TMEM accumulator buffers
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
   // [staging: one chunk per epilogue warp][residual ring: GEMM_RES_RING chunks per warp, if any][barriers]
@@ -290,6 +302,72 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const uint32_t tx_bytes = (uint32_t)((p.a_tx_bytes + b_stage_bytes) * CG);
     const int ctot = p.C0 + p.C1;
     int ltp = 0;
+    if (p.a3) {
+      // ----- filter-column staging: per channel block three stages (kx = 0, 1, 2), each ONE halo box + three W
+      // sub-tiles; the extra 1x1 source (if any) follows as classic one-tap stages
+      const uint32_t tx3 = (uint32_t)((p.a3_box_bytes + 3 * b_stage_bytes) * CG);
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
+        const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+        trace_stamp(trc, ltp, 0);
+        const int wn = t.n0 + cta_rank * b_rows;
+        int cb = 0, kx = 0;
+        bool extra = false;
+        for (int i = 0; i < p.a3_iters; ++i) {
+          mbar_wait(&empty_bar[s], ph, 1);
+          uint8_t* a_dst = smem + s * stage_bytes;
+          uint8_t* b_dst = a_dst + p.a3_box_bytes;
+          const int cbl0 = extra ? p.cblocks_x0 : p.cblocks0;
+          const bool second = cb >= cbl0;
+          const CUtensorMap* ma = extra ? (second ? &p.map_x1 : &p.map_x0) : (second ? &p.map_a1 : &p.map_a0);
+          const int c = (second ? (cb - cbl0) : cb) * GEMM_BK;
+          if (elect_one()) {
+            if (!extra) {
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], tx3);
+              const int wk = kx * ctot + cb * GEMM_BK;                    // tap (ky, kx) starts at (3 ky + kx) * ctot
+              if constexpr (CG == 2) {
+                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0 + kx - 1, 0, t.h0 - 1, t.nb0);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + 3 * ky * ctot, wn);
+                  if (p.n_acc == 2)
+                    tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes, wk + 3 * ky * ctot,
+                                     wn + p.acc_n);
+                }
+              } else {
+                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0 + kx - 1, 0, t.h0 - 1, t.nb0);
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                  tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + 3 * ky * ctot, wn);
+                  if (p.n_acc == 2)
+                    tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes, wk + 3 * ky * ctot,
+                                wn + p.acc_n);
+                }
+              }
+            } else {
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+              const int wk = p.ntaps * ctot + cb * GEMM_BK;
+              if constexpr (CG == 2) {
+                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0, 0, t.h0, t.nb0);
+                tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst, wk, wn);
+                if (p.n_acc == 2) tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
+              } else {
+                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0, 0, t.h0, t.nb0);
+                tma_load_2d(&p.map_w, &full_bar[s], b_dst, wk, wn);
+                if (p.n_acc == 2) tma_load_2d(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
+              }
+            }
+          }
+          __syncwarp();
+          if (!extra) {
+            if (++kx == 3) { kx = 0; if (++cb == p.cblocks) { cb = 0; extra = true; } }
+          } else {
+            ++cb;
+          }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+        trace_stamp(trc, ltp, 1);
+      }
+    } else
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
       const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
       trace_stamp(trc, ltp, 0);
@@ -335,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer: warp 1 of the leader CTA, one elected lane issues
     if (leader) {
-      const uint32_t idesc = make_idesc_bf16(GEMM_BM * CG, (uint32_t)p.acc_n);
+      const uint32_t idesc = make_idesc_16(GEMM_BM * CG, (uint32_t)p.acc_n, p.ab_f16);
       const uint64_t b_half = (uint64_t)(b_sub_bytes >> 4);
       const bool wide = (p.n_acc == 2);
       const uint64_t a_desc0 = make_kmajor_sw128_desc(smem_u32(smem));
@@ -353,6 +431,56 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
         uint32_t accum = 0;
+        if (p.a3) {
+          // filter-column staging: a stage holds ONE halo box and the W sub-tiles of ky = 0, 1, 2; tap (ky, kx)
+          // reads the box ky * bw rows further down. The extra 1x1 source follows as one-tap stages.
+          const uint64_t b3_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + (uint32_t)p.a3_box_bytes);
+          const uint64_t a_row_step = (uint64_t)((p.bw * 128) >> 4);
+          const uint64_t b_tap_step = (uint64_t)(b_stage_bytes >> 4);
+          const int n3 = 3 * p.cblocks;
+          for (int i = 0; i < p.a3_iters; ++i) {
+            mbar_wait(&full_bar[s], ph, 2);
+            if (i == 0) trace_stamp(trc, lt, 3);
+            tc_fence_after();
+            const int nsub = (i < n3) ? 3 : 1;
+            if (elect_one()) {
+              for (int j = 0; j < nsub; ++j) {
+                const uint64_t a_desc = a_desc0 + soff + (uint64_t)j * a_row_step;
+                const uint64_t b_desc = b3_desc0 + soff + (uint64_t)j * b_tap_step;
+                if constexpr (CG == 2) {
+                  mma_ss_pair(d_tmem, a_desc, b_desc, idesc, accum);
+                  mma_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                  mma_ss_pair(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                  mma_ss_pair(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                  if (wide) {
+                    mma_ss_pair(d_tmem + 256, a_desc, b_desc + b_half, idesc, accum);
+                    mma_ss_pair(d_tmem + 256, a_desc + 2, b_desc + b_half + 2, idesc, 1u);
+                    mma_ss_pair(d_tmem + 256, a_desc + 4, b_desc + b_half + 4, idesc, 1u);
+                    mma_ss_pair(d_tmem + 256, a_desc + 6, b_desc + b_half + 6, idesc, 1u);
+                  }
+                } else {
+                  mma_ss(d_tmem, a_desc, b_desc, idesc, accum);
+                  mma_ss(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                  mma_ss(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                  mma_ss(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
+                  if (wide) {
+                    mma_ss(d_tmem + 256, a_desc, b_desc + b_half, idesc, accum);
+                    mma_ss(d_tmem + 256, a_desc + 2, b_desc + b_half + 2, idesc, 1u);
+                    mma_ss(d_tmem + 256, a_desc + 4, b_desc + b_half + 4, idesc, 1u);
+                    mma_ss(d_tmem + 256, a_desc + 6, b_desc + b_half + 6, idesc, 1u);
+                  }
+                }
+                accum = 1;
+              }
+              if constexpr (CG == 2) tc_commit_pair(&empty_bar[s], 3);
+              else tc_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+            accum = 1;
+            soff += stage_step;
+            if (++s == p.stages) { s = 0; ph ^= 1u; soff = 0; }
+          }
+        } else
         for (int i = 0; i < t.nkb; ++i) {
           mbar_wait(&full_bar[s], ph, 2);
           if (i == 0) trace_stamp(trc, lt, 3);
@@ -528,7 +656,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
             case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
             case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            default: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 9: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 10: epi_rows<false, true, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 11: epi_rows<true, true, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 12: epi_rows<false, false, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 13: epi_rows<true, false, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 14: epi_rows<false, true, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            default: epi_rows<true, true, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
           }
         }
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
@@ -855,8 +989,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             for (int i = 0; i < 8; ++i)
               if (mrow[i] >= 0)
                 *reinterpret_cast<uint2*>(ob + (long long)mrow[i] * p.ldo) =
-                    p.out_f16 ? make_uint2(pack_f16x2(x[i].x, x[i].y), pack_f16x2(x[i].z, x[i].w))
-                              : make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+                    make_uint2(pack16x2(x[i].x, x[i].y, p.out_f16), pack16x2(x[i].z, x[i].w, p.out_f16));
           }
           if (p.gn_part != nullptr) {
             // GroupNorm statistics of the values just written: this lane's 4 columns over its 8 rows, then
@@ -956,12 +1089,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             if (bp != nullptr) {
               __nv_bfloat16* op = bp + ooff;
               if (vec_ok && ((reinterpret_cast<uintptr_t>(op) & 7u) == 0)) {
-                *reinterpret_cast<uint2*>(op) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+                *reinterpret_cast<uint2*>(op) = make_uint2(pack16x2(x.x, x.y, p.out_f16), pack16x2(x.z, x.w, p.out_f16));
               } else {
-                op[0] = __float2bfloat16_rn(x.x);
-                if (cl + 1 < ncol) op[1] = __float2bfloat16_rn(x.y);
-                if (cl + 2 < ncol) op[2] = __float2bfloat16_rn(x.z);
-                if (cl + 3 < ncol) op[3] = __float2bfloat16_rn(x.w);
+                unsigned short* os = reinterpret_cast<unsigned short*>(op);
+                os[0] = cvt16(x.x, p.out_f16);
+                if (cl + 1 < ncol) os[1] = cvt16(x.y, p.out_f16);
+                if (cl + 2 < ncol) os[2] = cvt16(x.z, p.out_f16);
+                if (cl + 3 < ncol) os[3] = cvt16(x.w, p.out_f16);
               }
             }
           }
@@ -999,7 +1133,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 __global__ void gemm_splitk_finalize4_kernel(const float* __restrict__ ws, int nsplit, long long m_total, int N,
                                              void* out, long long ldo, int out_fp32, const float* __restrict__ bias,
                                              const float* __restrict__ residual, long long ldr, int act,
-                                             __nv_bfloat16* __restrict__ out2) {
+                                             __nv_bfloat16* __restrict__ out2, int f16) {
   pdl_trigger();
   pdl_wait();
   const int nv = N >> 2;
@@ -1026,7 +1160,7 @@ __global__ void gemm_splitk_finalize4_kernel(const float* __restrict__ ws, int n
       const float4 r = *reinterpret_cast<const float4*>(residual + m * ldr + n);
       acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
     }
-    const uint2 h = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    const uint2 h = make_uint2(pack16x2(acc.x, acc.y, f16), pack16x2(acc.z, acc.w, f16));
     if (out_fp32) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + m * ldo + n) = acc;
       if (out2) *reinterpret_cast<uint2*>(out2 + m * ldo + n) = h;
@@ -1042,7 +1176,7 @@ __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int ns
                                             int out_fp32, const float* __restrict__ bias,
                                             int bias_mode, const void* __restrict__ residual,
                                             int res_fp32, long long ldr, int act,
-                                            __nv_bfloat16* __restrict__ out2) {
+                                            __nv_bfloat16* __restrict__ out2, int f16) {
   pdl_trigger();
   pdl_wait();
   const long long total = m_total * N;
@@ -1061,9 +1195,9 @@ __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int ns
     }
     if (out_fp32) {
       reinterpret_cast<float*>(out)[m * ldo + n] = acc;
-      if (out2) out2[m * ldo + n] = __float2bfloat16_rn(acc);
+      if (out2) reinterpret_cast<unsigned short*>(out2)[m * ldo + n] = cvt16(acc, f16);
     } else {
-      reinterpret_cast<__nv_bfloat16*>(out)[m * ldo + n] = __float2bfloat16_rn(acc);
+      reinterpret_cast<unsigned short*>(out)[m * ldo + n] = cvt16(acc, f16);
     }
   }
 }
@@ -1148,6 +1282,19 @@ extern "C" int sdb_gemm_gn_slabs(int kind, int NB, int HI, int WI, int M, int gn
   if (plane % 32 != 0) return 0;
   const int spq = plane / 32 < 4 ? plane / 32 : 4;
   return ((WO + bw - 1) / bw) * ((HO + bh - 1) / bh) * spq;
+}
+
+// Bytes of A one pipeline stage fetches per THREE k-blocks when a stride-1 3x3 conv over [NB, HI, WI] takes the
+// filter-column staging (one halo box per filter column), or 0 when its tile geometry rules that out (the classic
+// form fetches 3 x 16 KiB). For the tile chooser's TMA model.
+extern "C" int sdb_gemm_conv_a3_bytes(int NB, int HI, int WI) {
+  using namespace sdb;
+  int bw = 0, bh = 0, bn = 0;
+  if (NB <= 0 || HI <= 0 || WI <= 0 || pick_tile_box(NB, HI, WI, &bw, &bh, &bn)) return 0;
+  const char* ev = getenv("SDB_NO_A3");
+  if (ev && ev[0] == '1') return 0;
+  if (bn != 1 || bw * bh != GEMM_BM || bw % 8 != 0) return 0;
+  return (bh + 2) * bw * 128;
 }
 
 extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
@@ -1301,8 +1448,41 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     if ((rc = make_tmap_bf16(&p.map_w, a->w, 2, dims, str, box, "gemm W"))) return rc;
   }
 
+  // ---- filter-column staging (a3): stride-1 3x3 conv, tile = bw x bh patch of one sample with bw % 8 == 0 (tap views
+  // stay on 1024-byte swizzle atoms), no split-K (a split could cut a filter column), at least one whole channel block
+  const int b_stage_host = p.n_acc * (p.acc_n / cg) * GEMM_BK * 2;
+  {
+    static int no_a3 = -1;
+    if (no_a3 < 0) { const char* ev = getenv("SDB_NO_A3"); no_a3 = (ev && ev[0] == '1') ? 1 : 0; }
+    const bool ok = !no_a3 && kind == SDB_GEMM_CONV3X3_S1 && p.bn == 1 && p.bw * p.bh == GEMM_BM && p.bw % 8 == 0 &&
+                    a->nsplit <= 1 && ((p.acc_n / cg) % 8 == 0) && a->C0 % 64 == 0 && a->C1 % 64 == 0 &&
+                    // long reductions only (main-loop bound; short ones keep the shared memory for the TMA epilogue),
+                    // and two stages must fit next to the per-lane epilogue's staging
+                    p.nkb_total > 32 &&
+                    2 * ((p.bh + 2) * p.bw * 128 + 3 * b_stage_host) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 +
+                            GEMM_BAR_BYTES <= 227 * 1024 && (a->smem_budget <= 0 || a->smem_budget >= 227 * 1024);
+    if (ok) {
+      p.a3 = 1;
+      p.a3_box_bytes = (p.bh + 2) * p.bw * 128;
+      p.a3_iters = 3 * p.cblocks + p.cblocks_x;
+      // the main sources are fetched with the taller box; the extra 1x1 source keeps its one-tap boxes
+      uint32_t box3[5] = {64, (uint32_t)p.bw, 1, (uint32_t)(p.bh + 2), 1};
+      const uint64_t WI = (uint64_t)a->WI, HI = (uint64_t)a->HI;
+      const uint64_t c0b = (uint64_t)a->C0 * 2;
+      uint64_t dims[5] = {(uint64_t)a->C0, WI, 1, HI, (uint64_t)a->NB};
+      uint64_t str[4] = {c0b, c0b * WI, c0b * WI, c0b * WI * HI};
+      if ((rc = make_tmap_bf16(&p.map_a0, a->a0, 5, dims, str, box3, "conv A0 (filter-column box)"))) return rc;
+      if (a->C1 > 0) {
+        const uint64_t c1b = (uint64_t)a->C1 * 2;
+        uint64_t dims1[5] = {(uint64_t)a->C1, WI, 1, HI, (uint64_t)a->NB};
+        uint64_t str1[4] = {c1b, c1b * WI, c1b * WI, c1b * WI * HI};
+        if ((rc = make_tmap_bf16(&p.map_a1, a->a1, 5, dims1, str1, box3, "conv A1 (filter-column box)"))) return rc;
+      }
+    }
+  }
+
   // ---- pipeline depth from the shared-memory budget
-  const int stage_bytes = GEMM_A_STAGE_BYTES + p.n_acc * (p.acc_n / cg) * GEMM_BK * 2;
+  const int stage_bytes = p.a3 ? (p.a3_box_bytes + 3 * b_stage_host) : (GEMM_A_STAGE_BYTES + b_stage_host);
   const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
   const long long ldo_eff = a->ldo ? a->ldo : a->Cout;
   const int want_split = a->nsplit > 1;
@@ -1407,9 +1587,11 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.ldo = a->ldo ? a->ldo : a->Cout;
   p.out_fp32 = a->out_fp32;
   p.out_f16 = a->out_f16;
-  if (a->out_f16 && ((reinterpret_cast<uintptr_t>(a->out) & 7u) != 0 || a->residual != nullptr ||
-                     a->out_fp32 || a->nsplit > 1 || (a->Cout % 32) != 0 || ((a->ldo ? a->ldo : a->Cout) % 4) != 0)) {
-    set_error("sdb_gemm_tc: out_f16 needs a 16-bit output, no split-K, Cout %% 32 == 0 and ldo %% 4 == 0");
+  p.ab_f16 = a->ab_f16;
+  // out_f16: every store path (TMA epilogue, both per-lane paths, split-K finalize) writes the 16-bit tensor as IEEE
+  // half; a bf16 residual is the one combination without a path
+  if (a->out_f16 && a->residual != nullptr && !a->res_fp32) {
+    set_error("sdb_gemm_tc: out_f16 with a bf16 residual is not supported");
     return SDB_ERR_UNSUPPORTED;
   }
   p.bias = a->bias;
@@ -1497,13 +1679,13 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
       if (blocks4 > 148 * 8) blocks4 = 148 * 8;
       (void)launch_k(gemm_splitk_finalize4_kernel, dim3(blocks4), dim3(256), 0, stream, 1,
                      (const float*)p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias,
-                     reinterpret_cast<const float*>(p.residual), p.ldr, p.act, p.out2);
+                     reinterpret_cast<const float*>(p.residual), p.ldr, p.act, p.out2, p.out_f16);
       if ((rc = check_launch("gemm_splitk_finalize4_kernel"))) return rc;
       return SDB_OK;
     }
     (void)launch_k(gemm_splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, 1,
         (const float*)p.workspace, nsplit, p.m_total, p.N, p.out, p.ldo, p.out_fp32, p.bias, p.bias_mode,
-        p.residual, p.res_fp32, p.ldr, p.act, p.out2);
+        p.residual, p.res_fp32, p.ldr, p.act, p.out2, p.out_f16);
     if ((rc = check_launch("gemm_splitk_finalize_kernel"))) return rc;
   }
   return SDB_OK;

@@ -10,10 +10,10 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
 }
-__device__ __forceinline__ uint4 pack8(const float* f) {
+__device__ __forceinline__ uint4 pack8(const float* f, int f16 = 0) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack16x2(f[0], f[1], f16); u.y = pack16x2(f[2], f[3], f16);
+  u.z = pack16x2(f[4], f[5], f16); u.w = pack16x2(f[6], f[7], f16);
   return u;
 }
 
@@ -105,7 +105,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                 long long HW, int C0, int C1, int groups, float eps, int silu,
                                 long long ppc, int V, int lanes, int x0_fp32, int x1_fp32,
-                                int stat_chunks) {
+                                int stat_chunks, int out_f16) {
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
   extern __shared__ double s_stat[];     // [stat_chunks][groups][2] partial statistics of this sample
@@ -173,7 +173,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
         if (silu) y = silu_f(y);
         f[u][j] = y;
       }
-      *reinterpret_cast<uint4*>(obase + (p + (long long)u * lanes) * ctot) = pack8(f[u]);
+      *reinterpret_cast<uint4*>(obase + (p + (long long)u * lanes) * ctot) = pack8(f[u], out_f16);
     }
   }
   for (; p < p_end; p += lanes) {
@@ -185,7 +185,7 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
       if (silu) y = silu_f(y);
       f[j] = y;
     }
-    *reinterpret_cast<uint4*>(obase + p * ctot) = pack8(f);
+    *reinterpret_cast<uint4*>(obase + p * ctot) = pack8(f, out_f16);
   }
 }
 
@@ -232,13 +232,13 @@ __global__ void layernorm_kernel(const void* __restrict__ x, const float* __rest
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         y[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
-      if (out_fp32) {
+      if (out_fp32 == 1) {
         float* o = reinterpret_cast<float*>(out) + row * C + v * 8;
         *reinterpret_cast<float4*>(o) = make_float4(y[0], y[1], y[2], y[3]);
         *reinterpret_cast<float4*>(o + 4) = make_float4(y[4], y[5], y[6], y[7]);
       } else {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out) + row * C + v * 8;
-        *reinterpret_cast<uint4*>(o) = pack8(y);
+        *reinterpret_cast<uint4*>(o) = pack8(y, out_fp32 == 2);
       }
     }
   }
@@ -307,11 +307,11 @@ layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamm
           y.y = (f[r][i].y - mean) * rstd * g.y + b.y;
           y.z = (f[r][i].z - mean) * rstd * g.z + b.z;
           y.w = (f[r][i].w - mean) * rstd * g.w + b.w;
-          if (out_fp32) {
+          if (out_fp32 == 1) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * C + v * 4) = y;
           } else {
             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * C + v * 4) =
-                make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                make_uint2(pack16x2(y.x, y.y, out_fp32 == 2), pack16x2(y.z, y.w, out_fp32 == 2));
           }
         }
       }
@@ -473,6 +473,7 @@ struct GnFusedParams {
   __nv_bfloat16* out;
   int HW, C0, C1, cpg, G, SC, CS, PX, nslabs, silu;
   float eps;
+  int out_f16;
 };
 
 constexpr int GNF_THREADS = 256;
@@ -604,8 +605,8 @@ __global__ void __launch_bounds__(GNF_THREADS) gn_fused_kernel(const GnFusedPara
         for (int i = 0; i < 8; ++i) y[i] = silu_f(y[i]);
       }
       uint4 o;
-      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-      o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+      o.x = pack16x2(y[0], y[1], p.out_f16); o.y = pack16x2(y[2], y[3], p.out_f16);
+      o.z = pack16x2(y[4], y[5], p.out_f16); o.w = pack16x2(y[6], y[7], p.out_f16);
       *reinterpret_cast<uint4*>(p.out + (row0 + px) * C + cb + 8 * v) = o;
       v += db; px += da;
       if (v >= VO) { v -= VO; ++px; }
@@ -690,7 +691,7 @@ extern "C" int sdb_groupnorm_reduce_partials(const float* part0, const float* pa
 extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double* stats,
                                    const float* gamma, const float* beta, void* out, int NB,
                                    long long HW, int C0, int C1, int groups, float eps, int silu,
-                                   int x0_fp32, int x1_fp32, int stat_chunks, void* stream) {
+                                   int x0_fp32, int x1_fp32, int stat_chunks, int out_f16, void* stream) {
   using namespace sdb;
   const int ctot = C0 + C1;
   if (!x0 || !stats || !gamma || !beta || !out || NB <= 0 || HW <= 0 || groups <= 0 || groups > 64 ||
@@ -711,7 +712,7 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
   }
   cudaError_t le = launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
                             x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
-                            lanes, x0_fp32, x1_fp32, stat_chunks > 0 ? stat_chunks : chunks);
+                            lanes, x0_fp32, x1_fp32, stat_chunks > 0 ? stat_chunks : chunks, out_f16);
   if (le != cudaSuccess) { set_error("gn_apply_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_apply_kernel");
 }
@@ -727,13 +728,14 @@ extern "C" int sdb_groupnorm_fused_supported(long long HW, int C0, int C1, int g
 
 extern "C" int sdb_groupnorm_fused(const float* x0, const float* x1, const float* gamma, const float* beta,
                                    void* out, int NB, long long HW, int C0, int C1, int groups, float eps,
-                                   int silu, void* stream) {
+                                   int silu, int out_f16, void* stream) {
   using namespace sdb;
   if (!x0 || !gamma || !beta || !out || NB <= 0 || (C1 > 0 && !x1)) {
     set_error("sdb_groupnorm_fused: bad arguments");
     return SDB_ERR_ARG;
   }
   GnFusedParams p;
+  p.out_f16 = out_f16;
   size_t smem;
   if (!gn_fused_plan(HW, C0, C1, groups, &p.G, &p.CS, &p.PX, &smem)) {
     set_error("sdb_groupnorm_fused: no plan for HW=%lld C=%d+%d groups=%d", HW, C0, C1, groups);

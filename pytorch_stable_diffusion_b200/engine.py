@@ -42,27 +42,38 @@ SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 QK_OFFSET_FOLD = os.environ.get("SDB_NO_QK_FOLD") != "1"
 # GroupNorm statistics accumulated by the epilogue of the GEMM that produces the tensor (sdb_gemm_args.gn_part)
 GN_EPILOGUE_STATS = os.environ.get("SDB_NO_GN_EPI") != "1"
+# The UNet's FULL-RESOLUTION level (encoders 0-3, decoders 9-11, the output layer: everything whose tensor-core
+# operands are tensors of latent resolution) takes IEEE-half operands instead of bf16: same width, same tcgen05
+# kind::f16 rate, fp32 accumulation, but 11 instead of 8 significand bits. tools/diag_layer_budget.py measured that
+# this level carries 76 % of the squared operand-rounding error of a UNet evaluation (decoders.11 alone 30 %, the
+# output layer 11 %); with it in half the per-evaluation error against the fp32 reference drops from 7-11e-3 (over the
+# 1e-2 tolerance for some 768^2 inputs) to ~4e-3. The operands there are GroupNorm / LayerNorm outputs and 16-bit
+# shadows of the fp32 stream written with a saturating conversion; the fp32 master tensors are untouched. Every other
+# level, the attention kernels (Q, K, V, P, O), CLIP and the VAE stay bf16. SDB_NO_TOP_F16=1 restores bf16 everywhere.
+TOP_F16 = os.environ.get("SDB_NO_TOP_F16") != "1"
+BF16, F16 = torch.bfloat16, torch.float16
 
 
 # ------------------------------------------------------------------------------------------------
 # packing
-def _bf16(t, dev):
-    return t.detach().to(device=dev, dtype=torch.bfloat16).contiguous()
+def _bf16(t, dev, dtype=torch.bfloat16):
+    """Weights as a 16-bit tensor-core operand: bf16, or IEEE half for the layers of the full-resolution level."""
+    return t.detach().to(device=dev, dtype=dtype).contiguous()
 
 
 def _f32(t, dev):
     return t.detach().to(device=dev, dtype=torch.float32).contiguous()
 
 
-def pack_conv3x3(conv, dev):
+def pack_conv3x3(conv, dev, dtype=torch.bfloat16):
     w = conv.weight.detach()
     cout = w.shape[0]
-    return _bf16(w.permute(0, 2, 3, 1).reshape(cout, -1), dev), _f32(conv.bias, dev)
+    return _bf16(w.permute(0, 2, 3, 1).reshape(cout, -1), dev, dtype), _f32(conv.bias, dev)
 
 
-def pack_conv1x1(conv, dev):
+def pack_conv1x1(conv, dev, dtype=torch.bfloat16):
     w = conv.weight.detach()
-    return _bf16(w.reshape(w.shape[0], w.shape[1]), dev), _f32(conv.bias, dev)
+    return _bf16(w.reshape(w.shape[0], w.shape[1]), dev, dtype), _f32(conv.bias, dev)
 
 
 def pack_direct(conv, dev):
@@ -85,21 +96,23 @@ def fingerprint(module):
     return tuple((p.data_ptr(), p._version, p.device.index if p.is_cuda else -1) for p in module.parameters())
 
 
-def pack_resblock(m, dev, time=True):
-    """UNET_ResidualBlock (sd/diffusion.py:111-143) or VAE_ResidualBlock (sd/decoder.py:103-133)."""
+def pack_resblock(m, dev, time=True, dt=torch.bfloat16):
+    """UNET_ResidualBlock (sd/diffusion.py:111-143) or VAE_ResidualBlock (sd/decoder.py:103-133). dt: 16-bit operand
+    type of the block's convolutions (weights here, activations in run_resblock)."""
     if time:
         gn1, conv1, gn2, conv2 = m.groupnorm_feature, m.conv_feature, m.groupnorm_merged, m.conv_merged
     else:
         gn1, conv1, gn2, conv2 = m.groupnorm_1, m.conv_1, m.groupnorm_2, m.conv_2
     pk = NS()
+    pk.dt = dt
     pk.gn1_w, pk.gn1_b = pack_norm(gn1, dev)
-    pk.conv1_w, pk.conv1_b = pack_conv3x3(conv1, dev)
+    pk.conv1_w, pk.conv1_b = pack_conv3x3(conv1, dev, dt)
     pk.gn2_w, pk.gn2_b = pack_norm(gn2, dev)
-    pk.conv2_w, pk.conv2_b = pack_conv3x3(conv2, dev)
+    pk.conv2_w, pk.conv2_b = pack_conv3x3(conv2, dev, dt)
     pk.cin, pk.cout = conv1.in_channels, conv1.out_channels
     pk.conv2x_w = None
     if isinstance(m.residual_layer, torch.nn.Conv2d):
-        pk.skip_w, pk.skip_b = pack_conv1x1(m.residual_layer, dev)
+        pk.skip_w, pk.skip_b = pack_conv1x1(m.residual_layer, dev, dt)
         # the 1x1 skip convolution as extra k-blocks of conv_merged: its weights behind the 9 * Cout columns of the
         # 3x3 filter, the two biases added - one GEMM, no fp32 round trip of the skip branch (FUSE_SKIP_CONV)
         if FUSE_SKIP_CONV and pk.cin % 64 == 0 and pk.cout % 64 == 0:
@@ -113,13 +126,16 @@ def pack_resblock(m, dev, time=True):
     return pk
 
 
-def pack_unet_attn(m, dev):
-    """UNET_AttentionBlock (sd/diffusion.py:243-269)."""
+def pack_unet_attn(m, dev, dt=torch.bfloat16):
+    """UNET_AttentionBlock (sd/diffusion.py:243-269). dt: 16-bit operand type of conv_input and of the feed-forward /
+    conv_output GEMMs (the block's error-relevant operators, tools/diag_layer_budget.py); the projections around the
+    two attention kernels stay bf16 like the kernels themselves."""
     pk = NS()
+    pk.dt = dt
     c = m.conv_input.in_channels
     pk.c, pk.heads = c, m.attention_1.n_heads
     pk.gn_w, pk.gn_b = pack_norm(m.groupnorm, dev)
-    pk.cin_w, pk.cin_b = pack_conv1x1(m.conv_input, dev)
+    pk.cin_w, pk.cin_b = pack_conv1x1(m.conv_input, dev, dt)
     pk.ln1 = pack_norm(m.layernorm_1, dev)
     w = m.attention_1.in_proj.weight.detach()
     pk.wqk = _bf16(w[:2 * c], dev)
@@ -185,7 +201,7 @@ def pack_unet_attn(m, dev):
         b2 = m.linear_geglu_2.bias.detach().to(device=dev, dtype=torch.float64)
         w21 = ops.matmul_f64(w2, w1)                                        # [C, C] fp64
         b21 = ops.matmul_f64(w2, b1.view(-1, 1)).view(-1) + b2              # [C] fp64
-        pk.wg = w21.to(torch.bfloat16).contiguous()
+        pk.wg = w21.to(dt).contiguous()
         pk.bg = b21.to(torch.float32).contiguous()
         pk.wg1 = None
         pk.w_ffout = None
@@ -196,13 +212,13 @@ def pack_unet_attn(m, dev):
             # two GEMMs with a bf16 round trip of t3 in between (sd/diffusion.py:355-381)
             wo = _f32(m.conv_output.weight.detach().reshape(c, c), dev)
             bo = m.conv_output.bias.detach().to(device=dev, dtype=torch.float64)
-            pk.w_ffout = torch.cat([ops.matmul_f64(wo, w21), wo.to(torch.float64)], dim=1).to(torch.bfloat16).contiguous()
+            pk.w_ffout = torch.cat([ops.matmul_f64(wo, w21), wo.to(torch.float64)], dim=1).to(dt).contiguous()
             pk.b_ffout = (ops.matmul_f64(wo, b21.view(-1, 1).contiguous()).view(-1) + bo).to(torch.float32).contiguous()
     else:
-        pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev)
+        pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev, dt)
         pk.bg1 = _f32(m.linear_geglu_1.bias[:4 * c], dev)
-        pk.wg2, pk.bg2 = pack_linear(m.linear_geglu_2, dev)
-    pk.cout_w, pk.cout_b = pack_conv1x1(m.conv_output, dev)
+        pk.wg2, pk.bg2 = _bf16(m.linear_geglu_2.weight, dev, dt), _f32(m.linear_geglu_2.bias, dev)
+    pk.cout_w, pk.cout_b = pack_conv1x1(m.conv_output, dev, dt)
     return pk
 
 
@@ -242,10 +258,15 @@ class Stream:
     def shape(self):
         return self.f.shape
 
-    def bf16(self):
-        if self.b is None:
-            self.b = ops.f32_to_bf16(self.f)
+    def b16(self, dtype=torch.bfloat16):
+        """The 16-bit shadow in the operand type the consumer wants (converted from the fp32 master when the producer
+        did not write one, or wrote the other type)."""
+        if self.b is None or self.b.dtype != dtype:
+            self.b = ops.f32_to_bf16(self.f, dtype)
         return self.b
+
+    def bf16(self):
+        return self.b16(torch.bfloat16)
 
 
 def _stream(out, shape):
@@ -267,13 +288,15 @@ def _gn_samples(n, hw, c):
 
 # ------------------------------------------------------------------------------------------------
 # block runners (Stream in / Stream out)
-def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
+def run_resblock(pk, x, x1=None, bias1=None, want_b16=False, out16=torch.bfloat16):
     """conv2(silu(GN(conv1(silu(GN(x ++ x1))) + t))) + skip(x ++ x1).  bias1 = conv1 bias (+ time).
-    UNET_ResidualBlock (sd/diffusion.py:145-209) / VAE_ResidualBlock (sd/decoder.py:135-189)."""
+    UNET_ResidualBlock (sd/diffusion.py:145-209) / VAE_ResidualBlock (sd/decoder.py:135-189). pk.dt = 16-bit type of
+    this block's operands, out16 = type of the output's 16-bit shadow (what its consumer reads)."""
     n, h, w, c0 = x.shape
     c1 = x1.shape[-1] if x1 is not None else 0
+    dt = pk.dt
     a = ops.groupnorm(x.f, pk.gn1_w, pk.gn1_b, x1=x1.f if x1 is not None else None, silu=True,
-                      part0=x.gp, part1=x1.gp if x1 is not None else None)
+                      part0=x.gp, part1=x1.gp if x1 is not None else None, out_dtype=dt)
     gs = _gn_samples(n, h * w, pk.cout)
     # the hidden tensor stays fp32: it is only ever read by GroupNorm, never as a tensor-core operand
     hid = ops.conv3x3(a, pk.conv1_w, pk.cout, bias=bias1 if bias1 is not None else pk.conv1_b,
@@ -281,21 +304,21 @@ def run_resblock(pk, x, x1=None, bias1=None, want_b16=False):
     hid_gp = None
     if gs is not None:
         hid, _, hid_gp = hid
-    a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True, part0=hid_gp)
+    a2 = ops.groupnorm(hid, pk.gn2_w, pk.gn2_b, silu=True, part0=hid_gp, out_dtype=dt)
     if pk.conv2x_w is not None and c0 % 64 == 0 and c1 % 64 == 0:
         out = ops.conv3x3(a2, pk.conv2x_w, pk.cout, bias=pk.conv2x_b, out_fp32=True, out2=True if want_b16 else None,
-                          gn_samples=gs, ax0=x.bf16(), ax1=x1.bf16() if x1 is not None else None)
+                          gn_samples=gs, ax0=x.b16(dt), ax1=x1.b16(dt) if x1 is not None else None, out16=out16)
         if isinstance(out, tuple):
             return Stream(*out)
         return Stream(out)
     if pk.skip_w is None:
         res = x.f.view(-1, c0)
     else:
-        res = ops.gemm(x.bf16().view(-1, c0), pk.skip_w, pk.cout,
-                       a1=x1.bf16().view(-1, c1) if x1 is not None else None,
+        res = ops.gemm(x.b16(dt).view(-1, c0), pk.skip_w, pk.cout,
+                       a1=x1.b16(dt).view(-1, c1) if x1 is not None else None,
                        M=n * h * w, c0=c0, c1=c1, bias=pk.skip_b, out_fp32=True)
     out = ops.conv3x3(a2, pk.conv2_w, pk.cout, bias=pk.conv2_b, residual=res, out_fp32=True,
-                      out2=True if want_b16 else None, gn_samples=gs)
+                      out2=True if want_b16 else None, gn_samples=gs, out16=out16)
     if isinstance(out, tuple):
         return Stream(*out)
     return Stream(out)
@@ -326,14 +349,15 @@ def context_kv(pk, ctx_pad):
     return k, vt
 
 
-def run_unet_attn(pk, x, kv, want_b16=False):
+def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
     """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is fp32."""
+    dt = pk.dt
     n, h, w, c = x.shape
     s = h * w
     m = n * s
     d = c // pk.heads
     dev = x.f.device
-    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp)
+    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp, out_dtype=dt)
     t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=True)
     # self-attention
     l1 = ops.layernorm(t0, *pk.ln1)
@@ -354,22 +378,22 @@ def run_unet_attn(pk, x, kv, want_b16=False):
     ops.attention(q, k2, vt2, o2, NB=n, heads=pk.heads, d=d, S=s, Skv=77, Skv_pad=CTX_PAD,
                   ldq=c, ldk=c, ldo=c)
     ff_out = pk.wg1 is None and pk.w_ffout is not None
-    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True, out2=True if ff_out else None)
+    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True, out2=True if ff_out else None, out16=dt)
     # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
     if ff_out:
         t2, t2_b = t2
-        l3 = ops.layernorm(t2, *pk.ln3)
+        l3 = ops.layernorm(t2, *pk.ln3, out_dtype=dt)
         out = ops.gemm(l3, pk.w_ffout, c, a1=t2_b, M=m, c0=c, c1=c, bias=pk.b_ffout, residual=x.f.view(m, c),
-                       out_fp32=True, out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c))
+                       out_fp32=True, out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c), out16=out16)
         return _stream(out, (n, h, w, c))
-    l3 = ops.layernorm(t2, *pk.ln3)
+    l3 = ops.layernorm(t2, *pk.ln3, out_dtype=dt)
     if pk.wg1 is None:
-        t3 = ops.linear(l3, pk.wg, bias=pk.bg, residual=t2)       # folded affine map; only conv_output reads it: bf16
+        t3 = ops.linear(l3, pk.wg, bias=pk.bg, residual=t2, out16=dt)   # folded affine map; only conv_output reads it
     else:
-        g = ops.linear(l3, pk.wg1, bias=pk.bg1)
-        t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2)
+        g = ops.linear(l3, pk.wg1, bias=pk.bg1, out16=dt)
+        t3 = ops.linear(g, pk.wg2, bias=pk.bg2, residual=t2, out16=dt)
     out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=x.f.view(m, c), out_fp32=True,
-                     out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c))
+                     out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c), out16=out16)
     return _stream(out, (n, h, w, c))
 
 
@@ -432,40 +456,50 @@ class UNetEngine:
         self.t2_w, self.t2_b = pack_linear(te.linear_2, dev)
         self.res_blocks = []
 
-        def pack_seq(seq):
+        def pack_seq(seq, top=False, out_top=None):
+            """Program of one SwitchSequential: entries [kind, packed, want_b16, out16]. top: the block's 16-bit
+            operands are tensors of the full-resolution level (IEEE half when TOP_F16); out_top: so is its OUTPUT
+            (differs for the down-sampling conv of encoders.3 and the Upsample conv that ends decoders.8)."""
+            if out_top is None:
+                out_top = top
+            dt = F16 if (top and TOP_F16) else BF16
+            dt_out = F16 if (out_top and TOP_F16) else BF16
             prog = []
             for layer in seq:
                 if isinstance(layer, UNET_ResidualBlock):
-                    pk = pack_resblock(layer, dev, time=True)
+                    pk = pack_resblock(layer, dev, time=True, dt=dt)
                     self.res_blocks.append(pk)
-                    prog.append(["res", pk, False])
+                    prog.append(["res", pk, False, dt])
                 elif isinstance(layer, UNET_AttentionBlock):
-                    prog.append(["attn", pack_unet_attn(layer, dev), False])
+                    prog.append(["attn", pack_unet_attn(layer, dev, dt), False, dt])
                 elif isinstance(layer, Upsample):
-                    w, b = pack_conv3x3(layer.conv, dev)
-                    prog.append(["up", NS(w=w, b=b, cout=layer.conv.out_channels), False])
+                    # nearest x2 of the block's (lower-level) output, then a conv whose OUTPUT is one level up
+                    w, b = pack_conv3x3(layer.conv, dev, dt)
+                    prog.append(["up", NS(w=w, b=b, cout=layer.conv.out_channels, dt=dt), False, dt_out])
                 elif isinstance(layer, torch.nn.Conv2d):
                     if layer.in_channels <= 8:
-                        prog.append(["direct", pack_direct(layer, dev), False])
+                        prog.append(["direct", pack_direct(layer, dev), False, dt_out])
                     else:
-                        w, b = pack_conv3x3(layer, dev)
+                        w, b = pack_conv3x3(layer, dev, dt)
                         kind = ops.GEMM_CONV3X3_S2 if layer.stride[0] == 2 else ops.GEMM_CONV3X3_S1
-                        prog.append(["conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind), False])
+                        prog.append(["conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind, dt=dt), False, dt_out])
                 else:
                     raise TypeError(f"unexpected layer {type(layer)}")
             return prog
 
         u = diffusion.unet
-        self.encoders = [pack_seq(s) for s in u.encoders]
+        # full-resolution level: encoders 0-2 and decoders 9-11 entirely; encoders.3 (stride-2 conv) reads it and
+        # writes the next level; the Upsample conv closing decoders.8 reads the lower level and writes it
+        self.encoders = [pack_seq(s, top=i <= 3, out_top=i <= 2) for i, s in enumerate(u.encoders)]
         self.bottleneck = pack_seq(u.bottleneck)
-        self.decoders = [pack_seq(s) for s in u.decoders]
+        self.decoders = [pack_seq(s, top=i >= 9, out_top=i >= 8) for i, s in enumerate(u.decoders)]
         # third field of every entry: does a later tensor-core kernel read this output directly?
         flat = [e for prog in self.encoders + [self.bottleneck] + self.decoders for e in prog]
         for cur, nxt in zip(flat, flat[1:]):
             cur[2] = _reads_bf16(nxt[0], nxt[1])
         for prog in self.encoders:        # skips feed the decoders' 1x1 skip convs (sd/diffusion.py:671)
             prog[-1][2] = True
-        self.attn_blocks = [pk for kind, pk, _ in flat if kind == "attn"]
+        self.attn_blocks = [pk for kind, pk, _, _ in flat if kind == "attn"]
         # all linear_time projections as one [sum(Cout), 1280] matrix
         offs, off = [], 0
         for pk in self.res_blocks:
@@ -478,8 +512,9 @@ class UNetEngine:
             pk.time_off = o
             pk.time_w = None
         fin = diffusion.final
+        self.fin_dt = F16 if TOP_F16 else BF16
         self.fin_gn = pack_norm(fin.groupnorm, dev)
-        self.fin_w, self.fin_b = pack_conv3x3(fin.conv, dev)
+        self.fin_w, self.fin_b = pack_conv3x3(fin.conv, dev, self.fin_dt)
         self.fin_cout = fin.conv.out_channels
 
     def time_vectors(self, time):
@@ -497,26 +532,27 @@ class UNetEngine:
         return [context_kv(pk, ctx) for pk in self.attn_blocks]
 
     def _run_seq(self, prog, x, x1, tvec, kv_iter):
-        for kind, pk, want in prog:
+        for kind, pk, want, o16 in prog:
             if kind == "res":
-                x = run_resblock(pk, x, x1, tvec[pk.time_off:pk.time_off + pk.cout], want_b16=want)
+                x = run_resblock(pk, x, x1, tvec[pk.time_off:pk.time_off + pk.cout], want_b16=want, out16=o16)
                 x1 = None
             elif kind == "attn":
-                x = run_unet_attn(pk, x, next(kv_iter), want_b16=want)
+                x = run_unet_attn(pk, x, next(kv_iter), want_b16=want, out16=o16)
             elif kind == "up":
                 nn_, hh_, ww_, _ = x.shape
-                o = ops.conv3x3(ops.upsample2x(x.bf16()), pk.w, pk.cout, bias=pk.b, out_fp32=True,
-                                out2=True if want else None, gn_samples=_gn_samples(nn_, 4 * hh_ * ww_, pk.cout))
+                o = ops.conv3x3(ops.upsample2x(x.b16(pk.dt)), pk.w, pk.cout, bias=pk.b, out_fp32=True,
+                                out2=True if want else None, gn_samples=_gn_samples(nn_, 4 * hh_ * ww_, pk.cout),
+                                out16=o16)
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "conv":
                 nn_, hh_, ww_, _ = x.shape
                 s2_ = pk.kind != ops.GEMM_CONV3X3_S1
-                o = ops.conv3x3(x.bf16(), pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True,
+                o = ops.conv3x3(x.b16(pk.dt), pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True,
                                 out2=True if want else None,
-                                gn_samples=_gn_samples(nn_, (hh_ * ww_) // (4 if s2_ else 1), pk.cout))
+                                gn_samples=_gn_samples(nn_, (hh_ * ww_) // (4 if s2_ else 1), pk.cout), out16=o16)
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "direct":
-                o = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=want)
+                o = ops.conv_direct(x, pk.w, pk.b, pk.cout, pk.k, out_fp32=True, out2=want, out2_dtype=o16)
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
         return x
 
@@ -531,7 +567,7 @@ class UNetEngine:
         x = self._run_seq(self.bottleneck, x, None, tvec, kv_iter)
         for prog in self.decoders:
             x = self._run_seq(prog, x, skips.pop(), tvec, kv_iter)
-        a = ops.groupnorm(x.f, *self.fin_gn, silu=True, part0=x.gp)
+        a = ops.groupnorm(x.f, *self.fin_gn, silu=True, part0=x.gp, out_dtype=self.fin_dt)
         return ops.conv3x3(a, self.fin_w, self.fin_cout, bias=self.fin_b, out_fp32=True)
 
 

@@ -76,9 +76,10 @@ def _chk(t, dtype, name):
 
 import os as _os
 _NO_WIDE = _os.environ.get("SDB_NO_WIDE") == "1"     # A/B switch: never pick the wide (320-column) tiles
+_A3_CHOOSER = _os.environ.get("SDB_A3_CHOOSER") != "0"   # A/B switch: the tile chooser ignores filter-column staging
 
 
-def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
+def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0, a3_bytes=0):
     """(block_n, nsplit) from a per-SM cycle model of gemm_tc_kernel, calibrated on B200 timelines
     (tools/gemm_trace.py, tools/micro/mma_rate.cu):
 
@@ -89,6 +90,9 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
         pipeline refill at every tile start; wide tiles (block_n = 320: two 160-column accumulators sharing
         the A tile, one buffer) are MMA-bound but their epilogue is exposed;
       * an epilogue moves its bytes at ~20 B/clk per SM (HBM share).
+
+      * a3_bytes > 0: the conv runs with filter-column staging when it is not split (sdb_gemm_conv_a3_bytes): a
+        k-block then moves a3_bytes / 3 of A instead of 16 KiB.
 
     Tiles are 256 rows (CTA pairs, 74 slots on a 148-SM part) or 128 rows when there is one row tile."""
     m_tiles = (rows + 127) // 128
@@ -120,7 +124,8 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
             if bn == 320:
                 tile = per * 8 * 88.0 + 1500.0 + epi
             else:
-                tma = (16384.0 + (bn // cg) * 128.0) / 63.0
+                a_kb = a3_bytes / 3.0 if (a3_bytes and ns == 1 and nkb > 32) else 16384.0
+                tma = (a_kb + (bn // cg) * 128.0) / 63.0
                 mma = 4.0 * max(88.0, bn / 2.0)
                 tile = max(per * max(tma, mma) + 3000.0, epi)
             cost = rounds * tile
@@ -134,16 +139,28 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0):
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
          lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0,
-         gn_samples=None, ax0=None, ax1=None):
+         gn_samples=None, ax0=None, ax1=None, out16=None):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h.
 
     gn_samples=N: the output is a GroupNorm input of N samples - the epilogue also writes per-slab, per-channel
     partial statistics and the call returns (out, out2 or None, part or None); part is None when the geometry or
-    the tiling (split-K) cannot provide them and the consumer has to run its own statistics pass."""
+    the tiling (split-K) cannot provide them and the consumer has to run its own statistics pass.
+
+    The 16-bit operands (a0, a1, ax0, ax1, w) are all bf16 or all IEEE half (sdb_gemm_args::ab_f16 follows a0's
+    dtype). out16 = torch.bfloat16 | torch.float16: type of the 16-bit tensor written (`out`, or `out2` next to an
+    fp32 `out`); default bf16."""
     lib = _ext.lib()
-    _chk(a0, torch.bfloat16, "a0")
-    _chk(w, torch.bfloat16, "w")
+    op16 = a0.dtype if a0.dtype == torch.float16 else torch.bfloat16
+    _chk(a0, op16, "a0")
+    _chk(w, op16, "w")
+    for t_, nm_ in ((a1, "a1"), (ax0, "ax0"), (ax1, "ax1")):
+        if t_ is not None:
+            _chk(t_, op16, nm_)
+    if out16 is None:
+        out16 = torch.float16 if out_f16 else torch.bfloat16
+    out_f16 = out16 == torch.float16
     args = GemmArgs()
+    args.ab_f16 = 1 if op16 == torch.float16 else 0
     args.kind = kind
     args.a0, args.a1, args.w = _p(a0), _p(a1), _p(w)
     args.bias = _p(_chk(bias, torch.float32, "bias")) if bias is not None else None
@@ -174,14 +191,11 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.C0, args.C1, args.Cout = c0, c1, cout
     args.lda0, args.lda1, args.ldw, args.ldo, args.ldr = lda0, lda1, ldw, ldo, ldr
     if out is None:
-        out = torch.empty((rows, cout), device=a0.device,
-                          dtype=torch.float32 if out_fp32 else (torch.float16 if out_f16 else torch.bfloat16))
-    if out_f16:
-        nsplit = 1
+        out = torch.empty((rows, cout), device=a0.device, dtype=torch.float32 if out_fp32 else out16)
     args.out = _p(out)
     args.out_fp32 = 1 if out_fp32 else 0
     if out2 is True:
-        out2 = torch.empty(out.shape, device=out.device, dtype=torch.bfloat16)
+        out2 = torch.empty(out.shape, device=out.device, dtype=out16)
     args.out2 = _p(out2)
     args.bias_per_row = 1 if bias_per_row else 0
     args.act = act
@@ -190,13 +204,14 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     if ax0 is not None:        # extra 1x1 source (resblock skip conv) accumulated behind the nine taps
         cx0 = ax0.shape[-1]
         cx1 = ax1.shape[-1] if ax1 is not None else 0
-        args.ax0, args.ax1 = _p(_chk(ax0, torch.bfloat16, "ax0")), _p(ax1)
+        args.ax0, args.ax1 = _p(ax0), _p(ax1)
         args.Cx0, args.Cx1 = cx0, cx1
         nkb += (cx0 + cx1) // 64
     if block_n == 0 or nsplit == 0:
         ob = (4 if out_fp32 else 2) + (2 if out2 is not None else 0)
         rb = 0 if residual is None else residual.element_size()
-        bn_auto, ns_auto = _choose_tiling(rows, cout, nkb, ob, rb)
+        a3b = lib.sdb_gemm_conv_a3_bytes(*conv_dims) if (kind == GEMM_CONV3X3_S1 and _A3_CHOOSER) else 0
+        bn_auto, ns_auto = _choose_tiling(rows, cout, nkb, ob, rb, a3b)
         if block_n == 0:
             block_n = bn_auto
             if nsplit == 0:
@@ -229,7 +244,8 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         res_b = residual.element_size() if residual is not None else 0
         shape = (f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps} cx={cx0 + cx1} "
                  f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={('f32', 'bf16')[res_b == 2] if res_b else 'none'} "
-                 f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit}")
+                 f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit} "
+                 f"ab={'f16' if op16 == torch.float16 else 'bf16'}")
         keep = (a0, a1, w, bias, residual, out, out2, ws, part, ax0, ax1)     # the relaunch closure owns its operands
         ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear",
                    2.0 * rows * cout * k_total,
@@ -298,10 +314,12 @@ _NO_GN_FUSED = _os.environ.get("SDB_NO_GN_FUSED") == "1"     # A/B switch: alway
 _NO_GN_EPI = _os.environ.get("SDB_NO_GN_EPI") == "1"         # A/B switch: ignore epilogue partial statistics
 
 
-def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fused=None, part0=None, part1=None):
-    """GroupNorm (+SiLU) over NHWC x0 ++ x1 (channel concat; each bf16 or fp32); returns bf16
-    [N, H, W, C0+C1]. fp32 inputs whose (sample, group slab) fits a cluster's shared memory take the
+def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fused=None, part0=None, part1=None,
+              out_dtype=torch.bfloat16):
+    """GroupNorm (+SiLU) over NHWC x0 ++ x1 (channel concat; each bf16 or fp32); returns bf16 (or IEEE half:
+    out_dtype) [N, H, W, C0+C1]. fp32 inputs whose (sample, group slab) fits a cluster's shared memory take the
     one-pass kernel (fused=None: when supported; True: required; False: never)."""
+    o16 = 1 if out_dtype == torch.float16 else 0
     lib = _ext.lib()
     f0 = 1 if x0.dtype == torch.float32 else 0
     f1 = 1 if (x1 is not None and x1.dtype == torch.float32) else 0
@@ -312,7 +330,7 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     if fused is None:
         fused = (not _NO_GN_FUSED) and f0 == 1 and (x1 is None or f1 == 1) and \
             lib.sdb_groupnorm_fused_supported(hw, c0, c1, groups) == 2
-    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=torch.bfloat16)
+    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=out_dtype)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
     if fused:
@@ -320,7 +338,7 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
 
         def launch():
             _ext.check(lib.sdb_groupnorm_fused(_p(x0), _p(x1), _p(gamma), _p(beta), _p(out), n, hw, c0, c1, groups,
-                                               float(eps), 1 if silu else 0, _stream()), "sdb_groupnorm_fused")
+                                               float(eps), 1 if silu else 0, o16, _stream()), "sdb_groupnorm_fused")
         passes, form = 1.0, "one-pass"
     else:
         stats = torch.empty((lib.sdb_groupnorm_stats_bytes(n, groups) // 8,), device=x0.device, dtype=torch.float64)
@@ -337,7 +355,7 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
                            "sdb_groupnorm_stats")
             _ext.check(lib.sdb_groupnorm_apply(_p(x0), _p(x1), _p(stats), _p(gamma), _p(beta), _p(out), n, hw,
                                                c0, c1, groups, float(eps), 1 if silu else 0, f0, f1,
-                                               1 if have_parts else 0, _stream()), "sdb_groupnorm_apply")
+                                               1 if have_parts else 0, o16, _stream()), "sdb_groupnorm_apply")
         passes, form = (1.0, "epilogue-stats+apply") if have_parts else (2.0, "stats+apply")
     ev = _prof("groupnorm", 0.0, passes * in_bytes + 2.0 * (nel0 + nel1),
                shape=f"n={n} hw={hw} c0={c0} c1={c1} in={'f32' if f0 else 'bf16'} silu={int(silu)} {form}",
@@ -347,15 +365,16 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False):
+def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False, out_dtype=torch.bfloat16):
     lib = _ext.lib()
     c = x.shape[-1]
     rows = x.numel() // c
-    out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else out_dtype)
+    kind = 1 if out_fp32 else (2 if out_dtype == torch.float16 else 0)
 
     def launch():
         _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
-                                     1 if x.dtype == torch.float32 else 0, 1 if out_fp32 else 0, _stream()),
+                                     1 if x.dtype == torch.float32 else 0, kind, _stream()),
                    "sdb_layernorm")
     ev = _prof("layernorm", 0.0, x.numel() * x.element_size() + out.numel() * out.element_size(),
                shape=f"rows={rows} c={c} in={'f32' if x.dtype == torch.float32 else 'bf16'} "
@@ -403,21 +422,22 @@ def nhwc_to_nchw_f32(x):
 def upsample2x(x):
     lib = _ext.lib()
     n, h, w, c = x.shape
-    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)     # any 16-bit type: a pure copy
     _ext.check(lib.sdb_upsample2x_nhwc(_p(x), _p(out), n, h, w, c, _stream()), "sdb_upsample2x_nhwc")
     return out
 
 
-def conv_direct(x, w, bias, cout, ksize, out_fp32=False, out2=False):
+def conv_direct(x, w, bias, cout, ksize, out_fp32=False, out2=False, out2_dtype=torch.bfloat16):
     """x NHWC (bf16 or fp32) with Cin <= 8; w fp32 [Cout, k*k, Cin]. out2=True also returns a bf16 copy
     of an fp32 output."""
     lib = _ext.lib()
     n, h, wd, cin = x.shape
     out = torch.empty((n, h, wd, cout), device=x.device,
                       dtype=torch.float32 if out_fp32 else torch.bfloat16)
-    o2 = torch.empty((n, h, wd, cout), device=x.device, dtype=torch.bfloat16) if out2 else None
+    o2 = torch.empty((n, h, wd, cout), device=x.device, dtype=out2_dtype) if out2 else None
     _ext.check(lib.sdb_conv_direct(_p(x), _p(w), _p(bias), _p(out), _p(o2), n, h, wd, cin, cout, ksize,
-                                   1 if out_fp32 else 0, 1 if x.dtype == torch.float32 else 0, _stream()),
+                                   1 if out_fp32 else 0, 1 if x.dtype == torch.float32 else 0,
+                                   1 if out2_dtype == torch.float16 else 0, _stream()),
                "sdb_conv_direct")
     return (out, o2) if out2 else out
 
@@ -465,11 +485,13 @@ def zeros(shape, dtype, device):
     return out
 
 
-def f32_to_bf16(x):
+def f32_to_bf16(x, dtype=torch.bfloat16):
+    """fp32 -> 16-bit shadow (bf16, or IEEE half with dtype=torch.float16)."""
     lib = _ext.lib()
     _chk(x, torch.float32, "x")
-    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _ext.check(lib.sdb_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "sdb_f32_to_bf16")
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    _ext.check(lib.sdb_f32_to_bf16(_p(x.contiguous()), _p(out), x.numel(), 1 if dtype == torch.float16 else 0, _stream()),
+               "sdb_f32_to_bf16")
     return out
 
 

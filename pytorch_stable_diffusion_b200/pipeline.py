@@ -202,14 +202,18 @@ def generate(
         latents_shape = (B, 4, lh, lw)
 
         # ---- initial latents (sd/pipeline.py:149-196)
-        if input_image:
+        has_image = input_image is not None and not (isinstance(input_image, (list, tuple)) and not input_image)
+        if has_image:
             encoder = models["encoder"]
             encoder.to(device)
-            img = np.array(input_image.resize((W, H)))
-            img_u8 = torch.tensor(img, dtype=torch.uint8, device=device).unsqueeze(0)
-            x = ops.uint8_to_image(img_u8.contiguous(), out_fp32=True)   # fp32 NHWC in [-1, 1]
-            if B > 1:
+            # resize (Pillow's bicubic resampler, byte-exact) + rescale to [-1, 1] on the device; one image for the
+            # whole batch, or a list with one image per sample
+            from . import imageio
+            _, x = imageio.load_images(input_image, W, H, device)          # fp32 NHWC in [-1, 1]
+            if x.shape[0] == 1 and B > 1:
                 x = x.expand(B, -1, -1, -1).contiguous()
+            elif x.shape[0] != B:
+                raise ValueError("a list-valued input_image must have batch_size entries")
             enc_noise = noise["encoder"].to(device) if noise is not None else _draw(
                 latents_shape, generator, sample_gens, device)
             latents = encoder._engine().forward_from_nhwc(x, enc_noise.to(torch.float32).contiguous())
@@ -255,7 +259,7 @@ def generate(
             # is the packed bf16 engines and the captured loop, which would otherwise keep everything resident.
             # The next call repacks and re-captures.
             drop_cached_graphs(diffusion.__dict__.get("_sdb_engine", (None, None))[1])
-            for m in (clip, diffusion, decoder) + ((models["encoder"],) if input_image else ()):
+            for m in (clip, diffusion, decoder) + ((models["encoder"],) if has_image else ()):
                 m.invalidate_packed()
             diffusion.__dict__.pop("_sdb_ctx", None)
         to_idle(diffusion)

@@ -5,6 +5,8 @@ Tolerances: GEMM/conv/attention outputs are bf16 with fp32 accumulation -> 1e-2 
 """
 import math
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -765,3 +767,144 @@ def test_matmul_f64_pack_time_composition():
         ref = a.double() @ b.double()
         assert got.dtype == torch.float64 and got.shape == (m, n)
         assert float((got - ref).abs().max() / ref.abs().max()) < 1e-13
+
+
+@pytest.mark.parametrize("N,H,W,C0,C1,Cout,block_n,pair", [
+    (1, 16, 16, 320, 0, 160, 0, 0),       # two row tiles -> one CTA pair
+    (1, 16, 16, 320, 0, 160, 0, 1),       # the same through single-CTA tiles
+    (1, 8, 16, 512, 0, 128, 0, 0),        # ONE row tile (bw = 16, bh = 8): cta_group::1
+    (2, 32, 32, 320, 0, 320, 160, 0),
+    (2, 32, 32, 320, 0, 320, 320, 0),     # wide tile: two accumulators share the halo box
+    (1, 48, 48, 256, 64, 320, 0, 0),      # ragged: 48 = 3 patches of 16 columns, dual source
+    (1, 96, 32, 320, 0, 64, 0, 0),        # H != W
+    (3, 16, 16, 640, 640, 640, 0, 0),     # odd batch, dual source
+    (1, 64, 64, 384, 0, 96, 0, 0),        # block_n = 96
+])
+def test_conv3x3_filter_column_staging(N, H, W, C0, C1, Cout, block_n, pair):
+    """Filter-column staging (GemmTcParams::a3): one halo box per filter column, the three taps of the column read it
+    as row-shifted views. Eligible shapes (patch of one sample, > 32 k-blocks, no split-K) against F.conv2d, with a
+    residual, the bf16 copy and the GroupNorm partial sums in the same launch."""
+    ops = _ops()
+    setup_exact_fp32()
+    from pytorch_stable_diffusion_b200 import _ext
+    assert _ext.lib().sdb_gemm_conv_a3_bytes(N, H, W) > 0 and 9 * (C0 + C1) // 64 > 32
+    x0 = rnd(N, H, W, C0).bfloat16()
+    x1 = rnd(N, H, W, C1, seed=5).bfloat16() if C1 else None
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).bfloat16()
+    b = rnd(Cout, seed=2)
+    r = rnd(N * H * W, Cout, seed=3)
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout) + r
+    out, out2, part = ops.gemm(x0, pack3x3(w), Cout, kind=ops.GEMM_CONV3X3_S1, a1=x1, bias=b, residual=r,
+                               conv_dims=(N, H, W), c0=C0, c1=C1, out_fp32=True, out2=True, block_n=block_n, nsplit=1,
+                               cta_pair=pair, gn_samples=N)
+    report(f"conv3x3 filter-column {C0 + C1}->{Cout}@{H}x{W} bn={block_n} pair={pair}", out, ref, 3e-3)
+    assert torch.equal(out2, out.bfloat16())
+    if part is not None:
+        _check_partials(part, out, N, "conv3x3 filter-column")
+
+
+# ------------------------------------------------------------------------------------ IEEE-half operands
+@pytest.mark.parametrize("M,K,N,nsplit", [(4096, 320, 320, 1), (8192, 320, 640, 1), (1024, 2560, 320, 4), (300, 128, 96, 1)])
+def test_linear_f16_operands(M, K, N, nsplit):
+    """sdb_gemm_args::ab_f16: A and W in IEEE half (the UNet's full-resolution level), fp32 accumulation, fp32 result
+    + half shadow, fp32 residual - through the TMA epilogue (short K), the per-lane one and split-K."""
+    ops = _ops()
+    setup_exact_fp32()
+    a = rnd(M, K).half()
+    w = rnd(N, K, scale=K ** -0.5, seed=1).half()
+    b = rnd(N, seed=2)
+    r = rnd(M, N, seed=3)
+    ref = a.float() @ w.float().t() + b + r
+    out, out2 = ops.linear(a, w, bias=b, residual=r, out_fp32=True, out2=True, out16=torch.float16, nsplit=nsplit)
+    report(f"linear f16 operands {M}x{K}x{N} split={nsplit}", out, ref, 1e-3)
+    assert out2.dtype == torch.float16 and torch.equal(out2, out.half())
+    o16 = ops.linear(a, w, bias=b, out16=torch.float16, nsplit=1)
+    assert o16.dtype == torch.float16
+    report("linear f16 operands, half out", o16, a.float() @ w.float().t() + b, 1e-3)
+    with pytest.raises(ValueError):
+        ops.linear(a, w.bfloat16(), bias=b)                 # mixed operand types are refused
+
+
+@pytest.mark.parametrize("N,H,C0,C1,Cout,cx", [(2, 32, 320, 0, 320, 0), (1, 64, 320, 320, 320, 0), (2, 16, 320, 0, 320, 640),
+                                               (2, 8, 128, 0, 64, 0)])
+def test_conv3x3_f16_operands(N, H, C0, C1, Cout, cx):
+    ops = _ops()
+    setup_exact_fp32()
+    x0 = rnd(N, H, H, C0).half()
+    x1 = rnd(N, H, H, C1, seed=5).half() if C1 else None
+    w = rnd(Cout, C0 + C1, 3, 3, scale=(9 * (C0 + C1)) ** -0.5, seed=1).half()
+    b = rnd(Cout, seed=2)
+    xin = x0.float() if x1 is None else torch.cat([x0.float(), x1.float()], -1)
+    ref = F.conv2d(xin.permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    wp = pack3x3(w)
+    ax0 = None
+    if cx:
+        ax0 = rnd(N, H, H, cx, seed=6).half()
+        w1 = rnd(Cout, cx, scale=cx ** -0.5, seed=8).half()
+        ref = ref + F.conv2d(ax0.float().permute(0, 3, 1, 2), w1.float()[:, :, None, None]).permute(0, 2, 3, 1).reshape(-1, Cout)
+        wp = torch.cat([wp, w1], dim=1).contiguous()
+    out, out2, part = ops.gemm(x0, wp, Cout, kind=ops.GEMM_CONV3X3_S1, a1=x1, bias=b, conv_dims=(N, H, H), c0=C0, c1=C1,
+                               out_fp32=True, out2=True, out16=torch.float16, nsplit=1, ax0=ax0, gn_samples=N)
+    report(f"conv3x3 f16 operands {C0 + C1}(+{cx})->{Cout}@{H}", out, ref, 1e-3)
+    assert out2.dtype == torch.float16 and torch.equal(out2, out.half())
+    if part is not None:
+        _check_partials(part, out, N, "conv3x3 f16")
+
+
+def test_half_outputs_of_norms_and_shadows():
+    ops = _ops()
+    x = rnd(2, 32, 32, 320) * 3 + 0.5
+    g, be = rnd(320, seed=1), rnd(320, seed=2)
+    ref = F.silu(F.group_norm(x.permute(0, 3, 1, 2), 32, g, be, 1e-5)).permute(0, 2, 3, 1)
+    for fused in (False, None):
+        y = ops.groupnorm(x, g, be, silu=True, fused=fused, out_dtype=torch.float16)
+        assert y.dtype == torch.float16
+        report(f"groupnorm half out fused={fused}", y, ref, 1.5e-3)
+    xl = rnd(4096, 320, seed=4)
+    y = ops.layernorm(xl, g, be, out_dtype=torch.float16)
+    assert y.dtype == torch.float16
+    report("layernorm half out", y, F.layer_norm(xl, (320,), g, be, 1e-5), 1e-3)
+    y = ops.layernorm(xl.bfloat16(), g, be, out_dtype=torch.float16)           # generic kernel
+    report("layernorm (bf16 in) half out", y, F.layer_norm(xl.bfloat16().float(), (320,), g, be, 1e-5), 1e-3)
+    big = rnd(1000, 64, seed=7) * 100
+    big[0, 0], big[0, 1] = 1e6, -1e6                                             # saturates, never inf
+    h = ops.f32_to_bf16(big, torch.float16)
+    assert h.dtype == torch.float16 and torch.isfinite(h).all()
+    assert torch.equal(h, big.clamp(-65504, 65504).half())
+    assert torch.equal(ops.f32_to_bf16(big), big.bfloat16())
+    odd = rnd(777, seed=8)
+    assert torch.equal(ops.f32_to_bf16(odd, torch.float16), odd.half())
+    xs = rnd(2, 16, 16, 4, seed=9)
+    wd = rnd(320, 9, 4, scale=1 / 6, seed=10)
+    bd = rnd(320, seed=11)
+    o, o2 = ops.conv_direct(xs, wd, bd, 320, 3, out_fp32=True, out2=True, out2_dtype=torch.float16)
+    assert o2.dtype == torch.float16 and torch.equal(o2, o.half())
+    up = ops.upsample2x(o2)
+    assert up.dtype == torch.float16 and torch.equal(up[:, ::2, ::2], o2)
+
+
+@pytest.mark.parametrize("size", [(768, 768), (256, 256), (384, 640), (500, 300), (512, 512), (1024, 520)])
+def test_resize_matches_pillow_byte_for_byte(size):
+    """Device resize + rescale against PIL.Image.resize on the reference's own test image
+    (images/dog.jpg, stored in the img2img golden): identical bytes, identical fp32 pre-processing."""
+    from PIL import Image
+    from canon import golden
+    from pytorch_stable_diffusion_b200 import imageio
+    g = golden("img2img_5.pt")
+    if g is None:
+        pytest.skip("img2img golden (holds dog.jpg) not generated")
+    dog = Image.fromarray(g["input"].numpy())
+    w, h = size
+    ref = torch.from_numpy(np.array(dog.resize((w, h)))).to(DEV)
+    batch = torch.from_numpy(np.stack([np.asarray(dog), np.asarray(dog)[::-1].copy()])).to(DEV)
+    u8, img = imageio.resize_u8(batch, w, h, to_image=True)
+    assert u8.shape == (2, h, w, 3) and torch.equal(u8[0], ref)
+    flipped = torch.from_numpy(np.array(Image.fromarray(np.asarray(dog)[::-1].copy()).resize((w, h)))).to(DEV)
+    assert torch.equal(u8[1], flipped)
+    f = ref.float()
+    f *= 2 / 255
+    f += -1
+    assert torch.equal(img[0], f)
+    u8b, imgb = imageio.load_images([dog, dog.resize((300, 200))], w, h, DEV)
+    assert torch.equal(u8b[0], ref) and u8b.shape == (2, h, w, 3) and imgb.shape == (2, h, w, 3)
