@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SDB_ABI_VERSION 1
+#define SDB_ABI_VERSION 2   /* 2: IEEE-half operand / output flags, sdb_args_size, sdb_resample_u8, sdb_matmul_f64 */
 
 #define SDB_OK 0
 #define SDB_ERR_ARG (-1)

@@ -49,6 +49,7 @@ struct AttnParams {
   int qk_fold;   // two-tile kernel: the row offset of the softmax rides in Q.K^T (column d of K is all ones, column d
                  // of the Q tile in shared memory gets -round(row maximum of key block 0)), see the softmax loop
   int stagger;   // two-tile kernel, separate P: clocks tile 1 starts after tile 0 (0 = fixed issue order, lock step)
+  int two_issuers;  // two-tile kernel: one MMA issuer warp per query tile (default) instead of one for both
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -453,12 +454,18 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 //                P0.V(j)  Q0.K(j+1)  P1.V(j)  Q1.K(j+1)
 //   warps 2-5  softmax of tile 0, warps 6-9 softmax of tile 1 (one query row per thread)
 // TMEM: S0/P0 at columns [0,128), S1/P1 at [128,256), O0 at [256,384), O1 at [384,512).
-constexpr int ATT2_THREADS = 320;
+constexpr int ATT2_THREADS = 352;
 // Warp roles of the two-tile kernel: softmax warps 0-3 (tile 0) and 4-7 (tile 1) - TMEM lane quadrant = warp % 4 -,
 // then the TMA producer and the MMA issuer (highest warp id on its sub-partition; measured neutral against the
 // issuer as warp 1).
 constexpr int ATT2_TMA_WARP = 8;
 constexpr int ATT2_MMA_WARP = 9;
+// Second MMA issuer. A tcgen05.mma costs its ISSUING WARP ~60 ns (117 clk at 1.96 GHz) whatever its N - measured with
+// tools/micro/mma_issuers.cu: one warp 117 clk/MMA for N = 48 ... 128; two warps issuing independent streams 58.6
+// aggregate; four warps 29 (TS operands: the pipe floor N/2 = 24 is finally in sight). With d = 40 the 22 small MMAs
+// of a key block (2 x [3 Q.K^T + 8 P.V]) held ONE issuer for 2 600 of the ~2 950 clocks a key block took; with one
+// issuer warp per query tile the two tiles' chains run side by side.
+constexpr int ATT2_MMA_WARP2 = 10;
 constexpr int ATT2_MAX_STAGES = 3;   // K/V ring depth (4 and 6 measured no faster)
 
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
@@ -509,7 +516,7 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     mbar_init(q_full, 1);
     for (int i = 0; i < nstages; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], p.two_issuers ? 2 : 1);      // a K/V stage is free once BOTH tiles' P.V over it are done
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -556,8 +563,8 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       __syncwarp();
       if (++st == nstages) { st = 0; ph ^= 1u; }
     }
-  } else if (warp == ATT2_MMA_WARP) {
-    // ===================== MMA issuer
+  } else if (warp == ATT2_MMA_WARP || (warp == ATT2_MMA_WARP2 && p.two_issuers)) {
+    // ===================== MMA issuer(s)
     const uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BKV);
     // p_f16 variant: P (A operand, from TMEM) and V^T (B operand) are both IEEE half (formats 0)
     const uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, (uint32_t)p.dv_pad) & (p.p_f16 ? ~((7u << 7) | (7u << 10)) : ~0u);
@@ -598,7 +605,53 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
     };
     mbar_wait(&kv_full[0], 0, 23);
     tc_fence_after();
-    if (p_sep && p.stagger > 0) {
+    if (p.two_issuers) {
+      // one issuer per query tile: this warp owns tile t's Q.K^T / P.V chain; the tiles only meet at the K/V ring
+      // (both wait for kv_full, both commit their P.V to kv_empty)
+      const int t = warp - ATT2_MMA_WARP;
+      if (t == 1 && p.stagger < 0) {
+        // tile 1 starts about half a period after tile 0 so that the exponential phases of the two softmax
+        // warpgroups interleave on the sub-partitions (see the single-issuer form below)
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)(-p.stagger)) { }
+      }
+      issue_qk(t, 0);
+      int st = 0;
+      uint32_t ph_kv = 0;
+      for (int j = 0; j < nkv; ++j) {
+        int st_next = st + 1;
+        uint32_t ph_next = ph_kv;
+        if (st_next == nstages) { st_next = 0; ph_next ^= 1u; }
+        const bool more = (j + 1 < nkv);
+        const uint32_t par = (uint32_t)(j & 1);
+        if (p_sep) {
+          // P apart from S: the next key block's scores only need S_t to have been read
+          if (more) {
+            mbar_wait(&kv_full[st_next], ph_next, 25);
+            mbar_wait(&s_free[t], par, 30);
+            if (p.qk_fold && j == 0) mbar_wait(&q_ready[t], 0, 34);       // the rows' offsets are in the Q tile
+            tc_fence_after();
+            issue_qk(t, st_next);
+          }
+          if (t == 0 && lane == 0) ATT_STAMP(j, 7);
+          mbar_wait(&p_full[t], par, 24);
+          tc_fence_after();
+          issue_pv(t, st, j == 0, true);
+          if (t == 0 && lane == 0) ATT_STAMP(j, 6);
+        } else {
+          mbar_wait(&p_full[t], par, 24);
+          tc_fence_after();
+          issue_pv(t, st, j == 0, true);
+          if (more) {
+            mbar_wait(&kv_full[st_next], ph_next, 25);
+            tc_fence_after();
+            issue_qk(t, st_next);
+          }
+        }
+        st = st_next;
+        ph_kv = ph_next;
+      }
+    } else if (p_sep && p.stagger > 0) {
       // EXPERIMENT, off by default (SDB_ATTN_STAGGER=<clocks> enables it): event-driven issue with tile 1 started
       // <clocks> after tile 0. In lock step both tiles' softmax warps sit in the exponential loop at the same time
       // (the sub-partitions are saturated) and then in the TMEM load / row maximum / P store phases at the same
@@ -702,8 +755,9 @@ attn2_tc_kernel(const __grid_constant__ AttnParams p) {
       ph_kv = ph_next;
     }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================== softmax / correction / output: warps 0-3 tile 0, warps 4-7 tile 1
+    // (warp 10 falls through idle when the kernel runs with a single issuer)
     const int t = warp >> 2;
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -1031,6 +1085,10 @@ extern "C" int sdb_attention(const sdb_attn_args* a, void* stream) {
     // default: fixed issue order, tile 1 started 1 300 clocks after tile 0 when there are enough key blocks for
     // the offset to pay (S = 4096, d = 40: 843 -> 783 us; 1 100 / 1 500 / 1 900 clocks: 800 / 791 / 797 us)
     p.stagger = (stagger < 0 && (a->Skv + ATT_BKV - 1) / ATT_BKV < 8) ? 0 : stagger;
+    static int one_issuer = -1;
+    if (one_issuer < 0) { const char* ev = getenv("SDB_ATTN_ONE_ISSUER"); one_issuer = (ev && ev[0] == '1') ? 1 : 0; }
+    // one MMA issuer warp per query tile (the event-driven experiment, stagger > 0, keeps its single issuer)
+    p.two_issuers = (!one_issuer && p.stagger <= 0) ? 1 : 0;
   }
   p.dchunks = (dqk + 63) / 64;
   p.dk_steps = (dqk + 15) / 16;

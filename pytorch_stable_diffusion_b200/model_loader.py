@@ -8,6 +8,12 @@ from .encoder import VAE_Encoder
 
 def preload_models_from_standard_weights(ckpt_path, device):
     state_dict = model_converter.load_from_standard_weights(ckpt_path, device)
+    return models_from_state_dicts(state_dict, device)
+
+
+def models_from_state_dicts(state_dict, device):
+    """{'encoder','decoder','diffusion','clip'} state_dicts -> the four modules (strict load), as the reference's
+    preload_models_from_standard_weights builds them (sd/model_loader.py:28-50)."""
 
     encoder = VAE_Encoder().to(device)
     encoder.load_state_dict(state_dict['encoder'], strict=True)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"not exported: {missing}"
     unbound = sorted(declared - set(_ext.SIGNATURES))
     assert not unbound, f"declared in sdb200.h but not bound in _ext.py: {unbound}"
-    assert _ext.lib().sdb_abi_version() == 1
+    assert _ext.lib().sdb_abi_version() == 2
     # no torch types at the boundary: the library links only the CUDA runtime
     assert ctypes.sizeof(_ext.GemmArgs) > 0 and ctypes.sizeof(_ext.AttnArgs) > 0
 

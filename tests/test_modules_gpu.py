@@ -365,3 +365,16 @@ def test_checkpoint_load_path_on_gpu(models, tmp_path):
     img_loaded = pipeline.generate("a", "b", models=loaded, **kw)
     img_canon = pipeline.generate("a", "b", models=models, **kw)
     assert (img_loaded == img_canon).all()
+
+
+def test_command_line_front_end(tmp_path):
+    """python -m pytorch_stable_diffusion_b200 --synthetic (the notebook's replacement)."""
+    import subprocess
+    out = str(tmp_path / "img.png")
+    r = subprocess.run([sys.executable, "-m", "pytorch_stable_diffusion_b200", "--synthetic", "--prompt", "a", "--uncond", "b",
+                        "--steps", "2", "--batch", "2", "--out", out], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    from PIL import Image
+    for i in range(2):
+        im = Image.open(str(tmp_path / f"img_{i}.png"))
+        assert im.size == (512, 512) and im.mode == "RGB"

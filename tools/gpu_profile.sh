@@ -2,8 +2,8 @@
 # One gpurun call: per-kernel micro-benchmark, ncu launch list of one UNet evaluation + decode, and
 # `ncu --set full` captures of the three hot kernels (each only after its plain run exited 0).
 set -u
-TAG=${1:-r01}
-K='regex:^(gemm_|attn2?_tc|gn_|layernorm|softmax_rows|fill_zero|nchw_f32|nhwc_to|upsample2x|conv_direct|small_linear|cfg_ddpm|vae_|f32_to_bf16|axpby|image_to|uint8_to|clip_embed)'
+TAG=${1:-r02}
+K='regex:^(gemm_|attn2?_tc|gn_|layernorm|softmax_rows|fill_zero|nchw_f32|nhwc_to|upsample2x|conv_direct|small_linear|cfg_ddpm|vae_|f32_to_bf16|axpby|image_to|uint8_to|clip_embed|matmul_f64|resample_u8)'
 python tools/kernel_bench.py --graph --attn-mode 3 --json gpurun_out/${TAG}_kernel_bench.json > gpurun_out/${TAG}_kernel_bench.log 2>&1
 python bench.py --profile-only > gpurun_out/${TAG}_po.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-file gpurun_out/${TAG}_launches.csv \
