@@ -619,7 +619,7 @@ def test_attention_growing_maximum():
 
 
 @pytest.mark.parametrize("S,amp,ramp", [(4096, 1.0, False), (1024, 3.0, False), (1024, 1.0, True), (1000, 2.0, False),
-                                        (256, 1.0, False)])
+                                        (256, 1.0, False), (384, 1.0, True), (2304, 2.0, True), (9216, 1.0, False)])
 def test_attention_qk_fold(S, amp, ramp):
     """Row offset of the softmax folded into Q.K^T (ones column in K, offset column written into the Q tile by the
     kernel): padded 48-column heads, pre-scaled queries, ones-row denominator."""
