@@ -526,13 +526,15 @@ def main():
             top = lambda kvs: max(kvs, key=lambda kv: kv[1]["ms"])[0] if kvs else None
             # `roofline`: the north-star's named kernel, the implicit-GEMM 3x3 conv (the dominant kernel by time
             # and by FLOPs), its dominant tensor-bound variant
-            # (the problem size with the largest total time first - 320 -> 320 @ 64x64, nine launches per evaluation -
-            # then its most expensive launch variant: a stable choice from run to run)
+            # (the problem size with the most FLOPs per evaluation first, full resolution winning ties - 320 -> 320 @
+            # 64x64, nine launches per evaluation - then its most expensive launch variant: a stable choice)
             convs = [kv for kv in fam("gemm_tc_conv3x3") if kv[1]["flops"] / max(kv[1]["bytes"], 1.0) >= ridge]
             size_of = lambda kv: " ".join(kv[0][1].split()[:4])          # rows= cin= cout= taps=
             by_size = {}
-            for kv in convs:
-                by_size[size_of(kv)] = by_size.get(size_of(kv), 0.0) + kv[1]["ms"]
+            for kv in convs:     # rank problem sizes by their FLOPs per evaluation, then by rows: no timing noise in the choice
+                rows_ = int(kv[0][1].split()[0].split("=")[1])
+                fl_, _ = by_size.get(size_of(kv), (0.0, rows_))
+                by_size[size_of(kv)] = (fl_ + kv[1]["flops"], rows_)
             dom_size = max(by_size, key=by_size.get) if by_size else None
             k_conv = top([kv for kv in convs if size_of(kv) == dom_size])
             k_attn = top(fam("attention"))

@@ -16,6 +16,7 @@
 // Replaces the reference's nn.Conv2d / nn.Linear call sites (sd/diffusion.py:125,135,143,256,
 // 266-269,410,545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112-129,235-339;
 // sd/encoder.py:56-92; sd/clip.py:117,121).
+#include <algorithm>
 #include "common.cuh"
 #include "host.h"
 #include "../../include/sdb200.h"
@@ -71,7 +72,10 @@ struct GemmTcParams {
   // producer / issuer hand-shake runs once per three k-blocks.
   int a3;                  // 0 = one tap per stage (classic), 1 = filter-column staging
   int a3_box_bytes;        // (bh + 2) * bw * 128
-  int a3_iters;            // pipeline stages consumed per tile: 3 * cblocks + cblocks_x
+  int a3_iters;            // pipeline stages consumed per tile: 3 * cblocks + ceil(cblocks_x / 2)
+  int a3_stage_bytes;      // max(box + 3 W sub-tiles, 2 x (classic A tile + W sub-tile)): the extra 1x1 source's k-blocks
+                           // travel TWO per stage ([A0][A1][W0][W1]) - one per stage left only `stages` k-blocks in
+                           // flight and the extra phase ran at half the speed of the taps
   // epilogue
   int N;                   // valid output columns (Cout)
   int block_n;             // UMMA N (multiple of 16, <= 256)
@@ -240,7 +244,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
   const int b_rows = p.acc_n / CG;                       // W rows this CTA stages per k-block and accumulator
   const int b_sub_bytes = b_rows * GEMM_BK * 2;
   const int b_stage_bytes = p.n_acc * b_sub_bytes;
-  const int stage_bytes = p.a3 ? (p.a3_box_bytes + 3 * b_stage_bytes) : (GEMM_A_STAGE_BYTES + b_stage_bytes);
+  const int stage_bytes = p.a3 ? p.a3_stage_bytes : (GEMM_A_STAGE_BYTES + b_stage_bytes);
   const int nbuf = (p.n_acc == 2) ? 1 : 2;               // TMEM accumulator buffers
   uint8_t* epi_smem = smem + p.stages * stage_bytes;
   // [staging: one chunk per epilogue warp][residual ring: GEMM_RES_RING chunks per warp, if any][barriers]
@@ -344,16 +348,27 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 }
               }
             } else {
-              if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-              const int wk = p.ntaps * ctot + cb * GEMM_BK;
-              if constexpr (CG == 2) {
-                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0, 0, t.h0, t.nb0);
-                tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst, wk, wn);
-                if (p.n_acc == 2) tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
-              } else {
-                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0, 0, t.h0, t.nb0);
-                tma_load_2d(&p.map_w, &full_bar[s], b_dst, wk, wn);
-                if (p.n_acc == 2) tma_load_2d(&p.map_w, &full_bar[s], b_dst + b_sub_bytes, wk, wn + p.acc_n);
+              // extra 1x1 source: two k-blocks per stage, [A0][A1][W0][W1]
+              const int nx = min(2, p.cblocks_x - cb);
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_bytes * (uint32_t)nx);
+              uint8_t* bx_dst = a_dst + 2 * GEMM_A_STAGE_BYTES;
+              for (int e = 0; e < nx; ++e) {
+                const int cbe = cb + e;
+                const bool sec = cbe >= p.cblocks_x0;
+                const CUtensorMap* mx = sec ? &p.map_x1 : &p.map_x0;
+                const int cx = (sec ? (cbe - p.cblocks_x0) : cbe) * GEMM_BK;
+                const int wk = p.ntaps * ctot + cbe * GEMM_BK;
+                uint8_t* ad = a_dst + e * GEMM_A_STAGE_BYTES;
+                uint8_t* bd = bx_dst + e * b_stage_bytes;
+                if constexpr (CG == 2) {
+                  tma_load_5d_pair(mx, &full_bar[s], ad, cx, t.w0, 0, t.h0, t.nb0);
+                  tma_load_2d_pair(&p.map_w, &full_bar[s], bd, wk, wn);
+                  if (p.n_acc == 2) tma_load_2d_pair(&p.map_w, &full_bar[s], bd + b_sub_bytes, wk, wn + p.acc_n);
+                } else {
+                  tma_load_5d(mx, &full_bar[s], ad, cx, t.w0, 0, t.h0, t.nb0);
+                  tma_load_2d(&p.map_w, &full_bar[s], bd, wk, wn);
+                  if (p.n_acc == 2) tma_load_2d(&p.map_w, &full_bar[s], bd + b_sub_bytes, wk, wn + p.acc_n);
+                }
               }
             }
           }
@@ -361,7 +376,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           if (!extra) {
             if (++kx == 3) { kx = 0; if (++cb == p.cblocks) { cb = 0; extra = true; } }
           } else {
-            ++cb;
+            cb += 2;
           }
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
@@ -438,15 +453,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const uint64_t a_row_step = (uint64_t)((p.bw * 128) >> 4);
           const uint64_t b_tap_step = (uint64_t)(b_stage_bytes >> 4);
           const int n3 = 3 * p.cblocks;
+          const uint64_t bx_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + 2u * GEMM_A_STAGE_BYTES);
+          const uint64_t ax_step = (uint64_t)(GEMM_A_STAGE_BYTES >> 4);
           for (int i = 0; i < p.a3_iters; ++i) {
             mbar_wait(&full_bar[s], ph, 2);
             if (i == 0) trace_stamp(trc, lt, 3);
             tc_fence_after();
-            const int nsub = (i < n3) ? 3 : 1;
+            const bool taps = i < n3;
+            const int nsub = taps ? 3 : min(2, p.cblocks_x - 2 * (i - n3));
             if (elect_one()) {
               for (int j = 0; j < nsub; ++j) {
-                const uint64_t a_desc = a_desc0 + soff + (uint64_t)j * a_row_step;
-                const uint64_t b_desc = b3_desc0 + soff + (uint64_t)j * b_tap_step;
+                const uint64_t a_desc = a_desc0 + soff + (uint64_t)j * (taps ? a_row_step : ax_step);
+                const uint64_t b_desc = (taps ? b3_desc0 : bx_desc0) + soff + (uint64_t)j * b_tap_step;
                 if constexpr (CG == 2) {
                   mma_ss_pair(d_tmem, a_desc, b_desc, idesc, accum);
                   mma_ss_pair(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
@@ -1459,12 +1477,16 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
                     // long reductions only (main-loop bound; short ones keep the shared memory for the TMA epilogue),
                     // and two stages must fit next to the per-lane epilogue's staging
                     p.nkb_total > 32 &&
-                    2 * ((p.bh + 2) * p.bw * 128 + 3 * b_stage_host) + GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 +
-                            GEMM_BAR_BYTES <= 227 * 1024 && (a->smem_budget <= 0 || a->smem_budget >= 227 * 1024);
+                    2 * std::max((p.bh + 2) * p.bw * 128 + 3 * b_stage_host, 2 * (GEMM_A_STAGE_BYTES + b_stage_host)) +
+                            GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + GEMM_BAR_BYTES <= 227 * 1024 &&
+                    (a->smem_budget <= 0 || a->smem_budget >= 227 * 1024);
     if (ok) {
       p.a3 = 1;
       p.a3_box_bytes = (p.bh + 2) * p.bw * 128;
-      p.a3_iters = 3 * p.cblocks + p.cblocks_x;
+      p.a3_iters = 3 * p.cblocks + (p.cblocks_x + 1) / 2;
+      p.a3_stage_bytes = p.a3_box_bytes + 3 * b_stage_host;
+      if (p.cblocks_x > 0 && 2 * (GEMM_A_STAGE_BYTES + b_stage_host) > p.a3_stage_bytes)
+        p.a3_stage_bytes = 2 * (GEMM_A_STAGE_BYTES + b_stage_host);
       // the main sources are fetched with the taller box; the extra 1x1 source keeps its one-tap boxes
       uint32_t box3[5] = {64, (uint32_t)p.bw, 1, (uint32_t)(p.bh + 2), 1};
       const uint64_t WI = (uint64_t)a->WI, HI = (uint64_t)a->HI;
@@ -1482,7 +1504,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   }
 
   // ---- pipeline depth from the shared-memory budget
-  const int stage_bytes = p.a3 ? (p.a3_box_bytes + 3 * b_stage_host) : (GEMM_A_STAGE_BYTES + b_stage_host);
+  const int stage_bytes = p.a3 ? p.a3_stage_bytes : (GEMM_A_STAGE_BYTES + b_stage_host);
   const long long ldr_eff = a->ldr ? a->ldr : a->Cout;
   const long long ldo_eff = a->ldo ? a->ldo : a->Cout;
   const int want_split = a->nsplit > 1;
