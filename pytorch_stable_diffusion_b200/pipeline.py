@@ -67,6 +67,28 @@ def _draw(shape, generator, seeds, device):
     return torch.cat(parts, 0).to(device)
 
 
+_TABLE_CACHE = collections.OrderedDict()
+
+
+def _step_tables(sampler, device):
+    """Device-resident per-step constants of a schedule: DDPM coefficients [steps, 5] and sinusoidal time embeddings
+    [steps, 320] (sd/pipeline.py:211, sd/ddpm.py:102-139). Both depend only on the timestep list and the betas, so
+    they are built once per (schedule, device) instead of on every generate() call (100 small host ops + 2 copies)."""
+    key = (tuple(int(t) for t in sampler.timesteps), float(sampler.betas[0]), float(sampler.betas[-1]),
+           int(sampler.num_train_timesteps), str(device))
+    hit = _TABLE_CACHE.get(key)
+    if hit is None:
+        coef = sampler.coefficient_table(device)
+        temb = torch.cat([get_time_embedding(int(t)) for t in sampler.timesteps]).to(device)
+        hit = (coef, temb)
+        _TABLE_CACHE[key] = hit
+        while len(_TABLE_CACHE) > 8:
+            _TABLE_CACHE.popitem(last=False)
+    else:
+        _TABLE_CACHE.move_to_end(key)
+    return hit
+
+
 class _Loop:
     """Static buffers + captured CUDA graph of one denoising-loop configuration."""
 
@@ -242,8 +264,7 @@ def generate(
         if step_noise.shape[0] < n_steps:   # the last step (t = 0) draws nothing
             pad = torch.zeros((n_steps - step_noise.shape[0],) + tuple(latents_shape), device=device)
             step_noise = torch.cat([step_noise, pad])
-        coef = sampler.coefficient_table(device)
-        temb = torch.cat([get_time_embedding(int(t)) for t in timesteps]).to(device)
+        coef, temb = _step_tables(sampler, device)
 
         diffusion = models["diffusion"]
         diffusion.to(device)
