@@ -19,6 +19,7 @@ WIDTH = 512
 HEIGHT = 512
 LATENTS_WIDTH = WIDTH // 8
 LATENTS_HEIGHT = HEIGHT // 8
+MAX_LATENT_TOKENS = 24576     # row length limit of sdb_softmax_rows (VAE attention, sd/decoder.py:34-73)
 
 # Captured denoising loops, least recently used first. Each entry pins its static buffers and its graph's memory
 # pool (a few GB at batch 8), so only the GRAPH_CACHE_SIZE most recently used configurations stay resident:
@@ -190,6 +191,11 @@ def generate(
         W = WIDTH if width is None else width
         if H % 64 or W % 64:
             raise ValueError("height and width must be multiples of 64")
+        if (H // 8) * (W // 8) > MAX_LATENT_TOKENS:
+            # the VAE's single-head d = 512 attention keeps one fp32 score row per query in shared memory
+            # (sdb_softmax_rows: 24 576 columns) and an S x S fp32 score matrix per sample in HBM
+            raise ValueError(f"{H}x{W} exceeds the largest supported image: (H/8)*(W/8) must not exceed "
+                             f"{MAX_LATENT_TOKENS} latent positions (e.g. 1248x1248)")
         lh, lw = H // 8, W // 8
         B = batch_size
 

@@ -80,6 +80,8 @@ def test_product_path_has_no_cpu_fallback():
         pipeline.generate("a", "b", strength=1.5, models={}, tokenizer=StubTokenizer(), device="cpu")
     with pytest.raises(ValueError):
         pipeline.generate("a", "b", sampler_name="ddim", models={}, tokenizer=StubTokenizer(), device="cpu")
+    with pytest.raises(ValueError, match="largest supported image"):
+        pipeline.generate("a", "b", models={}, tokenizer=StubTokenizer(), device="cuda", height=2048, width=2048)
 
 
 def test_unsafe_pickle_is_opt_in(tmp_path, monkeypatch):
