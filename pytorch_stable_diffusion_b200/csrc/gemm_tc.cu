@@ -33,6 +33,7 @@ constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;          // one 32x32 fp32 chu
 constexpr int GEMM_RES_RING = 3;                           // residual chunks in flight per epilogue warp (+1)
 constexpr int GEMM_BAR_BYTES = 512;                        // mbarriers + TMEM slot at the end of shared memory
 constexpr int GEMM_EPI16_BYTES = 32 * 32 * 2;              // one 32x32 16-bit chunk
+constexpr int GEMM_BIAS_LINES = 5;                         // TMA epilogue: 128-byte bias lines per warp (its <= 5 chunks of a tile)
 
 struct GemmTcParams {
   CUtensorMap map_a0;
@@ -564,7 +565,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const uint32_t wblk = smem_u32(epi_smem) + (uint32_t)(e * p.epi_warp_bytes);
     const uint32_t b16_base = wblk + (uint32_t)(nslot * GEMM_EPI_STAGE_BYTES);
     const uint32_t rbar0 = smem_u32(res_bar + e * 4);
-    const uint32_t bias_line = smem_u32(epi_smem) + (uint32_t)(GEMM_EPI_WARPS * p.epi_warp_bytes + e * 128);
+    const uint32_t bias_line = smem_u32(epi_smem) + (uint32_t)(GEMM_EPI_WARPS * p.epi_warp_bytes + e * (GEMM_BIAS_LINES * 128));
     const bool slab_ok = p.slab_ok[q] != 0;
     const int sw0 = p.slab_w0[q], sh0 = p.slab_h0[q], sn0 = p.slab_n0[q];
     const int pfd = nslot - 2;                 // residual prefetch distance in chunks (slots: ahead | current | draining)
@@ -610,13 +611,40 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
       const int acc = (p.n_acc == 2) ? 0 : (lt & 1);
       const int ch_first = (half + lt) & 1;
+      const int c1 = t.w0 + sw0, c2 = t.h0 + sh0, c3 = t.nb0 + sn0;
+      // Bias of every chunk this warp owns in the tile (chunks ch_first, ch_first + 2, ...: at most GEMM_BIAS_LINES),
+      // requested BEFORE the accumulator wait: five independent loads whose latency hides behind the main loop - a
+      // load per chunk sat on the epilogue's per-chunk latency chain (the bound of every short-K GEMM). The 32 column
+      // values of a chunk reach the row-threads through a 128-byte shared-memory line (broadcast reads).
+      float rowb = 0.f;
+      if (p.bias_mode == 1) {
+        float cb[GEMM_BIAS_LINES];
+#pragma unroll
+        for (int k = 0; k < GEMM_BIAS_LINES; ++k) {
+          const int col = t.n0 + (ch_first + 2 * k) * 32 + lane;
+          cb[k] = (ch_first + 2 * k < nchunks && col < p.N) ? __ldg(p.bias + col) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < GEMM_BIAS_LINES; ++k)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(k * 128 + lane * 4)), "f"(cb[k]) : "memory");
+      } else {
+        if (lt == 0) {
+#pragma unroll
+          for (int k = 0; k < GEMM_BIAS_LINES; ++k)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(k * 128 + lane * 4)), "f"(0.f) : "memory");
+        }
+        if (p.bias_mode == 2) {
+          const long long m = (long long)c1 + lane;          // rank-2 outputs only (host-checked)
+          if (m < p.m_total) rowb = __ldg(p.bias + m);
+        }
+      }
+      __syncwarp();
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
       mbar_wait(&tfull_bar[acc], (uint32_t)(lt / nbuf) & 1u, 3);
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 6); trace_epi(trc, lt, 1); }
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * p.acc_stride) + ((uint32_t)(q * 32) << 16);
       const int cpa = p.acc_n >> 5;
-      const int c1 = t.w0 + sw0, c2 = t.h0 + sh0, c3 = t.nb0 + sn0;
       // all tcgen05.ld of this accumulator have completed: hand it back to the MMA issuer (the leader's barrier;
       // a remote arrive from the peer CTA) - before the last chunk's arithmetic and stores
       auto release_acc = [&]() {
@@ -631,32 +659,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       auto taddr = [&](int c) {
         return t_addr + (uint32_t)((p.n_acc == 2 && c >= cpa) ? 256 + (c - cpa) * 32 : c * 32);
       };
-      float rowb = 0.f, colb = 0.f;
-      // chunk prologue: free the buffers of the chunk before the previous one, request the next residual and
-      // this chunk's bias - everything that does not need the accumulator
+      // chunk prologue: free the buffers of the chunk before the previous one and request the next residual -
+      // everything that does not need the accumulator
       auto pre = [&](int ch) {
-        const int col0 = t.n0 + ch * 32;
-        const int ncol = min(32, p.N - col0);
         // stores of the chunk before the previous one have left shared memory: its slot / 16-bit buffer
         // are free again (and the slot the prefetch below targets is the one that chunk used)
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
         if (has_res) issue_prefetch();
-        // bias: requested before the accumulator wait; the 32 column values reach every row-thread through a
-        // 128-byte shared-memory line (broadcast reads)
-        rowb = 0.f; colb = 0.f;
-        if (p.bias_mode == 2) {
-          const long long m = (long long)c1 + lane;          // rank-2 outputs only (host-checked)
-          if (m < p.m_total) rowb = __ldg(p.bias + m);
-        } else if (p.bias_mode == 1) {
-          if (lane < ncol) colb = __ldg(p.bias + col0 + lane);
-        }
       };
       // chunk body: accumulator row in v (loaded and waited for)
       auto post = [&](const uint32_t (&v)[32], int ch) {
         const int col0 = t.n0 + ch * 32;
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_line + (uint32_t)(lane * 4)), "f"(colb) : "memory");
-        __syncwarp();
+        const uint32_t bline = bias_line + (uint32_t)(((ch - ch_first) >> 1) * 128);
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
         const uint32_t srow = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES + lane * 128);
         if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
@@ -665,22 +680,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         {
           const uint32_t sx = (uint32_t)(lane & 7);
           switch ((p.act != 0 ? 1 : 0) | (has_res ? 2 : 0) | (f32out ? 4 : 0) | (p.out_f16 ? 8 : 0)) {
-            case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 1: epi_rows<true, false, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 2: epi_rows<false, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 3: epi_rows<true, true, false, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 4: epi_rows<false, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 5: epi_rows<true, false, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 9: epi_rows<true, false, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 10: epi_rows<false, true, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 11: epi_rows<true, true, false, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 12: epi_rows<false, false, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 13: epi_rows<true, false, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            case 14: epi_rows<false, true, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
-            default: epi_rows<true, true, true, true>(v, pk, srow, sx, bias_line, rowb, p.act); break;
+            case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 1: epi_rows<true, false, false, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 2: epi_rows<false, true, false, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 3: epi_rows<true, true, false, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 4: epi_rows<false, false, true, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 5: epi_rows<true, false, true, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 6: epi_rows<false, true, true, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 7: epi_rows<true, true, true, false>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 8: epi_rows<false, false, false, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 9: epi_rows<true, false, false, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 10: epi_rows<false, true, false, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 11: epi_rows<true, true, false, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 12: epi_rows<false, false, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 13: epi_rows<true, false, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            case 14: epi_rows<false, true, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
+            default: epi_rows<true, true, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
           }
         }
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
@@ -1536,7 +1551,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
       int nslot = a->residual ? 4 : (f32o ? 2 : 0);
       for (;;) {
         p.epi_warp_bytes = nslot * GEMM_EPI_STAGE_BYTES + (has16 ? 2 * GEMM_EPI16_BYTES : 0);
-        fixed_bytes = GEMM_EPI_WARPS * (p.epi_warp_bytes + 128) + 1024 + GEMM_BAR_BYTES;   // + one bias line per warp
+        fixed_bytes = GEMM_EPI_WARPS * (p.epi_warp_bytes + GEMM_BIAS_LINES * 128) + 1024 + GEMM_BAR_BYTES;   // + the bias lines of a warp
         stages = (smem_budget - fixed_bytes) / stage_bytes;
         if (stages >= 3 || !(a->residual && nslot == 4)) break;
         nslot = 3;
