@@ -46,7 +46,13 @@ enum {
   SDB_GEMM_LINEAR = 0,            /* out[M,Cout] = A[M,C0(+C1)] . W^T   (nn.Linear, 1x1 conv)   */
   SDB_GEMM_CONV3X3_S1 = 1,        /* 3x3, stride 1, pad 1                                        */
   SDB_GEMM_CONV3X3_S2 = 2,        /* 3x3, stride 2, pad 1   (sd/diffusion.py:553,561,569)        */
-  SDB_GEMM_CONV3X3_S2_PAD_RB = 3  /* 3x3, stride 2, pad right/bottom only (sd/encoder.py:120-122)*/
+  SDB_GEMM_CONV3X3_S2_PAD_RB = 3, /* 3x3, stride 2, pad right/bottom only (sd/encoder.py:120-122)*/
+  SDB_GEMM_CONV2X2_UP = 4         /* one parity phase of [nearest x2 up-sampling -> 3x3 conv, pad 1] (Upsample,
+                                     sd/diffusion.py:412-435): the output pixels (2y + a, 2x + b), up_phase = 2a + b, are a
+                                     2x2 convolution of the LOW-resolution input a0 [NB, HI, WI, C0] with taps
+                                     (a - 1 + u, b - 1 + v); w rows hold [u][v][C0] = the 3x3 taps that fall on the same
+                                     input pixel summed at pack time. out / out2 are the [NB, 2HI, 2WI, Cout] tensors; four
+                                     launches (phases 0..3) fill them: 4/9 of the FLOPs, no up-sampled tensor in HBM. */
 };
 enum { SDB_ACT_NONE = 0, SDB_ACT_QUICK_GELU = 1, SDB_ACT_SILU = 2 };
 
@@ -90,6 +96,8 @@ typedef struct sdb_gemm_args {
   const void* ax1;        /* resblock's skip convolution (sd/diffusion.py:138-143,208): bf16 NHWC             */
   int Cx0, Cx1;           /* [NB, HI, WI, Cx0] (++ [.., Cx1]); w rows then hold 9*(C0+C1) + Cx0 + Cx1 values,  */
                           /* the 1x1 weights last; multiples of 64. NULL = off.                               */
+  int up_phase;           /* CONV2X2_UP: 2a + b. With gn_part the four phases share one partial-sum tensor
+                             [samples][4 * K][Cout][2], K = sdb_gemm_gn_slabs(SDB_GEMM_CONV2X2_UP, NB, HI, WI, 0, 0)      */
   int ab_f16;             /* every 16-bit operand (a0, a1, ax0, ax1, w) is IEEE half instead of bf16: 11 instead of 8
                              significand bits at the same width and tensor-core rate (tcgen05 kind::f16 takes either),
                              fp32 accumulation unchanged. The UNet's full-resolution level runs this way: it carries

@@ -20,7 +20,8 @@ class GemmArgs(ctypes.Structure):
         ("out_fp32", c_int), ("res_fp32", c_int), ("bias_per_row", c_int), ("act", c_int), ("block_n", c_int),
         ("nsplit", c_int), ("smem_budget", c_int), ("cta_pair", c_int), ("out_f16", c_int),
         ("epi_mode", c_int), ("gn_part", c_void_p), ("gn_hw", c_int),
-        ("ax0", c_void_p), ("ax1", c_void_p), ("Cx0", c_int), ("Cx1", c_int), ("ab_f16", c_int),
+        ("ax0", c_void_p), ("ax1", c_void_p), ("Cx0", c_int), ("Cx1", c_int), ("up_phase", c_int),
+        ("ab_f16", c_int),
     ]
 
 

@@ -72,7 +72,9 @@ struct GemmTcParams {
   // L2 (0.42 for 16 x 8 patches) - the narrow pair tiles were bound by exactly that L2 -> SM traffic - and the
   // producer / issuer hand-shake runs once per three k-blocks.
   int a3;                  // 0 = one tap per stage (classic), 1 = filter-column staging
-  int a3_box_bytes;        // (bh + 2) * bw * 128
+  int a3_nrow, a3_ncol;    // filter rows per column / filter columns: 3 x 3, or 2 x 2 for an up-sampling phase
+  int a3_h0, a3_w0;        // offset of the first filter row / column from the output pixel: -1 / -1, or a - 1 / b - 1
+  int a3_box_bytes;        // (bh + a3_nrow - 1) * bw * 128
   int a3_iters;            // pipeline stages consumed per tile: 3 * cblocks + ceil(cblocks_x / 2)
   int a3_stage_bytes;      // max(box + 3 W sub-tiles, 2 x (classic A tile + W sub-tile)): the extra 1x1 source's k-blocks
                            // travel TWO per stage ([A0][A1][W0][W1]) - one per stage left only `stages` k-blocks in
@@ -115,6 +117,13 @@ struct GemmTcParams {
   int gn_K;                // slabs per sample
   int gn_hw;               // rank-2 outputs: rows per sample (multiple of 32)
   int gn_spq;              // conv outputs: slabs of one sample inside a tile = min(4, bw*bh/32)
+  int gn_stride, gn_off;   // slab index = sample * gn_stride + gn_off + ...: gn_K and 0, or 4 * gn_K and phase * gn_K for
+                           // the four phase launches of an up-sampling conv that share one partial-sum tensor
+  // Nearest-neighbour x2 up-sampling folded into the following 3x3 conv (SDB_GEMM_CONV2X2_UP): the output pixels of
+  // one parity (2y + a, 2x + b) are a 2x2 convolution of the LOW-resolution input (taps (a - 1 + u, b - 1 + v)) with
+  // the 3x3 taps that fall on the same input pixel summed at pack time. The tile space is the low-resolution grid; the
+  // epilogue scatters row (n, y, x) to row ((n*HO + y)*2 + a) * 2*WO + 2*x + b of the high-resolution tensor.
+  int up, up_a, up_b;
   // TMA epilogue (short reductions, where the epilogue bounds the tile time): thread = row, result staged in
   // swizzled shared memory and written with cp.async.bulk.tensor stores, fp32 residual fetched by TMA loads
   int epi_tma;
@@ -310,7 +319,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     if (p.a3) {
       // ----- filter-column staging: per channel block three stages (kx = 0, 1, 2), each ONE halo box + three W
       // sub-tiles; the extra 1x1 source (if any) follows as classic one-tap stages
-      const uint32_t tx3 = (uint32_t)((p.a3_box_bytes + 3 * b_stage_bytes) * CG);
+      const uint32_t tx3 = (uint32_t)((p.a3_box_bytes + p.a3_nrow * b_stage_bytes) * CG);
+      const int nrow = p.a3_nrow, ncol = p.a3_ncol;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         trace_stamp(trc, ltp, 0);
@@ -328,23 +338,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           if (elect_one()) {
             if (!extra) {
               if (leader) mbar_arrive_expect_tx(&full_bar[s], tx3);
-              const int wk = kx * ctot + cb * GEMM_BK;                    // tap (ky, kx) starts at (3 ky + kx) * ctot
+              const int wk = kx * ctot + cb * GEMM_BK;                    // tap (ky, kx) starts at (ncol ky + kx) * ctot
               if constexpr (CG == 2) {
-                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0 + kx - 1, 0, t.h0 - 1, t.nb0);
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                  tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + 3 * ky * ctot, wn);
+                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0 + kx + p.a3_w0, 0, t.h0 + p.a3_h0, t.nb0);
+                for (int ky = 0; ky < nrow; ++ky) {
+                  tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + ncol * ky * ctot, wn);
                   if (p.n_acc == 2)
-                    tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes, wk + 3 * ky * ctot,
-                                     wn + p.acc_n);
+                    tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes,
+                                     wk + ncol * ky * ctot, wn + p.acc_n);
                 }
               } else {
-                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0 + kx - 1, 0, t.h0 - 1, t.nb0);
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                  tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + 3 * ky * ctot, wn);
+                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0 + kx + p.a3_w0, 0, t.h0 + p.a3_h0, t.nb0);
+                for (int ky = 0; ky < nrow; ++ky) {
+                  tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + ncol * ky * ctot, wn);
                   if (p.n_acc == 2)
-                    tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes, wk + 3 * ky * ctot,
+                    tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes + b_sub_bytes, wk + ncol * ky * ctot,
                                 wn + p.acc_n);
                 }
               }
@@ -375,7 +383,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           }
           __syncwarp();
           if (!extra) {
-            if (++kx == 3) { kx = 0; if (++cb == p.cblocks) { cb = 0; extra = true; } }
+            if (++kx == ncol) { kx = 0; if (++cb == p.cblocks) { cb = 0; extra = true; } }
           } else {
             cb += 2;
           }
@@ -453,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const uint64_t b3_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + (uint32_t)p.a3_box_bytes);
           const uint64_t a_row_step = (uint64_t)((p.bw * 128) >> 4);
           const uint64_t b_tap_step = (uint64_t)(b_stage_bytes >> 4);
-          const int n3 = 3 * p.cblocks;
+          const int n3 = p.a3_ncol * p.cblocks;
           const uint64_t bx_desc0 = make_kmajor_sw128_desc(smem_u32(smem) + 2u * GEMM_A_STAGE_BYTES);
           const uint64_t ax_step = (uint64_t)(GEMM_A_STAGE_BYTES >> 4);
           for (int i = 0; i < p.a3_iters; ++i) {
@@ -461,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             if (i == 0) trace_stamp(trc, lt, 3);
             tc_fence_after();
             const bool taps = i < n3;
-            const int nsub = taps ? 3 : min(2, p.cblocks_x - 2 * (i - n3));
+            const int nsub = taps ? p.a3_nrow : min(2, p.cblocks_x - 2 * (i - n3));
             if (elect_one()) {
               for (int j = 0; j < nsub; ++j) {
                 const uint64_t a_desc = a_desc0 + soff + (uint64_t)j * (taps ? a_row_step : ax_step);
@@ -820,7 +828,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int dn = rdec[i] >> 16;
         const int ww = t.w0 + (rdec[i] & 0xff), hh = t.h0 + ((rdec[i] >> 8) & 0xff), nn = t.nb0 + dn;
         const bool ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
-        mr[i] = ok ? (nn * p.HO + hh) * p.WO + ww : -1;       // output row index, -1 = outside the tensor
+        // output row index, -1 = outside the tensor (up-sampling phases scatter into the 2x larger output)
+        mr[i] = !ok ? -1 : (p.up ? ((nn * p.HO + hh) * 2 + p.up_a) * (2 * p.WO) + 2 * ww + p.up_b
+                                 : (nn * p.HO + hh) * p.WO + ww);
       }
     };
     // ---- residual prefetch cursor: walks the same (tile, chunk) sequence as the main loop,
@@ -887,7 +897,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const int dn = r0 / plane;
           const int sn = t.nb0 + dn;
           gn_ok = (dn < p.bn) && (sn < p.NB);
-          gn_slab = (long long)sn * p.gn_K + t.sp * p.gn_spq + (r0 - dn * plane) / 32;
+          gn_slab = (long long)sn * p.gn_stride + p.gn_off + t.sp * p.gn_spq + (r0 - dn * plane) / 32;
         }
       }
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
@@ -1307,8 +1317,8 @@ extern "C" int sdb_gemm_gn_slabs(int kind, int NB, int HI, int WI, int M, int gn
     return gn_hw / 32;
   }
   if (NB <= 0 || HI <= 0 || WI <= 0) return 0;
-  const bool s2 = (kind != SDB_GEMM_CONV3X3_S1);
-  const int HO = s2 ? HI / 2 : HI, WO = s2 ? WI / 2 : WI;
+  const bool s2 = (kind == SDB_GEMM_CONV3X3_S2 || kind == SDB_GEMM_CONV3X3_S2_PAD_RB);
+  const int HO = s2 ? HI / 2 : HI, WO = s2 ? WI / 2 : WI;     // CONV2X2_UP: slabs of ONE phase (low-resolution grid)
   int bw = 0, bh = 0, bn = 0;
   if (pick_tile_box(NB, HO, WO, &bw, &bh, &bn)) return 0;
   const int plane = bw * bh;
@@ -1327,7 +1337,7 @@ extern "C" int sdb_gemm_conv_a3_bytes(int NB, int HI, int WI) {
   const char* ev = getenv("SDB_NO_A3");
   if (ev && ev[0] == '1') return 0;
   if (bn != 1 || bw * bh != GEMM_BM || bw % 8 != 0) return 0;
-  return (bh + 2) * bw * 128;
+  return (bh + 2) * bw * 128;      // (an up-sampling phase fetches (bh + 1) * bw * 128 per two k-blocks: same per k-block)
 }
 
 extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
@@ -1336,7 +1346,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   if (!a || !a->a0 || !a->w || !a->out) { set_error("sdb_gemm_tc: null pointer"); return SDB_ERR_ARG; }
   if (a->Cout <= 0 || a->C0 <= 0) { set_error("sdb_gemm_tc: bad channel counts"); return SDB_ERR_ARG; }
   const int kind = a->kind;
-  if (kind < SDB_GEMM_LINEAR || kind > SDB_GEMM_CONV3X3_S2_PAD_RB) {
+  if (kind < SDB_GEMM_LINEAR || kind > SDB_GEMM_CONV2X2_UP) {
     set_error("sdb_gemm_tc: unknown kind %d", kind);
     return SDB_ERR_ARG;
   }
@@ -1376,15 +1386,29 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     p.a_rank = 5;
     const int NB = a->NB, HI = a->HI, WI = a->WI;
     if (NB <= 0 || HI <= 0 || WI <= 0) { set_error("sdb_gemm_tc: bad conv dims"); return SDB_ERR_ARG; }
-    const bool s2 = (kind != SDB_GEMM_CONV3X3_S1);
+    const bool s2 = (kind == SDB_GEMM_CONV3X3_S2 || kind == SDB_GEMM_CONV3X3_S2_PAD_RB);
+    const bool up = (kind == SDB_GEMM_CONV2X2_UP);
     if (s2 && (a->C1 > 0 || (HI & 1) || (WI & 1))) {
       set_error("sdb_gemm_tc: stride-2 conv needs even H, W and a single source");
       return SDB_ERR_UNSUPPORTED;
     }
+    if (up && (a->up_phase < 0 || a->up_phase > 3 || a->nsplit > 1 || a->residual != nullptr)) {
+      set_error("sdb_gemm_tc: CONV2X2_UP needs up_phase in 0..3, no split-K and no residual");
+      return SDB_ERR_UNSUPPORTED;
+    }
     if (a->C0 % 64 != 0) { set_error("sdb_gemm_tc: conv needs C0 %% 64 == 0"); return SDB_ERR_UNSUPPORTED; }
     p.NB = NB; p.HO = s2 ? HI / 2 : HI; p.WO = s2 ? WI / 2 : WI;
-    p.ntaps = 9;
+    p.ntaps = up ? 4 : 9;
     if (pick_tile_box(p.NB, p.HO, p.WO, &p.bw, &p.bh, &p.bn)) { set_error("tile box"); return SDB_ERR_ARG; }
+    if (up) {
+      p.up = 1; p.up_a = a->up_phase >> 1; p.up_b = a->up_phase & 1;
+      for (int u = 0; u < 2; ++u)
+        for (int v = 0; v < 2; ++v) {
+          const int t = u * 2 + v;
+          p.tap_dc_sel[t] = 0; p.tap_d2[t] = 0;
+          p.tap_dh[t] = (int8_t)(p.up_a - 1 + u); p.tap_dw[t] = (int8_t)(p.up_b - 1 + v);
+        }
+    } else
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         const int t = ky * 3 + kx;
@@ -1487,23 +1511,27 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   {
     static int no_a3 = -1;
     if (no_a3 < 0) { const char* ev = getenv("SDB_NO_A3"); no_a3 = (ev && ev[0] == '1') ? 1 : 0; }
-    const bool ok = !no_a3 && kind == SDB_GEMM_CONV3X3_S1 && p.bn == 1 && p.bw * p.bh == GEMM_BM && p.bw % 8 == 0 &&
+    const int fr = p.up ? 2 : 3;                 // filter rows = filter columns
+    const bool ok = !no_a3 && (kind == SDB_GEMM_CONV3X3_S1 || p.up) && p.bn == 1 && p.bw * p.bh == GEMM_BM && p.bw % 8 == 0 &&
                     a->nsplit <= 1 && ((p.acc_n / cg) % 8 == 0) && a->C0 % 64 == 0 && a->C1 % 64 == 0 &&
                     // long reductions only (main-loop bound; short ones keep the shared memory for the TMA epilogue),
                     // and two stages must fit next to the per-lane epilogue's staging
                     p.nkb_total > 32 &&
-                    2 * std::max((p.bh + 2) * p.bw * 128 + 3 * b_stage_host, 2 * (GEMM_A_STAGE_BYTES + b_stage_host)) +
+                    2 * std::max((p.bh + fr - 1) * p.bw * 128 + fr * b_stage_host, 2 * (GEMM_A_STAGE_BYTES + b_stage_host)) +
                             GEMM_EPI_WARPS * GEMM_EPI_STAGE_BYTES + 1024 + GEMM_BAR_BYTES <= 227 * 1024 &&
                     (a->smem_budget <= 0 || a->smem_budget >= 227 * 1024);
     if (ok) {
       p.a3 = 1;
-      p.a3_box_bytes = (p.bh + 2) * p.bw * 128;
-      p.a3_iters = 3 * p.cblocks + (p.cblocks_x + 1) / 2;
-      p.a3_stage_bytes = p.a3_box_bytes + 3 * b_stage_host;
+      p.a3_nrow = fr; p.a3_ncol = fr;
+      p.a3_h0 = p.up ? p.up_a - 1 : -1;
+      p.a3_w0 = p.up ? p.up_b - 1 : -1;
+      p.a3_box_bytes = (p.bh + fr - 1) * p.bw * 128;
+      p.a3_iters = fr * p.cblocks + (p.cblocks_x + 1) / 2;
+      p.a3_stage_bytes = p.a3_box_bytes + fr * b_stage_host;
       if (p.cblocks_x > 0 && 2 * (GEMM_A_STAGE_BYTES + b_stage_host) > p.a3_stage_bytes)
         p.a3_stage_bytes = 2 * (GEMM_A_STAGE_BYTES + b_stage_host);
       // the main sources are fetched with the taller box; the extra 1x1 source keeps its one-tap boxes
-      uint32_t box3[5] = {64, (uint32_t)p.bw, 1, (uint32_t)(p.bh + 2), 1};
+      uint32_t box3[5] = {64, (uint32_t)p.bw, 1, (uint32_t)(p.bh + fr - 1), 1};
       const uint64_t WI = (uint64_t)a->WI, HI = (uint64_t)a->HI;
       const uint64_t c0b = (uint64_t)a->C0 * 2;
       uint64_t dims[5] = {(uint64_t)a->C0, WI, 1, HI, (uint64_t)a->NB};
@@ -1537,6 +1565,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     const int epi_mode = a->epi_mode;            // 0 auto, 1 never, 2 whenever eligible (also long reductions)
     bool ok = !no_epi_tma && epi_mode != 1 && !want_split && (nkb_all <= 32 || epi_mode == 2);
     if (a->gn_part != nullptr && p.a_rank == 5) ok = false;      // conv outputs: statistics in the per-lane epilogue
+    if (p.up) ok = false;                                        // scattered output rows: per-lane epilogue
     ok = ok && (block_n % 32 == 0 || n_tiles == 1);
     ok = ok && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && (f32o ? (ldo_eff % 4 == 0) : (ldo_eff % 8 == 0));
     if (a->out2) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) & 15u) == 0 && (ldo_eff % 8 == 0);
@@ -1655,6 +1684,8 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     }
     p.gn_part = a->gn_part;
     p.gn_K = K;
+    p.gn_stride = p.up ? 4 * K : K;
+    p.gn_off = p.up ? a->up_phase * K : 0;
     p.gn_hw = a->gn_hw;
     const int plane = p.bw * p.bh;
     p.gn_spq = (p.a_rank == 5) ? (plane / 32 < 4 ? plane / 32 : 4) : 0;

@@ -51,6 +51,10 @@ GN_EPILOGUE_STATS = os.environ.get("SDB_NO_GN_EPI") != "1"
 # shadows of the fp32 stream written with a saturating conversion; the fp32 master tensors are untouched. Every other
 # level, the attention kernels (Q, K, V, P, O), CLIP and the VAE stay bf16. SDB_NO_TOP_F16=1 restores bf16 everywhere.
 TOP_F16 = os.environ.get("SDB_NO_TOP_F16") != "1"
+# Upsample (nearest x2 -> conv3x3, sd/diffusion.py:412-435) as four parity-phase 2x2 convolutions of the LOW-resolution
+# tensor: the 3x3 taps that land on the same input pixel are summed at pack time (fp32, rounded once), so the layer costs
+# 4/9 of the FLOPs and the 4x up-sampled tensor never exists (ops.conv_up2x, SDB_GEMM_CONV2X2_UP).
+FOLD_UPSAMPLE = os.environ.get("SDB_NO_FOLD_UPSAMPLE") != "1"
 BF16, F16 = torch.bfloat16, torch.float16
 
 
@@ -74,6 +78,28 @@ def pack_conv3x3(conv, dev, dtype=torch.bfloat16):
 def pack_conv1x1(conv, dev, dtype=torch.bfloat16):
     w = conv.weight.detach()
     return _bf16(w.reshape(w.shape[0], w.shape[1]), dev, dtype), _f32(conv.bias, dev)
+
+
+def pack_upsample_phases(conv, dev, dtype=torch.bfloat16):
+    """[4][Cout][4 * Cin] weights of the four parity phases of conv3x3(nearest_upsample_x2(.)): output pixel
+    (2y + a, 2x + b) reads input rows (y + a - 1 + u), u = 0, 1, through the filter rows {0} | {1, 2} (a = 0) or
+    {0, 1} | {2} (a = 1) - the same along x with b - so each phase is a 2x2 convolution whose taps are sums of the 3x3
+    taps (summed in fp32, rounded to the operand type once). Phase index = 2a + b, tap order [u][v][Cin]."""
+    w = conv.weight.detach().to(torch.float32)                    # [Cout, Cin, 3, 3]
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    phases = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for u in (0, 1):
+                for v in (0, 1):
+                    acc = torch.zeros_like(w[:, :, 0, 0])
+                    for ky in groups[a][u]:
+                        for kx in groups[b][v]:
+                            acc = acc + w[:, :, ky, kx]
+                    taps.append(acc)                              # [Cout, Cin]
+            phases.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))
+    return torch.stack(phases).to(device=dev, dtype=dtype).contiguous(), _f32(conv.bias, dev)
 
 
 def pack_direct(conv, dev):
@@ -475,7 +501,8 @@ class UNetEngine:
                 elif isinstance(layer, Upsample):
                     # nearest x2 of the block's (lower-level) output, then a conv whose OUTPUT is one level up
                     w, b = pack_conv3x3(layer.conv, dev, dt)
-                    prog.append(["up", NS(w=w, b=b, cout=layer.conv.out_channels, dt=dt), False, dt_out])
+                    w4 = pack_upsample_phases(layer.conv, dev, dt)[0] if FOLD_UPSAMPLE else None
+                    prog.append(["up", NS(w=w, b=b, w4=w4, cout=layer.conv.out_channels, dt=dt), False, dt_out])
                 elif isinstance(layer, torch.nn.Conv2d):
                     if layer.in_channels <= 8:
                         prog.append(["direct", pack_direct(layer, dev), False, dt_out])
@@ -540,10 +567,14 @@ class UNetEngine:
                 x = run_unet_attn(pk, x, next(kv_iter), want_b16=want, out16=o16)
             elif kind == "up":
                 nn_, hh_, ww_, _ = x.shape
-                o = ops.conv3x3(ops.upsample2x(x.b16(pk.dt)), pk.w, pk.cout, bias=pk.b, out_fp32=True,
-                                out2=True if want else None, gn_samples=_gn_samples(nn_, 4 * hh_ * ww_, pk.cout),
-                                out16=o16)
-                x = Stream(*o) if isinstance(o, tuple) else Stream(o)
+                gs = _gn_samples(nn_, 4 * hh_ * ww_, pk.cout)
+                if pk.w4 is not None:
+                    x = Stream(*ops.conv_up2x(x.b16(pk.dt), pk.w4, pk.cout, bias=pk.b, out2=bool(want), gn_samples=gs,
+                                              out16=o16))
+                else:
+                    o = ops.conv3x3(ops.upsample2x(x.b16(pk.dt)), pk.w, pk.cout, bias=pk.b, out_fp32=True,
+                                    out2=True if want else None, gn_samples=gs, out16=o16)
+                    x = Stream(*o) if isinstance(o, tuple) else Stream(o)
             elif kind == "conv":
                 nn_, hh_, ww_, _ = x.shape
                 s2_ = pk.kind != ops.GEMM_CONV3X3_S1

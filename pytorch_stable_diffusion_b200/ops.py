@@ -11,7 +11,7 @@ import torch
 from . import _ext
 from ._ext import AttnArgs, GemmArgs
 
-GEMM_LINEAR, GEMM_CONV3X3_S1, GEMM_CONV3X3_S2, GEMM_CONV3X3_S2_PAD_RB = 0, 1, 2, 3
+GEMM_LINEAR, GEMM_CONV3X3_S1, GEMM_CONV3X3_S2, GEMM_CONV3X3_S2_PAD_RB, GEMM_CONV2X2_UP = 0, 1, 2, 3, 4
 ACT_NONE, ACT_QUICK_GELU, ACT_SILU = 0, 1, 2
 NUM_SMS = 148
 
@@ -139,7 +139,7 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0, a3_bytes=0):
 def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, act=ACT_NONE,
          out=None, out_fp32=False, out2=None, bias_per_row=False, M=None, conv_dims=None, c0=None, c1=0,
          lda0=0, lda1=0, ldw=0, ldo=0, ldr=0, block_n=0, nsplit=0, cta_pair=0, out_f16=False, epi_mode=0,
-         gn_samples=None, ax0=None, ax1=None, out16=None):
+         gn_samples=None, ax0=None, ax1=None, out16=None, up_phase=None, gn_part=None):
     """out = act(A . W^T + bias) + residual through sdb_gemm_tc. See include/sdb200.h.
 
     gn_samples=N: the output is a GroupNorm input of N samples - the epilogue also writes per-slab, per-channel
@@ -183,11 +183,16 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         if c0 is None:
             c0 = a0.shape[-1]
         args.NB, args.HI, args.WI = nb, hi, wi
-        s2 = kind != GEMM_CONV3X3_S1
+        s2 = kind in (GEMM_CONV3X3_S2, GEMM_CONV3X3_S2_PAD_RB)
         ho, wo = (hi // 2, wi // 2) if s2 else (hi, wi)
-        rows = nb * ho * wo
-        ntaps = 9
+        rows = nb * ho * wo                      # CONV2X2_UP: rows of ONE phase (the low-resolution grid)
+        ntaps = 4 if kind == GEMM_CONV2X2_UP else 9
         m_tiles = (rows + 127) // 128
+        if kind == GEMM_CONV2X2_UP:
+            if out is None or up_phase is None:
+                raise ValueError("CONV2X2_UP writes one phase of a caller-allocated [NB, 2H, 2W, Cout] output")
+            args.up_phase = up_phase
+            nsplit = 1
     args.C0, args.C1, args.Cout = c0, c1, cout
     args.lda0, args.lda1, args.ldw, args.ldo, args.ldr = lda0, lda1, ldw, ldo, ldr
     if out is None:
@@ -210,7 +215,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     if block_n == 0 or nsplit == 0:
         ob = (4 if out_fp32 else 2) + (2 if out2 is not None else 0)
         rb = 0 if residual is None else residual.element_size()
-        a3b = lib.sdb_gemm_conv_a3_bytes(*conv_dims) if (kind == GEMM_CONV3X3_S1 and _A3_CHOOSER) else 0
+        a3b = lib.sdb_gemm_conv_a3_bytes(*conv_dims) if (kind in (GEMM_CONV3X3_S1, GEMM_CONV2X2_UP) and _A3_CHOOSER) else 0
         bn_auto, ns_auto = _choose_tiling(rows, cout, nkb, ob, rb, a3b)
         if block_n == 0:
             block_n = bn_auto
@@ -228,7 +233,10 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.out_f16 = 1 if out_f16 else 0
     args.epi_mode = epi_mode
     part = None
-    if gn_samples is not None and (out_fp32 or kind != GEMM_LINEAR) and nsplit == 1 and cout % 32 == 0 \
+    if gn_part is not None:                      # shared partial-sum tensor of the four up-sampling phases
+        part = gn_part
+        args.gn_part = _p(part)
+    elif gn_samples is not None and (out_fp32 or kind != GEMM_LINEAR) and nsplit == 1 and cout % 32 == 0 \
             and block_n % 32 == 0 and ldo == 0:
         hw = rows // gn_samples
         k_slabs = lib.sdb_gemm_gn_slabs(kind, args.NB, args.HI, args.WI, args.M, hw if kind == GEMM_LINEAR else 0)
@@ -247,7 +255,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
                  f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit} "
                  f"ab={'f16' if op16 == torch.float16 else 'bf16'}")
         keep = (a0, a1, w, bias, residual, out, out2, ws, part, ax0, ax1)     # the relaunch closure owns its operands
-        ev = _prof("gemm_tc_conv3x3" if ntaps == 9 else "gemm_tc_linear",
+        ev = _prof("gemm_tc_conv3x3" if ntaps != 1 else "gemm_tc_linear",
                    2.0 * rows * cout * k_total,
                    2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * k_total) + out.numel() * out.element_size()
                    + rows * cout * res_b + (rows * cout * 2 if out2 is not None else 0),
@@ -278,6 +286,25 @@ def conv3x3(x, w, cout, bias=None, kind=GEMM_CONV3X3_S1, **kw):
     if isinstance(out, tuple):
         return out[0].view(shape), out[1].view(shape)
     return out.view(shape)
+
+
+def conv_up2x(x, w4, cout, bias=None, *, out2=False, gn_samples=None, out16=torch.bfloat16, block_n=0):
+    """conv3x3(nearest_upsample_x2(x)) without the up-sampled tensor (Upsample, sd/diffusion.py:412-435): four parity
+    phases, each a 2x2 convolution of the low-resolution x [N, H, W, C] with pre-summed taps (w4: [4][Cout][4*C],
+    engine.pack_upsample_phases). Returns (out fp32 [N, 2H, 2W, Cout], out2 16-bit or None, GroupNorm partials or None)."""
+    lib = _ext.lib()
+    n, h, wd, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * wd, cout), device=x.device, dtype=torch.float32)
+    o2 = torch.empty(out.shape, device=x.device, dtype=out16) if out2 else None
+    part = None
+    if gn_samples is not None and cout % 32 == 0:
+        k = lib.sdb_gemm_gn_slabs(GEMM_CONV2X2_UP, n, h, wd, 0, 0)
+        if k > 0:
+            part = torch.empty((n, 4 * k, cout, 2), device=x.device, dtype=torch.float32)
+    for phase in range(4):
+        gemm(x, w4[phase], cout, kind=GEMM_CONV2X2_UP, bias=bias, conv_dims=(n, h, wd), c0=c, out=out, out_fp32=True,
+             out2=o2, out16=out16, up_phase=phase, gn_part=part, block_n=block_n)
+    return out, o2, part
 
 
 def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, causal=False, vt_ld=0,

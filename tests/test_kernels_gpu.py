@@ -908,3 +908,27 @@ def test_resize_matches_pillow_byte_for_byte(size):
     assert torch.equal(img[0], f)
     u8b, imgb = imageio.load_images([dog, dog.resize((300, 200))], w, h, DEV)
     assert torch.equal(u8b[0], ref) and u8b.shape == (2, h, w, 3) and imgb.shape == (2, h, w, 3)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,dt", [(2, 8, 8, 1280, 1280, torch.bfloat16), (2, 16, 16, 1280, 1280, torch.bfloat16),
+                                               (1, 32, 32, 640, 640, torch.bfloat16), (1, 24, 40, 128, 64, torch.bfloat16),
+                                               (3, 12, 12, 256, 160, torch.float16), (1, 48, 48, 640, 640, torch.float16)])
+def test_conv_up2x_phases(N, H, W, Cin, Cout, dt):
+    """Upsample (nearest x2 -> conv3x3, sd/diffusion.py:412-435) as four parity-phase 2x2 convolutions of the
+    low-resolution input (SDB_GEMM_CONV2X2_UP, ops.conv_up2x) against F.conv2d(F.interpolate(x))."""
+    ops = _ops()
+    setup_exact_fp32()
+    from pytorch_stable_diffusion_b200 import engine
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=1))
+        conv.bias.copy_(rnd(Cout, seed=2))
+        x = rnd(N, H, W, Cin).to(dt)
+        ref = conv(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")).permute(0, 2, 3, 1)
+        w4, b = engine.pack_upsample_phases(conv, DEV, dt)
+        out, out2, part = ops.conv_up2x(x, w4, Cout, bias=b, out2=True, gn_samples=N, out16=dt)
+    assert out.shape == (N, 2 * H, 2 * W, Cout)
+    report(f"conv_up2x {Cin}->{Cout} @{H}x{W} {dt}", out, ref, 1e-2 if dt == torch.bfloat16 else 2e-3)
+    assert out2.dtype == dt and torch.equal(out2, out.to(dt))
+    if part is not None:
+        _check_partials(part, out.reshape(-1, Cout), N, "conv_up2x")
