@@ -45,13 +45,14 @@ H = W = 512
 # K/V excluded). "fold": linear_geglu_2 . linear_geglu_1[:4C] composed into one C x C map at pack time - the saved
 # GEMM FLOPs leave the numerator, as §8d prescribes (token-proportional: x2.25 at 96x96 latents). "upfold": the three
 # Upsample convs (1280 @ 16x16 and 32x32, 640 @ 64x64: 135.9 GFLOP per image-step as the reference executes them) run
-# as four 2x2 phase convolutions of the low-resolution input, 4/9 of the FLOPs: 75.5 GFLOP leave the numerator too.
+# as four 2x2 phase convolutions of the low-resolution input, 4/9 of the FLOPs: 75.5 GFLOP leave the numerator too, and
+# so do 386.5 GFLOP per image of the VAE decoder's three Upsample -> conv pairs (695.8 GFLOP as the reference runs them).
 WORKLOADS = {
-    1: {"hw": 512, "unet_gflop": 1498.25, "fold_gflop": 179.1, "upfold_gflop": 75.5, "vae_gflop": 2514.52,
+    1: {"hw": 512, "unet_gflop": 1498.25, "fold_gflop": 179.1, "upfold_gflop": 75.5, "vae_gflop": 2514.52, "vae_upfold_gflop": 386.5,
         "name": "configs[1]: SD1.5-arch random-init txt2img 512x512 (4x64x64 latent)"},
-    3: {"hw": 512, "unet_gflop": 1498.25, "fold_gflop": 179.1, "upfold_gflop": 75.5, "vae_gflop": 2514.52,
+    3: {"hw": 512, "unet_gflop": 1498.25, "fold_gflop": 179.1, "upfold_gflop": 75.5, "vae_gflop": 2514.52, "vae_upfold_gflop": 386.5,
         "name": "configs[3]: SD1.5-arch random-init txt2img 512x512, batch 64 sharded by seed across the ranks"},
-    4: {"hw": 768, "unet_gflop": 4060.02, "fold_gflop": 179.1 * 2.25, "upfold_gflop": 75.5 * 2.25, "vae_gflop": 5754.30,
+    4: {"hw": 768, "unet_gflop": 4060.02, "fold_gflop": 179.1 * 2.25, "upfold_gflop": 75.5 * 2.25, "vae_gflop": 5754.30, "vae_upfold_gflop": 386.5 * 2.25,
         "name": "configs[4]: SD1.5-arch random-init txt2img 768x768 (4x96x96 latent, 9216-token self-attention)"},
 }
 CLIP_GFLOP_PER_PROMPT = 13.30
@@ -292,7 +293,7 @@ def main():
     metric = METRIC if H == 512 else f"{H}x{W} txt2img images/s (50-step DDPM, CFG 7.5)"
     UNET_GFLOP_PER_IMAGE_STEP = wl["unet_gflop"] - (wl["fold_gflop"] if engine.FOLD_GEGLU else 0.0) - (
         wl["upfold_gflop"] if engine.FOLD_UPSAMPLE else 0.0)
-    VAE_GFLOP_PER_IMAGE = wl["vae_gflop"]
+    VAE_GFLOP_PER_IMAGE = wl["vae_gflop"] - (wl["vae_upfold_gflop"] if engine.FOLD_UPSAMPLE else 0.0)
     if args.config == 3:
         if 64 % world:
             raise SystemExit("bench.py --config 3: 64 images do not split evenly over this many ranks")

@@ -466,7 +466,7 @@ def _reads_bf16(kind, pk):
     """Does program entry (kind, pk) read its stream input as a bf16 tensor-core operand?"""
     if kind == "res":
         return pk.skip_w is not None
-    return kind in ("up", "conv", "conv1", "attn_vae")
+    return kind in ("up", "upconv", "conv", "conv1", "attn_vae")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -621,7 +621,11 @@ def _pack_vae_sequential(seq, dev, pad_rb):
                 kind = ops.GEMM_CONV3X3_S1
                 if layer.stride[0] == 2:
                     kind = ops.GEMM_CONV3X3_S2_PAD_RB if pad_rb else ops.GEMM_CONV3X3_S2
-                prog.append(["conv", NS(w=w, b=b, cout=layer.out_channels, kind=kind), False])
+                w4 = None
+                if (FOLD_UPSAMPLE and kind == ops.GEMM_CONV3X3_S1 and prog and prog[-1][0] == "up"
+                        and layer.in_channels % 64 == 0):
+                    w4 = pack_upsample_phases(layer, dev)[0]
+                prog.append(["conv", NS(w=w, b=b, w4=w4, cout=layer.out_channels, kind=kind), False])
         elif isinstance(layer, torch.nn.Upsample):
             prog.append(["up", None, False])
         elif isinstance(layer, torch.nn.GroupNorm):
@@ -630,12 +634,17 @@ def _pack_vae_sequential(seq, dev, pad_rb):
             prog.append(["silu", None, False])
         else:
             raise TypeError(f"unexpected layer {type(layer)}")
-    # GroupNorm followed by SiLU is one kernel
+    # GroupNorm followed by SiLU is one kernel; nn.Upsample(scale_factor=2) followed by a stride-1 3x3 conv
+    # (sd/decoder.py:269-273, 295-299, 321-325) is four parity-phase 2x2 convolutions of the low-resolution tensor
     fused = []
     i = 0
     while i < len(prog):
         if prog[i][0] == "gn" and i + 1 < len(prog) and prog[i + 1][0] == "silu":
             fused.append(["gn_silu", prog[i][1], False])
+            i += 2
+        elif (FOLD_UPSAMPLE and prog[i][0] == "up" and i + 1 < len(prog) and prog[i + 1][0] == "conv"
+              and prog[i + 1][1].kind == ops.GEMM_CONV3X3_S1 and prog[i + 1][1].w4 is not None):
+            fused.append(["upconv", prog[i + 1][1], False])
             i += 2
         else:
             fused.append(prog[i])
@@ -665,6 +674,9 @@ def _run_vae_sequential(prog, x):
             src = x.bf16() if isinstance(x, Stream) else x
             o = ops.conv3x3(src, pk.w, pk.cout, bias=pk.b, kind=pk.kind, out_fp32=True, out2=o2)
             x = Stream(*o) if isinstance(o, tuple) else Stream(o)
+        elif kind == "upconv":
+            o, ob, _ = ops.conv_up2x(x.bf16(), pk.w4, pk.cout, bias=pk.b, out2=bool(want))
+            x = Stream(o, ob)
         elif kind == "up":
             x = ops.upsample2x(x.bf16())        # bf16 tensor: the next entry is a conv reading it
         elif kind == "gn_silu":
