@@ -258,6 +258,11 @@ int sdb_resample_u8(const unsigned char* src, unsigned char* dst, float* img, in
 int sdb_clip_embed(const long long* tokens, const float* table, const float* pos, void* out, int NB,
                    int T, int T_pad, int D, int vocab, void* stream);
 
+/* Stream-ordered device-to-device copy (a memcpy node under graph capture). Duplicates the part of a UNet evaluation
+ * that the two members of a classifier-free-guidance pair share - everything before the first cross-attention, since
+ * both see the same latent and time step (sd/pipeline.py:221: latents.repeat(2, 1, 1, 1)). */
+int sdb_copy_bytes(void* dst, const void* src, long long bytes, void* stream);
+
 /* Pack-time helper (model load, not the sampling loop): C[M, N] = A[M, K] . B[K, N], row-major, A / B fp32 (or fp64
  * when a_f64 / b_f64), C fp64, accumulated in fp64 on the CUDA cores. Composes the reference's feed-forward
  * linear_geglu_2 . linear_geglu_1[:4C] (no non-linearity in between: the GEGLU gate is dead, sd/diffusion.py:359-363)

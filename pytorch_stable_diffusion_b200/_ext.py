@@ -76,6 +76,7 @@ SIGNATURES = {
     "sdb_clip_embed": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "sdb_resample_u8": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                         c_void_p],
+    "sdb_copy_bytes": [c_void_p, c_void_p, c_ll, c_void_p],
     "sdb_matmul_f64": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
 }
 _RESTYPES = {"sdb_last_error": ctypes.c_char_p, "sdb_launch_count": ctypes.c_ulonglong,

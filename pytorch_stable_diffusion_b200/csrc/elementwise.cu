@@ -706,3 +706,13 @@ extern "C" int sdb_resample_u8(const unsigned char* src, unsigned char* dst, flo
                                                                     coef, ksize);
   return check_launch("resample_u8_kernel");
 }
+
+// Device-to-device copy as a stream-ordered memcpy node (legal under CUDA-graph capture): duplicating the shared prefix
+// of a classifier-free-guidance pair (engine.UNetEngine.forward_nhwc, cfg_pairs).
+extern "C" int sdb_copy_bytes(void* dst, const void* src, long long bytes, void* stream) {
+  using namespace sdb;
+  if (!dst || !src || bytes <= 0) { set_error("sdb_copy_bytes: bad arguments"); return SDB_ERR_ARG; }
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, SDB_STREAM);
+  if (e != cudaSuccess) { set_error("sdb_copy_bytes: %s", cudaGetErrorString(e)); return SDB_ERR_CUDA; }
+  return SDB_OK;
+}

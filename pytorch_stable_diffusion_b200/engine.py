@@ -55,6 +55,9 @@ TOP_F16 = os.environ.get("SDB_NO_TOP_F16") != "1"
 # tensor: the 3x3 taps that land on the same input pixel are summed at pack time (fp32, rounded once), so the layer costs
 # 4/9 of the FLOPs and the 4x up-sampled tensor never exists (ops.conv_up2x, SDB_GEMM_CONV2X2_UP).
 FOLD_UPSAMPLE = os.environ.get("SDB_NO_FOLD_UPSAMPLE") != "1"
+# Classifier-free guidance feeds the UNet the same latent twice (cond / uncond differ only in the text context): the part
+# of the network before the first cross-attention is evaluated once per pair (UNetEngine._shared_cfg_prefix).
+SHARE_CFG_PREFIX = os.environ.get("SDB_NO_SHARE_CFG_PREFIX") != "1"
 BF16, F16 = torch.bfloat16, torch.float16
 
 
@@ -375,17 +378,18 @@ def context_kv(pk, ctx_pad):
     return k, vt
 
 
-def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
-    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is fp32."""
-    dt = pk.dt
+def unet_attn_prefix(pk, x):
+    """UNET_AttentionBlock.forward up to (and including) the self-attention residual: GroupNorm, conv_input,
+    LayerNorm, self-attention, out_proj (sd/diffusion.py:271-326). Nothing here depends on the text context - for a
+    classifier-free-guidance pair this half of the block is the same for both members. Returns the fp32 token stream
+    t1 [n*s, c]."""
     n, h, w, c = x.shape
     s = h * w
     m = n * s
     d = c // pk.heads
     dev = x.f.device
-    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp, out_dtype=dt)
+    a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp, out_dtype=pk.dt)
     t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=True)
-    # self-attention
     l1 = ops.layernorm(t0, *pk.ln1)
     qk = ops.linear(l1, pk.wqk, bias=pk.bqk)
     vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
@@ -395,8 +399,18 @@ def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
     ops.attention(qk, qk[:, cq:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
                   ldq=2 * cq, ldk=2 * cq, ldo=c, sum_row=pk.vt_rows > 0, q_prescaled=pk.vt_rows > 0,
                   qk_cols=pk.qk_cols, qk_fold=fold)
-    t1 = ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
-    # cross-attention over the CLIP tokens
+    return ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
+
+
+def unet_attn_suffix(pk, x, t1, kv, want_b16=False, out16=torch.bfloat16):
+    """The rest of UNET_AttentionBlock.forward (sd/diffusion.py:328-381): cross-attention over the CLIP tokens,
+    feed-forward, conv_output, + block input x. t1: fp32 token stream after the self-attention, same batch as x."""
+    dt = pk.dt
+    n, h, w, c = x.shape
+    s = h * w
+    m = n * s
+    d = c // pk.heads
+    dev = x.f.device
     l2 = ops.layernorm(t1, *pk.ln2)
     q = ops.linear(l2, pk.wq2, bias=pk.bq2)
     k2, vt2 = kv
@@ -421,6 +435,11 @@ def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
     out = ops.linear(t3, pk.cout_w, bias=pk.cout_b, residual=x.f.view(m, c), out_fp32=True,
                      out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c), out16=out16)
     return _stream(out, (n, h, w, c))
+
+
+def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
+    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is fp32."""
+    return unet_attn_suffix(pk, x, unet_attn_prefix(pk, x), kv, want_b16=want_b16, out16=out16)
 
 
 def run_vae_attn(pk, x, want_b16=False):
@@ -558,6 +577,10 @@ class UNetEngine:
         ctx[:, :t] = context.to(device=self.dev, dtype=torch.bfloat16)
         return [context_kv(pk, ctx) for pk in self.attn_blocks]
 
+    def _prefix_shareable(self):
+        e = self.encoders
+        return len(e) > 2 and [k for k, *_ in e[0]] == ["direct"] and [k for k, *_ in e[1]] == ["res", "attn"]
+
     def _run_seq(self, prog, x, x1, tvec, kv_iter):
         for kind, pk, want, o16 in prog:
             if kind == "res":
@@ -587,12 +610,38 @@ class UNetEngine:
                 x = Stream(*o) if isinstance(o, tuple) else Stream(o)
         return x
 
-    def forward_nhwc(self, x, tvec, kvs):
+    def _shared_cfg_prefix(self, x, tvec, kv_iter):
+        """encoders.0 and encoders.1 for a batch whose second half repeats the first (classifier-free guidance:
+        latents.repeat(2, 1, 1, 1), sd/pipeline.py:221, one time step for all): everything before the first
+        cross-attention - the stem conv, the first resblock, GroupNorm / conv_input / LayerNorm / SELF-attention /
+        out_proj of the first attention block - sees identical inputs in both halves, so it runs once on B samples
+        and is duplicated (three device copies) where the text context first enters. Per step at batch 8: one
+        S = 4096 self-attention, two 320 -> 320 convs and their norms for 8 instead of 16 samples."""
+        b = x.shape[0] // 2
+        s0 = self._run_seq(self.encoders[0], x[:b], None, tvec, kv_iter)           # Stream [B, h, w, 320]
+        (k_res, pk_res, want_res, o16_res), (k_att, pk_att, want_att, o16_att) = self.encoders[1]
+        r = run_resblock(pk_res, s0, None, tvec[pk_res.time_off:pk_res.time_off + pk_res.cout], want_b16=want_res,
+                         out16=o16_res)
+        t1 = unet_attn_prefix(pk_att, r)
+        r2 = Stream(ops.repeat2(r.f))                                               # block input: residual of conv_output
+        x1 = unet_attn_suffix(pk_att, r2, ops.repeat2(t1), next(kv_iter), want_b16=want_att, out16=o16_att)
+        skip0 = Stream(ops.repeat2(s0.f), ops.repeat2(s0.b) if s0.b is not None else None,
+                       ops.repeat2(s0.gp) if s0.gp is not None else None)
+        return skip0, x1
+
+    def forward_nhwc(self, x, tvec, kvs, cfg_pairs=False):
         """x fp32 (or bf16) NHWC [N, h, w, 4]; tvec fp32 [sum(Cout)] (one row of time_vectors); returns eps fp32
-        NHWC [N, h, w, 4]. UNET.forward sd/diffusion.py:628-676 without materialising torch.cat."""
+        NHWC [N, h, w, 4]. UNET.forward sd/diffusion.py:628-676 without materialising torch.cat.
+        cfg_pairs=True: the caller guarantees x[N/2:] == x[:N/2] (the pipeline's CFG batch) - the context-independent
+        prefix of the network is then evaluated once (see _shared_cfg_prefix)."""
         kv_iter = iter(kvs)
         skips = []
-        for prog in self.encoders:
+        encoders = self.encoders
+        if cfg_pairs and SHARE_CFG_PREFIX and x.shape[0] % 2 == 0 and self._prefix_shareable():
+            skip0, x = self._shared_cfg_prefix(x, tvec, kv_iter)
+            skips += [skip0, x]
+            encoders = self.encoders[2:]
+        for prog in encoders:
             x = self._run_seq(prog, x, None, tvec, kv_iter)
             skips.append(x)
         x = self._run_seq(self.bottleneck, x, None, tvec, kv_iter)

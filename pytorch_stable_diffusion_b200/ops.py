@@ -577,3 +577,16 @@ def matmul_f64(a, b):
     _ext.check(lib.sdb_matmul_f64(_p(a), 1 if a.dtype == torch.float64 else 0, _p(b), 1 if b.dtype == torch.float64 else 0,
                                   _p(out), m, n, k, _stream()), "sdb_matmul_f64")
     return out
+
+
+def repeat2(x):
+    """[B, ...] -> [2B, ...] with both halves equal to x (two stream-ordered device copies): the classifier-free-
+    guidance pair of a tensor computed once."""
+    lib = _ext.lib()
+    x = x.contiguous()
+    out = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    nbytes = x.numel() * x.element_size()
+    for half in range(2):
+        _ext.check(lib.sdb_copy_bytes(ctypes.c_void_p(out.data_ptr() + half * nbytes), _p(x), nbytes, _stream()),
+                   "sdb_copy_bytes")
+    return out

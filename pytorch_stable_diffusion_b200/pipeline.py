@@ -120,7 +120,7 @@ class _Loop:
 
     def run_steps(self, trace=None, timesteps=None):
         for i in range(self.n_steps):
-            eps = self.eng.forward_nhwc(self.x_in, self.tvecs[i], self.kvs)
+            eps = self.eng.forward_nhwc(self.x_in, self.tvecs[i], self.kvs, cfg_pairs=self.do_cfg)
             if trace is not None:
                 trace.append((int(timesteps[i]), self.latents.clone(), ops.nhwc_to_nchw_f32(eps)))
             ops.cfg_ddpm_step(self.latents, eps, self.noise[i], self.coef, i, self.cfg_scale, self.do_cfg,
@@ -128,7 +128,7 @@ class _Loop:
 
     def capture(self):
         # one eager UNet evaluation first: lazy CUDA/module initialisation must not happen under capture
-        self.eng.forward_nhwc(self.x_in, self.tvecs[0], self.kvs)
+        self.eng.forward_nhwc(self.x_in, self.tvecs[0], self.kvs, cfg_pairs=self.do_cfg)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         n0 = _ext.launch_count()

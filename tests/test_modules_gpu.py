@@ -378,3 +378,30 @@ def test_command_line_front_end(tmp_path):
     for i in range(2):
         im = Image.open(str(tmp_path / f"img_{i}.png"))
         assert im.size == (512, 512) and im.mode == "RGB"
+
+
+def test_cfg_pair_shares_the_context_independent_prefix(models, weights, oracle):
+    """engine.UNetEngine.forward_nhwc(cfg_pairs=True): encoders.0, the first resblock and the first self-attention run
+    once per classifier-free-guidance pair (both members see the same latent and time step, sd/pipeline.py:221).
+    Same result as the full evaluation to rounding (the batch of the shared kernels differs, hence their tiling), and
+    within tolerance of the oracle."""
+    from pytorch_stable_diffusion_b200 import ops
+    from pytorch_stable_diffusion_b200.pipeline import get_time_embedding
+    gen = torch.Generator().manual_seed(77)
+    lat = torch.randn(3, 4, 32, 32, generator=gen).to(DEV)
+    ctx = torch.randn(6, 77, 768, generator=gen).to(DEV)
+    temb = get_time_embedding(420).to(DEV)
+    with torch.no_grad():
+        eng = models["diffusion"]._engine()
+        tvec = eng.time_vectors(temb)[0]
+        kvs = eng.context_kv(ctx)
+        x = ops.nchw_to_nhwc(lat, repeat=2, out_fp32=True)
+        n0 = ops._ext.launch_count()
+        full = ops.nhwc_to_nchw_f32(eng.forward_nhwc(x, tvec, kvs))
+        n1 = ops._ext.launch_count()
+        shared = ops.nhwc_to_nchw_f32(eng.forward_nhwc(x, tvec, kvs, cfg_pairs=True))
+        n2 = ops._ext.launch_count()
+        ref = oracle.diffusion_forward(weights["diffusion"], lat.repeat(2, 1, 1, 1), ctx, temb)
+    report("UNet with shared CFG prefix vs oracle", shared, ref, TOL)
+    report("UNet with shared CFG prefix vs full evaluation", shared, full, 4e-3)
+    print(f"[shared CFG prefix] kernel launches: full {n1 - n0}, shared {n2 - n1} (+ 5 device copies)", flush=True)
