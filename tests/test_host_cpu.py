@@ -292,3 +292,53 @@ def test_seed_sharding_and_gather_world_size_2_gloo(n_total):
     assert res[0][1] + res[1][1] == seeds                       # disjoint, ordered, complete
     for _, _, gathered in res:
         assert gathered == [s % 256 for s in seeds]             # every rank sees all images in seed order
+
+
+# ------------------------------------------------------------------------------------ pack-time algebra (CPU)
+def test_upsample_phase_weights_reproduce_upsample_then_conv():
+    """engine.pack_upsample_phases: conv3x3(nearest_upsample_x2(x)) == four parity-phase 2x2 convolutions of x with the
+    3x3 taps that land on the same input pixel summed (sd/diffusion.py:412-435) - checked in fp32 on the CPU."""
+    import torch.nn.functional as F
+    from pytorch_stable_diffusion_b200 import engine
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(8, 6, 3, padding=1)
+    x = torch.randn(2, 8, 5, 7)
+    with torch.no_grad():
+        ref = conv(F.interpolate(x, scale_factor=2, mode="nearest"))
+        w4, b = engine.pack_upsample_phases(conv, "cpu", torch.float32)
+        out = torch.zeros_like(ref)
+        xp = F.pad(x, (1, 1, 1, 1))
+        for a in (0, 1):
+            for bb in (0, 1):
+                w = w4[2 * a + bb].view(6, 2, 2, 8).permute(0, 3, 1, 2)          # [Cout, Cin, u, v]
+                out[:, :, a::2, bb::2] = F.conv2d(xp[:, :, a:a + 6, bb:bb + 8], w) + b.view(1, -1, 1, 1)
+    assert float((out - ref).abs().max()) < 1e-5
+
+
+def test_resample_tables_reproduce_pillow():
+    """imageio.resample_tables (the taps sdb_resample_u8 runs on the device) evaluated in numpy against
+    PIL.Image.resize on the reference's test image: byte-exact for up- and down-sampling."""
+    import numpy as np
+    from PIL import Image
+    from pytorch_stable_diffusion_b200 import imageio
+    g = golden("img2img_5.pt")
+    if g is None:
+        pytest.skip("img2img golden (holds dog.jpg) not generated")
+    img = g["input"].numpy()
+    dog = Image.fromarray(img)
+
+    def one_pass(a, out_size, axis):
+        bounds, coef = imageio.resample_tables(a.shape[axis], out_size)
+        src = np.moveaxis(a, axis, 0).astype(np.int64)
+        out = np.zeros((out_size,) + src.shape[1:], np.int64)
+        for o in range(out_size):
+            lo, cnt = bounds[o]
+            acc = np.full(src.shape[1:], 1 << 21, np.int64)
+            for k in range(cnt):
+                acc += src[lo + k] * int(coef[o, k])
+            out[o] = np.clip(acc >> 22, 0, 255)
+        return np.moveaxis(out, 0, axis).astype(np.uint8)
+
+    for w, h in ((768, 768), (300, 200), (1024, 520)):
+        got = one_pass(one_pass(img, w, 1), h, 0)
+        assert np.array_equal(got, np.array(dog.resize((w, h)))), (w, h)
