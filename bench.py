@@ -539,12 +539,16 @@ def main():
             # (the problem size with the most FLOPs per evaluation first, full resolution winning ties - 320 -> 320 @
             # 64x64, nine launches per evaluation - then its most expensive launch variant: a stable choice)
             convs = [kv for kv in fam("gemm_tc_conv3x3") if kv[1]["flops"] / max(kv[1]["bytes"], 1.0) >= ridge]
-            size_of = lambda kv: " ".join(kv[0][1].split()[:4])          # rows= cin= cout= taps=
+            # a problem size = (cin, cout, taps, output pixels per sample): the shared CFG prefix runs two of the
+            # 320 -> 320 @ 64x64 convs on half the batch, they are the same problem
+            size_of = lambda kv: " ".join(t for t in kv[0][1].split() if t.split("=")[0] in ("cin", "cout", "taps", "hw"))
             by_size = {}
-            for kv in convs:     # rank problem sizes by their FLOPs per evaluation, then by rows: no timing noise in the choice
-                rows_ = int(kv[0][1].split()[0].split("=")[1])
-                fl_, _ = by_size.get(size_of(kv), (0.0, rows_))
-                by_size[size_of(kv)] = (fl_ + kv[1]["flops"], rows_)
+            for kv in convs:     # rank problem sizes by their FLOPs per evaluation (rounded to 1 %: the 64x64, 32x32 and
+                # 16x16 levels tie exactly), then by resolution: no timing noise in the choice
+                hw_ = int(dict(t.split("=") for t in kv[0][1].split())["hw"])
+                fl_, _ = by_size.get(size_of(kv), (0.0, hw_))
+                by_size[size_of(kv)] = (fl_ + kv[1]["flops"], hw_)
+            by_size = {k: (round(v[0] / 1e10), v[1]) for k, v in by_size.items()}
             dom_size = max(by_size, key=by_size.get) if by_size else None
             k_conv = top([kv for kv in convs if size_of(kv) == dom_size])
             k_attn = top(fam("attention"))

@@ -253,7 +253,8 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         shape = (f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps} cx={cx0 + cx1} "
                  f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={('f32', 'bf16')[res_b == 2] if res_b else 'none'} "
                  f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit} "
-                 f"ab={'f16' if op16 == torch.float16 else 'bf16'}")
+                 f"ab={'f16' if op16 == torch.float16 else 'bf16'}"
+                 + (f" hw={rows // conv_dims[0]}" if conv_dims is not None else ""))
         keep = (a0, a1, w, bias, residual, out, out2, ws, part, ax0, ax1)     # the relaunch closure owns its operands
         ev = _prof("gemm_tc_conv3x3" if ntaps != 1 else "gemm_tc_linear",
                    2.0 * rows * cout * k_total,
