@@ -157,8 +157,8 @@ typedef struct sdb_attn_args {
 int sdb_attention(const sdb_attn_args* args, void* stream);
 
 /* ---- normalisation (HBM-bound) ------------------------------------------------------------ */
-/* GroupNorm statistics over NHWC x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0), each bf16 or
- * fp32 (x?_fp32). Deterministic: every thread block writes its per-group partial {sum, sum of squares}
+/* GroupNorm statistics over NHWC x0 (C0 channels) ++ x1 (C1 channels, may be NULL/0), each bf16 (x?_fp32 = 0),
+ * fp32 (1) or IEEE half (2). Deterministic: every thread block writes its per-group partial {sum, sum of squares}
  * (fp64) into `stats`, a caller-provided buffer of sdb_groupnorm_stats_bytes(NB, groups) bytes that
  * needs no initialisation; sdb_groupnorm_apply (same NB, HW, C0, C1, groups) adds the partials in a
  * fixed order. nn.GroupNorm: sd/diffusion.py:123,133,255,708; sd/decoder.py:107,116,330;

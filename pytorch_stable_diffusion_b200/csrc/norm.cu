@@ -1,5 +1,6 @@
 // HBM-bound normalisation kernels: GroupNorm (statistics + apply[+SiLU]), LayerNorm, row softmax.
 // All reductions are fp32 per thread and fp64 across threads/blocks; activations are bf16 NHWC.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "host.h"
 #include "../../include/sdb200.h"
@@ -17,16 +18,25 @@ __device__ __forceinline__ uint4 pack8(const float* f, int f16 = 0) {
   return u;
 }
 
-// 8 consecutive channels of one pixel from a bf16 or fp32 tensor.
+// 8 consecutive channels of one pixel from a bf16 (is_fp32 = 0), fp32 (1) or IEEE-half (2) tensor.
 __device__ __forceinline__ void load8(const void* base, long long elem_off, int is_fp32, float* f) {
-  if (is_fp32) {
+  if (is_fp32 == 1) {
     const float* p = reinterpret_cast<const float*>(base) + elem_off;
     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
     const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   } else {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
-    unpack8(u, f);
+    if (is_fp32 == 2) {            // input kind 2: IEEE half
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = v.x; f[2 * i + 1] = v.y;
+      }
+    } else {
+      unpack8(u, f);
+    }
   }
 }
 
@@ -774,7 +784,7 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
   const int warps = 8;
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
                          reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15u) == 0;
-  if (in_fp32 && aligned && C % 4 == 0 && C <= 1280) {
+  if (in_fp32 == 1 && aligned && C % 4 == 0 && C <= 1280) {
     const int vpl = (C / 4 + 31) / 32;
     long long blocks = ((rows + 1) / 2 + warps - 1) / warps;
     const long long cap = 148LL * 8;

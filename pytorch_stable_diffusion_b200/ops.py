@@ -349,8 +349,9 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     one-pass kernel (fused=None: when supported; True: required; False: never)."""
     o16 = 1 if out_dtype == torch.float16 else 0
     lib = _ext.lib()
-    f0 = 1 if x0.dtype == torch.float32 else 0
-    f1 = 1 if (x1 is not None and x1.dtype == torch.float32) else 0
+    kind_of = {torch.float32: 1, torch.bfloat16: 0, torch.float16: 2}      # input kinds of the norm kernels
+    f0 = kind_of[x0.dtype]
+    f1 = kind_of[x1.dtype] if x1 is not None else 0
     n = x0.shape[0]
     c0 = x0.shape[-1]
     hw = x0.numel() // (n * c0)
@@ -386,7 +387,7 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
                                                1 if have_parts else 0, o16, _stream()), "sdb_groupnorm_apply")
         passes, form = (1.0, "epilogue-stats+apply") if have_parts else (2.0, "stats+apply")
     ev = _prof("groupnorm", 0.0, passes * in_bytes + 2.0 * (nel0 + nel1),
-               shape=f"n={n} hw={hw} c0={c0} c1={c1} in={'f32' if f0 else 'bf16'} silu={int(silu)} {form}",
+               shape=f"n={n} hw={hw} c0={c0} c1={c1} in={('bf16', 'f32', 'f16')[f0]} silu={int(silu)} {form}",
                relaunch=launch)
     launch()
     _prof_end(ev)

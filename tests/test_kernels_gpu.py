@@ -861,6 +861,9 @@ def test_half_outputs_of_norms_and_shadows():
         y = ops.groupnorm(x, g, be, silu=True, fused=fused, out_dtype=torch.float16)
         assert y.dtype == torch.float16
         report(f"groupnorm half out fused={fused}", y, ref, 1.5e-3)
+    xh = x.half()                                                              # IEEE-half INPUT (the resblock's hidden tensor)
+    refh = F.silu(F.group_norm(xh.float().permute(0, 3, 1, 2), 32, g, be, 1e-5)).permute(0, 2, 3, 1)
+    report("groupnorm half in (stats + apply)", ops.groupnorm(xh, g, be, silu=True, fused=False), refh, 6e-3)
     xl = rnd(4096, 320, seed=4)
     y = ops.layernorm(xl, g, be, out_dtype=torch.float16)
     assert y.dtype == torch.float16
