@@ -407,50 +407,38 @@ __global__ void __launch_bounds__(256) gn_reduce_partials_kernel(const float* __
                                                                  int C1, int groups) {
   pdl_trigger();
   pdl_wait();
-  // block = (32 channel lanes, 8 slab lanes): every load is independent of the others (the kernel is a latency
-  // chain otherwise - 10 dependent L2 round trips per thread in its first form), four slabs in flight per thread
+  // The (slab, channel) pairs of this group are one flat index space walked by all 256 threads, four independent
+  // loads in flight per thread: neighbouring threads read neighbouring channels of one slab row (8 B each), and a
+  // group of 4 channels x 2048 slabs (the VAE at 512 x 512) costs 8 L2 round trips per thread, not 64 on 32 threads
+  // (the first layout - 32 channel lanes x 8 slab lanes - left 7/8 of the block idle there: 281 us per launch).
   const int g = blockIdx.x, n = blockIdx.y;
-  const int cx = threadIdx.x & 31, ky = threadIdx.x >> 5;
+  const int t = threadIdx.x;
+  const int cx = t & 31, ky = t >> 5;
   const int cpg = (C0 + C1) / groups;
   const int cbeg = g * cpg, cend = cbeg + cpg;
   // channels of this group in source 0: [cbeg, min(cend, C0)); in source 1: [max(cbeg, C0) - C0, cend - C0)
   const int n0 = max(0, min(cend, C0) - cbeg), n1 = cpg - n0;
   double ds = 0.0, dq = 0.0;
-  for (int cc = cx; cc < n0; cc += 32) {
-    const float* base = part0 + ((long long)n * K0 * C0 + cbeg + cc) * 2;
-    int k = ky;
-    for (; k + 24 < K0; k += 32) {
-      const float2 v0 = *reinterpret_cast<const float2*>(base + (long long)k * C0 * 2);
-      const float2 v1 = *reinterpret_cast<const float2*>(base + (long long)(k + 8) * C0 * 2);
-      const float2 v2 = *reinterpret_cast<const float2*>(base + (long long)(k + 16) * C0 * 2);
-      const float2 v3 = *reinterpret_cast<const float2*>(base + (long long)(k + 24) * C0 * 2);
+  auto walk = [&](const float* base, int nch, int K, int C) {
+    // base -> [K][C][2] of this sample, already offset to the group's first channel in this source
+    const int tot = nch * K;
+    auto at = [&](int i) {
+      const int k = i / nch, cc = i - k * nch;
+      return *reinterpret_cast<const float2*>(base + ((long long)k * C + cc) * 2);
+    };
+    int i = t;
+    for (; i + 768 < tot; i += 1024) {
+      const float2 v0 = at(i), v1 = at(i + 256), v2 = at(i + 512), v3 = at(i + 768);
       ds += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
       dq += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
     }
-    for (; k < K0; k += 8) {
-      const float2 v = *reinterpret_cast<const float2*>(base + (long long)k * C0 * 2);
+    for (; i < tot; i += 256) {
+      const float2 v = at(i);
       ds += (double)v.x; dq += (double)v.y;
     }
-  }
-  if (n1 > 0) {
-    const int c1beg = max(cbeg, C0) - C0;
-    for (int cc = cx; cc < n1; cc += 32) {
-      const float* base = part1 + ((long long)n * K1 * C1 + c1beg + cc) * 2;
-      int k = ky;
-      for (; k + 24 < K1; k += 32) {
-        const float2 v0 = *reinterpret_cast<const float2*>(base + (long long)k * C1 * 2);
-        const float2 v1 = *reinterpret_cast<const float2*>(base + (long long)(k + 8) * C1 * 2);
-        const float2 v2 = *reinterpret_cast<const float2*>(base + (long long)(k + 16) * C1 * 2);
-        const float2 v3 = *reinterpret_cast<const float2*>(base + (long long)(k + 24) * C1 * 2);
-        ds += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
-        dq += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
-      }
-      for (; k < K1; k += 8) {
-        const float2 v = *reinterpret_cast<const float2*>(base + (long long)k * C1 * 2);
-        ds += (double)v.x; dq += (double)v.y;
-      }
-    }
-  }
+  };
+  if (n0 > 0) walk(part0 + ((long long)n * K0 * C0 + cbeg) * 2, n0, K0, C0);
+  if (n1 > 0) walk(part1 + ((long long)n * K1 * C1 + (max(cbeg, C0) - C0)) * 2, n1, K1, C1);
   __shared__ double sh[2][8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
