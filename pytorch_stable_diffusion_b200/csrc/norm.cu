@@ -110,12 +110,63 @@ __global__ void gn_stats_kernel(const void* __restrict__ x0, const void* __restr
   }
 }
 
-__global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
-                                const double* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
-                                long long HW, int C0, int C1, int groups, float eps, int silu,
-                                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32,
-                                int stat_chunks, int out_f16) {
+// raw (unconverted) 8-channel vector of one pixel: one 16-byte word for a 16-bit source, two for fp32
+template <bool ALL16> struct GnRaw { uint4 a; uint4 b; };
+template <> struct GnRaw<true> { uint4 a; };
+
+template <bool ALL16>
+__device__ __forceinline__ void gn_raw_load(GnRaw<ALL16>& r, const char* base, unsigned elem_off, int kind) {
+  if constexpr (ALL16) {
+    r.a = __ldg(reinterpret_cast<const uint4*>(base + (size_t)elem_off * 2u));
+  } else {
+    if (kind == 1) {
+      const uint4* q = reinterpret_cast<const uint4*>(base + (size_t)elem_off * 4u);
+      r.a = __ldg(q);
+      r.b = __ldg(q + 1);
+    } else {
+      r.a = __ldg(reinterpret_cast<const uint4*>(base + (size_t)elem_off * 2u));
+    }
+  }
+}
+
+template <bool ALL16>
+__device__ __forceinline__ void gn_raw_unpack(const GnRaw<ALL16>& r, int kind, float* f) {
+  if constexpr (!ALL16) {
+    if (kind == 1) {
+      f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z);
+      f[3] = __uint_as_float(r.a.w); f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y);
+      f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
+      return;
+    }
+  }
+  if (kind == 2) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = v.x; f[2 * i + 1] = v.y;
+    }
+  } else {
+    unpack8(r.a, f);
+  }
+}
+
+// The apply pass is a pure stream (read 2-4 bytes, write 2 bytes per element), so what decides its speed is how many
+// bytes each SM keeps in flight. A thread issues the raw 16-byte loads of U pixels back to back (U = 8 for 16-bit
+// sources, 4 for fp32: 32 registers of payload either way), converts afterwards, and the first batch is issued BEFORE
+// the statistics prologue (two block-wide syncs and fp64 arithmetic) so that its latency hides there; <= 68 registers
+// keep ~960 threads per SM resident. (The first form - load8 straight into fp32 registers, 92 registers, two blocks
+// per SM, one-pixel tail loop - ran the 16 x 64 x 64 x 320 tensor at 2.4 TB/s: long-scoreboard stalls 8.3 of 14
+// cycles per issue, 23 % of the warp slots occupied; ncu in profiles/r02r_ncu_full_summary.txt.)
+template <bool ALL16>
+__global__ void __launch_bounds__(320, 3)
+gn_apply_kernel(const void* __restrict__ x0, const void* __restrict__ x1,
+                const double* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                long long HW, int C0, int C1, int groups, float eps, int silu,
+                long long ppc, int V, int lanes, int x0_fp32, int x1_fp32,
+                int stat_chunks, int out_f16) {
+  constexpr int U = ALL16 ? 8 : 4;
   __shared__ float s_mean[64];
   __shared__ float s_rstd[64];
   extern __shared__ double s_stat[];     // [stat_chunks][groups][2] partial statistics of this sample
@@ -125,12 +176,36 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
   const int t = threadIdx.x;
   const int ctot = C0 + C1;
   const int cpg = ctot / groups;
+  const int v = t % V;
+  const int pl = t / V;
+  const int V0 = C0 >> 3;
+  const int c0 = v * 8;
+  const bool second = v >= V0;
+  const int kind = second ? x1_fp32 : x0_fp32;
+  const int stride = second ? C1 : C0;
+  // everything below is 32-bit arithmetic relative to this thread's first element of the sample (the host checks
+  // HW * channels < 2^31): pointer + pixel * stride
+  const char* src;
+  {
+    const long long e = second ? (long long)n * HW * C1 + (long long)(v - V0) * 8 : (long long)n * HW * C0 + (long long)v * 8;
+    src = reinterpret_cast<const char*>(second ? x1 : x0) + e * (kind == 1 ? 4 : 2);
+  }
+  const int p_begin = (int)(blockIdx.x * ppc);
+  const int p_end = (int)min(HW, (long long)p_begin + ppc);
+  const int pstep = U * lanes;
+  int p = p_begin + pl;
+  GnRaw<ALL16> raw[U];
+  if (pl < lanes) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * lanes < p_end) gn_raw_load<ALL16>(raw[u], src, (unsigned)(p + u * lanes) * (unsigned)stride, kind);
+  }
   // all threads fetch the per-chunk partials in parallel (one L2 round trip), then one thread per group
   // adds them in chunk order: the result does not depend on scheduling
   {
-    const double* src = stats + (long long)n * GN_MAX_CHUNKS * groups * 2;
+    const double* sp = stats + (long long)n * GN_MAX_CHUNKS * groups * 2;
     const int total = stat_chunks * groups * 2;
-    for (int i = t; i < total; i += blockDim.x) s_stat[i] = src[i];
+    for (int i = t; i < total; i += blockDim.x) s_stat[i] = sp[i];
   }
   __syncthreads();
   for (int g = t; g < groups; g += blockDim.x) {
@@ -147,55 +222,43 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, const void* __restr
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
-  const int v = t % V;
-  const int pl = t / V;
   if (pl >= lanes) return;
-  const int V0 = C0 >> 3;
   float sc[8], sh[8];
-  const int c0 = v * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    const int g = c / cpg;
-    const float ga = gamma[c], be = beta[c];
-    sc[j] = s_rstd[g] * ga;
-    sh[j] = be - s_mean[g] * s_rstd[g] * ga;
-  }
-  const bool second = v >= V0;
-  const void* src = second ? x1 : x0;
-  const int src_fp32 = second ? x1_fp32 : x0_fp32;
-  const long long base = second ? (long long)n * HW * C1 + (long long)(v - V0) * 8
-                                : (long long)n * HW * C0 + (long long)v * 8;
-  const long long stride = second ? C1 : C0;
-  __nv_bfloat16* obase = out + (long long)n * HW * ctot + c0;
-  const long long p_begin = (long long)blockIdx.x * ppc;
-  const long long p_end = min(HW, p_begin + ppc);
-  long long p = p_begin + pl;
-  for (; p + 3LL * lanes < p_end; p += 4LL * lanes) {
-    float f[4][8];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) load8(src, base + (p + (long long)u * lanes) * stride, src_fp32, f[u]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float y = f[u][j] * sc[j] + sh[j];
-        if (silu) y = silu_f(y);
-        f[u][j] = y;
-      }
-      *reinterpret_cast<uint4*>(obase + (p + (long long)u * lanes) * ctot) = pack8(f[u], out_f16);
-    }
-  }
-  for (; p < p_end; p += lanes) {
-    float f[8];
-    load8(src, base + p * stride, src_fp32, f);
+  {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = f[j] * sc[j] + sh[j];
-      if (silu) y = silu_f(y);
-      f[j] = y;
+      const int g = (c0 + j) / cpg;
+      sc[j] = s_rstd[g] * ga[j];
+      sh[j] = be[j] - s_mean[g] * s_rstd[g] * ga[j];
     }
-    *reinterpret_cast<uint4*>(obase + p * ctot) = pack8(f, out_f16);
+  }
+  char* obase = reinterpret_cast<char*>(out) + ((long long)n * HW * ctot + c0) * 2;
+  const unsigned ostride = (unsigned)ctot * 2u;
+  while (true) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p_end) {
+        float f[8];
+        gn_raw_unpack<ALL16>(raw[u], kind, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = f[j] * sc[j] + sh[j];
+          if (silu) y = silu_f(y);
+          f[j] = y;
+        }
+        *reinterpret_cast<uint4*>(obase + (size_t)((unsigned)pp * ostride)) = pack8(f, out_f16);
+      }
+    }
+    p += pstep;
+    if (p >= p_end) break;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (p + u * lanes < p_end) gn_raw_load<ALL16>(raw[u], src, (unsigned)(p + u * lanes) * (unsigned)stride, kind);
   }
 }
 
@@ -379,7 +442,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ scores, __nv_bfloa
 }
 
 static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* threads,
-                       long long* ppc, int* chunks) {
+                       long long* ppc, int* chunks, int blocks_per_sm = 4) {
   if (ctot % 8 != 0) return -1;
   *V = ctot / 8;
   if (*V > 1024) return -1;
@@ -387,7 +450,7 @@ static int gn_geometry(int NB, long long HW, int ctot, int* V, int* lanes, int* 
   if (*lanes < 1) *lanes = 1;
   *threads = *V * *lanes;
   // aim for ~4 resident blocks per SM across the batch
-  long long want = (148LL * 4 + NB - 1) / NB;
+  long long want = (148LL * blocks_per_sm + NB - 1) / NB;
   long long max_chunks = (HW + *lanes * 4 - 1) / (*lanes * 4);
   if (want > max_chunks) want = max_chunks;
   if (want > GN_MAX_CHUNKS) want = GN_MAX_CHUNKS;
@@ -698,19 +761,32 @@ extern "C" int sdb_groupnorm_apply(const void* x0, const void* x1, const double*
     return SDB_ERR_ARG;
   }
   int V, lanes, threads, chunks; long long ppc;
-  if (gn_geometry(NB, HW, ctot, &V, &lanes, &threads, &ppc, &chunks)) {
+  static int bps = 0;                   // resident blocks per SM the grid aims for (tuning switch, default 4)
+  if (bps == 0) { const char* ev = getenv("SDB_GN_APPLY_BPS"); bps = (ev && atoi(ev) > 0) ? atoi(ev) : 4; }
+  if (gn_geometry(NB, HW, ctot, &V, &lanes, &threads, &ppc, &chunks, bps)) {
     set_error("sdb_groupnorm_apply: unsupported channel count %d", ctot);
     return SDB_ERR_UNSUPPORTED;
   }
-  const size_t smem_apply = (size_t)chunks * groups * 2 * sizeof(double);
+  if (threads > 320 || HW * (long long)ctot >= (1LL << 31)) {
+    set_error("sdb_groupnorm_apply: %d channels x %lld pixels per sample is outside the kernel's range", ctot, HW);
+    return SDB_ERR_UNSUPPORTED;
+  }
+  const int sc = stat_chunks > 0 ? stat_chunks : chunks;
+  const size_t smem_apply = (size_t)sc * groups * 2 * sizeof(double);
   static PerDeviceOnce apply_once = {};
   if (first_use_on_device(apply_once)) {
-    int rc = set_max_smem(gn_apply_kernel, GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double), "sdb_groupnorm_apply");
+    int rc = set_max_smem(gn_apply_kernel<true>, GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double), "sdb_groupnorm_apply");
+    if (!rc) rc = set_max_smem(gn_apply_kernel<false>, GN_MAX_CHUNKS * 64 * 2 * (int)sizeof(double), "sdb_groupnorm_apply");
     if (rc) return rc;
   }
-  cudaError_t le = launch_k(gn_apply_kernel, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
-                            x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
-                            lanes, x0_fp32, x1_fp32, stat_chunks > 0 ? stat_chunks : chunks, out_f16);
+  const bool all16 = x0_fp32 != 1 && (C1 == 0 || x1_fp32 != 1);
+  cudaError_t le = all16
+      ? launch_k(gn_apply_kernel<true>, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
+                 x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
+                 lanes, x0_fp32, x1_fp32, sc, out_f16)
+      : launch_k(gn_apply_kernel<false>, dim3(chunks, NB), dim3(threads), smem_apply, (cudaStream_t)stream, 1,
+                 x0, x1, stats, gamma, beta, (__nv_bfloat16*)out, HW, C0, C1, groups, eps, silu, ppc, V,
+                 lanes, x0_fp32, x1_fp32, sc, out_f16);
   if (le != cudaSuccess) { set_error("gn_apply_kernel launch: %s", cudaGetErrorString(le)); (void)cudaGetLastError(); return SDB_ERR_CUDA; }
   return check_launch("gn_apply_kernel");
 }
