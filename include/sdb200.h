@@ -62,7 +62,7 @@ typedef struct sdb_gemm_args {
   const void* a1;         /* optional source 1 (channel concatenation without a copy), or NULL   */
   const void* w;          /* bf16 weights [Cout, ldw], row = taps * (C0 + C1) values             */
   const float* bias;      /* fp32 [Cout] (or [M] when bias_per_row), or NULL                     */
-  const void* residual;   /* bf16 (fp32 when res_fp32) [M, ldr] added after the activation, or NULL */
+  const void* residual;   /* [M, ldr] added after the activation, or NULL; type by res_fp32: 0 bf16, 1 fp32, 2 IEEE half */
   void* out;              /* bf16 (or fp32 when out_fp32) [M, ldo]                               */
   void* out2;             /* optional bf16 copy [M, ldo] written next to an fp32 `out`, or NULL  */
   float* workspace;       /* fp32 [nsplit, M, Cout] when nsplit > 1                              */

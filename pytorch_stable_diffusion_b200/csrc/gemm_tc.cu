@@ -16,6 +16,7 @@
 // Replaces the reference's nn.Conv2d / nn.Linear call sites (sd/diffusion.py:125,135,143,256,
 // 266-269,410,545-569,712; sd/attention.py:12,16,143-152; sd/decoder.py:112-129,235-339;
 // sd/encoder.py:56-92; sd/clip.py:117,121).
+#include <cuda_fp16.h>
 #include <algorithm>
 #include "common.cuh"
 #include "host.h"
@@ -100,7 +101,7 @@ struct GemmTcParams {
   int ab_f16;              // A and W are IEEE half (kind::f16 with f16 operand formats); accumulation stays fp32
   const float* bias;
   int bias_mode;           // 0 none, 1 per column, 2 per row
-  const void* residual;    // bf16, or fp32 when res_fp32
+  const void* residual;    // bf16 (res_fp32 = 0), fp32 (1) or IEEE half (2)
   int res_fp32;
   int res_async;           // fp32 residual streamed through a per-warp cp.async ring in shared memory
   int res_direct;          // fp32 residual, 16-byte aligned, fetched with vector loads per chunk
@@ -225,6 +226,40 @@ __device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], uint32_t (&pk)
                    : "memory");
     if (F16) { pk[2 * j] = pack_f16x2_sat(x.x, x.y); pk[2 * j + 1] = pack_f16x2_sat(x.z, x.w); }
     else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
+  }
+}
+
+// The same row with an IEEE-half residual and a 16-bit result only (the token stream inside an attention block): the
+// residual chunk is a 32 x 32 x 2-byte box in a 64B-swizzled slot (16-byte piece j of row r at (j ^ ((r >> 1) & 3))),
+// nothing is written back to the slot.
+template <bool ACT, bool F16>
+__device__ __forceinline__ void epi_rows16(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t rrow, uint32_t hx,
+                                           uint32_t bias_line, float rowb, int act) {
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    uint32_t r[4];
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(rrow + ((((uint32_t)j4) ^ hx) << 4)));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * j4 + h;
+      float4 b4;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                   : "r"(bias_line + (uint32_t)(j * 16)));
+      float4 x = make_float4(__uint_as_float(v[4 * j]) + (b4.x + rowb), __uint_as_float(v[4 * j + 1]) + (b4.y + rowb),
+                             __uint_as_float(v[4 * j + 2]) + (b4.z + rowb), __uint_as_float(v[4 * j + 3]) + (b4.w + rowb));
+      if (ACT) {
+        x.x = apply_act(x.x, act); x.y = apply_act(x.y, act);
+        x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
+      }
+      const float2 ra = __half22float2(*reinterpret_cast<const __half2*>(&r[2 * h]));
+      const float2 rb = __half22float2(*reinterpret_cast<const __half2*>(&r[2 * h + 1]));
+      x.x += ra.x; x.y += ra.y; x.z += rb.x; x.w += rb.y;
+      if (F16) { pk[2 * j] = pack_f16x2_sat(x.x, x.y); pk[2 * j + 1] = pack_f16x2_sat(x.z, x.w); }
+      else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
+    }
   }
 }
 
@@ -570,8 +605,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const bool f32out = (p.out_fp32 != 0);
     const bool b16out = (!f32out) || (p.out2 != nullptr);
     const CUtensorMap* map16 = f32out ? &p.map_out2 : &p.map_out;
+    const bool res16 = has_res && p.res_fp32 == 2;      // IEEE-half residual: 2 KB slots (64B swizzle), read only
+    const uint32_t slot_bytes = res16 ? (uint32_t)GEMM_EPI16_BYTES : (uint32_t)GEMM_EPI_STAGE_BYTES;
     const uint32_t wblk = smem_u32(epi_smem) + (uint32_t)(e * p.epi_warp_bytes);
-    const uint32_t b16_base = wblk + (uint32_t)(nslot * GEMM_EPI_STAGE_BYTES);
+    const uint32_t b16_base = wblk + (uint32_t)nslot * slot_bytes;
     const uint32_t rbar0 = smem_u32(res_bar + e * 4);
     const uint32_t bias_line = smem_u32(epi_smem) + (uint32_t)(GEMM_EPI_WARPS * p.epi_warp_bytes + e * (GEMM_BIAS_LINES * 128));
     const bool slab_ok = p.slab_ok[q] != 0;
@@ -596,8 +633,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       if (pf_tile < p.total_tiles) {
         if (lane == 0) {
           const uint32_t bar = rbar0 + (uint32_t)(pf_slot * 8);
-          const uint32_t dst = wblk + (uint32_t)(pf_slot * GEMM_EPI_STAGE_BYTES);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(GEMM_EPI_STAGE_BYTES) : "memory");
+          const uint32_t dst = wblk + (uint32_t)pf_slot * slot_bytes;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
           if (p.a_rank == 2) tma_load_2d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1);
           else tma_load_4d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1, pf_c2, pf_c3);
         }
@@ -681,11 +718,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int col0 = t.n0 + ch * 32;
         const uint32_t bline = bias_line + (uint32_t)(((ch - ch_first) >> 1) * 128);
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
-        const uint32_t srow = wblk + (uint32_t)(slot * GEMM_EPI_STAGE_BYTES + lane * 128);
+        const uint32_t srow = wblk + (uint32_t)slot * slot_bytes + (uint32_t)(lane * (res16 ? 64 : 128));
         if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
         if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
         uint32_t pk[16];
-        {
+        if (res16) {
+          const uint32_t hx16 = (uint32_t)((lane >> 1) & 3);
+          switch ((p.act != 0 ? 1 : 0) | (p.out_f16 ? 2 : 0)) {
+            case 0: epi_rows16<false, false>(v, pk, srow, hx16, bline, rowb, p.act); break;
+            case 1: epi_rows16<true, false>(v, pk, srow, hx16, bline, rowb, p.act); break;
+            case 2: epi_rows16<false, true>(v, pk, srow, hx16, bline, rowb, p.act); break;
+            default: epi_rows16<true, true>(v, pk, srow, hx16, bline, rowb, p.act); break;
+          }
+        } else {
           const uint32_t sx = (uint32_t)(lane & 7);
           switch ((p.act != 0 ? 1 : 0) | (has_res ? 2 : 0) | (f32out ? 4 : 0) | (p.out_f16 ? 8 : 0)) {
             case 0: epi_rows<false, false, false, false>(v, pk, srow, sx, bline, rowb, p.act); break;
@@ -1097,12 +1142,18 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             } else if (has_res) {
               // bf16 or unaligned fp32 residual: direct loads (not on the hot path of the engines)
               const long long roff = (long long)m * p.ldr + col0 + cl;
-              if (p.res_fp32) {
+              if (p.res_fp32 == 1) {
                 const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
                 x.x += rp[0];
                 if (cl + 1 < ncol) x.y += rp[1];
                 if (cl + 2 < ncol) x.z += rp[2];
                 if (cl + 3 < ncol) x.w += rp[3];
+              } else if (p.res_fp32 == 2) {
+                const __half* rp = reinterpret_cast<const __half*>(p.residual) + roff;
+                x.x += __half2float(rp[0]);
+                if (cl + 1 < ncol) x.y += __half2float(rp[1]);
+                if (cl + 2 < ncol) x.z += __half2float(rp[2]);
+                if (cl + 3 < ncol) x.w += __half2float(rp[3]);
               } else {
                 const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
                 if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 7u) == 0)) {
@@ -1233,8 +1284,9 @@ __global__ void gemm_splitk_finalize_kernel(const float* __restrict__ ws, int ns
     else if (bias_mode == 2) acc += bias[m];
     acc = apply_act(acc, act);
     if (residual) {
-      acc += res_fp32 ? reinterpret_cast<const float*>(residual)[m * ldr + n]
-                      : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[m * ldr + n]);
+      acc += res_fp32 == 1 ? reinterpret_cast<const float*>(residual)[m * ldr + n]
+           : res_fp32 == 2 ? __half2float(reinterpret_cast<const __half*>(residual)[m * ldr + n])
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[m * ldr + n]);
     }
     if (out_fp32) {
       reinterpret_cast<float*>(out)[m * ldo + n] = acc;
@@ -1569,8 +1621,11 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     ok = ok && (block_n % 32 == 0 || n_tiles == 1);
     ok = ok && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 && (f32o ? (ldo_eff % 4 == 0) : (ldo_eff % 8 == 0));
     if (a->out2) ok = ok && (reinterpret_cast<uintptr_t>(a->out2) & 15u) == 0 && (ldo_eff % 8 == 0);
+    const bool res16 = a->residual != nullptr && a->res_fp32 == 2;
     if (a->residual)
-      ok = ok && a->res_fp32 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 && (ldr_eff % 4 == 0);
+      ok = ok && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 &&
+           (res16 ? (!f32o && ldr_eff % 8 == 0) : (a->res_fp32 == 1 && ldr_eff % 4 == 0));
+    const int slot_bytes = res16 ? GEMM_EPI16_BYTES : GEMM_EPI_STAGE_BYTES;
     if (a->bias)
       ok = ok && (a->bias_per_row ? (kind == SDB_GEMM_LINEAR) : ((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0));
     const int rows = p.bw * p.bh * p.bn, plane = p.bw * p.bh;
@@ -1579,7 +1634,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     if (ok) {
       int nslot = a->residual ? 4 : (f32o ? 2 : 0);
       for (;;) {
-        p.epi_warp_bytes = nslot * GEMM_EPI_STAGE_BYTES + (has16 ? 2 * GEMM_EPI16_BYTES : 0);
+        p.epi_warp_bytes = nslot * slot_bytes + (has16 ? 2 * GEMM_EPI16_BYTES : 0);
         fixed_bytes = GEMM_EPI_WARPS * (p.epi_warp_bytes + GEMM_BIAS_LINES * 128) + 1024 + GEMM_BAR_BYTES;   // + the bias lines of a warp
         stages = (smem_budget - fixed_bytes) / stage_bytes;
         if (stages >= 3 || !(a->residual && nslot == 4)) break;
@@ -1616,13 +1671,13 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
         };
         if ((rc = mk(&p.map_out, a->out, f32o ? 4 : 2, ldo_eff, "gemm out"))) return rc;
         if (a->out2 && (rc = mk(&p.map_out2, a->out2, 2, ldo_eff, "gemm out2"))) return rc;
-        if (a->residual && (rc = mk(&p.map_res, a->residual, 4, ldr_eff, "gemm residual"))) return rc;
+        if (a->residual && (rc = mk(&p.map_res, a->residual, res16 ? 2 : 4, ldr_eff, "gemm residual"))) return rc;
       }
     }
   }
   if (!p.epi_tma) {
     // fp32 residuals stream through a cp.async ring (3 chunks per epilogue warp) when 16-byte aligned
-    const bool res_vec = (a->residual != nullptr && a->res_fp32 && !want_split && (ldr_eff % 4) == 0 &&
+    const bool res_vec = (a->residual != nullptr && a->res_fp32 == 1 && !want_split && (ldr_eff % 4) == 0 &&
                           (a->Cout % 4) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0);
     // short reductions are epilogue-bound (ring: deep prefetch); long ones keep the shared memory for stages
     p.res_async = (res_vec && nkb_all <= 32) ? 1 : 0;
@@ -1656,6 +1711,10 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   p.ab_f16 = a->ab_f16;
   // out_f16: every store path (TMA epilogue, both per-lane paths, split-K finalize) writes the 16-bit tensor as IEEE
   // half; a bf16 residual is the one combination without a path
+  if (a->residual != nullptr && (a->res_fp32 < 0 || a->res_fp32 > 2)) {
+    set_error("sdb_gemm_tc: res_fp32 must be 0 (bf16), 1 (fp32) or 2 (IEEE half)");
+    return SDB_ERR_ARG;
+  }
   if (a->out_f16 && a->residual != nullptr && !a->res_fp32) {
     set_error("sdb_gemm_tc: out_f16 with a bf16 residual is not supported");
     return SDB_ERR_UNSUPPORTED;
@@ -1674,7 +1733,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     const bool aligned = (ldo_eff % 4 == 0) && (reinterpret_cast<uintptr_t>(a->out) & 15u) == 0 &&
                          (!a->out2 || (reinterpret_cast<uintptr_t>(a->out2) & 7u) == 0) &&
                          (!a->bias || a->bias_per_row || (reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0) &&
-                         (!a->residual || (a->res_fp32 && (ldr_eff % 4) == 0 &&
+                         (!a->residual || (a->res_fp32 == 1 && (ldr_eff % 4) == 0 &&
                                            (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0)) &&
                          (reinterpret_cast<uintptr_t>(a->gn_part) & 15u) == 0;
     if (K <= 0 || (!a->out_fp32 && p.epi_tma) || nsplit != 1 || a->Cout % 32 != 0 || block_n % 32 != 0 || !aligned) {
@@ -1736,7 +1795,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     const bool vec4 = (p.N % 4 == 0) && (p.ldo % 4 == 0) && p.bias_mode != 2 &&
-                      (p.residual == nullptr || (p.res_fp32 && p.ldr % 4 == 0 &&
+                      (p.residual == nullptr || (p.res_fp32 == 1 && p.ldr % 4 == 0 &&
                                                  (reinterpret_cast<uintptr_t>(p.residual) & 15u) == 0)) &&
                       (reinterpret_cast<uintptr_t>(p.workspace) & 15u) == 0 &&
                       (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0 &&

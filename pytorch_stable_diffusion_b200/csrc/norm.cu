@@ -392,6 +392,95 @@ layernorm_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
+// IEEE-half rows (the token stream inside an attention block, engine.TOK_F16): 8-byte loads with the column mapping of
+// the fp32 kernel (VPL = ceil(C / 128) vectors of 4 per lane), R rows per warp iteration kept as RAW words and
+// converted on the fly - R = 4 keeps as many bytes in flight as the fp32 kernel's two rows.
+template <int VPL, int R>
+__global__ void __launch_bounds__(256)
+layernorm_h16_kernel(const __half* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, void* __restrict__ out, long long rows, int C,
+                     float eps, int out_fp32) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int V = C >> 2;
+  const float invC = 1.0f / (float)C;
+  auto unpack4 = [](const uint2& u, float* f) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  };
+  for (long long grp = warp0; grp * R < rows; grp += nwarps) {
+    uint2 raw[R][VPL];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        raw[r][i] = make_uint2(0u, 0u);
+        if (v < V && row < rows) {
+          const __half* src = x + row * C + v * 4;
+          asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];"
+                       : "=r"(raw[r][i].x), "=r"(raw[r][i].y)
+                       : "l"(src));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = grp * R + r;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float f[4];
+        unpack4(raw[r][i], f);
+        sum += (f[0] + f[1]) + (f[2] + f[3]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum * invC;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + i * 32 < V) {
+          float f[4];
+          unpack4(raw[r][i], f);
+          const float a = f[0] - mean, b = f[1] - mean, c = f[2] - mean, d = f[3] - mean;
+          sq += (a * a + b * b) + (c * c + d * d);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq * invC + eps);
+      if (row >= rows) continue;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + i * 32;
+        if (v < V) {
+          float f[4];
+          unpack4(raw[r][i], f);
+          const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + v);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + v);
+          float4 y;
+          y.x = (f[0] - mean) * rstd * g.x + b.x;
+          y.y = (f[1] - mean) * rstd * g.y + b.y;
+          y.z = (f[2] - mean) * rstd * g.z + b.z;
+          y.w = (f[3] - mean) * rstd * g.w + b.w;
+          if (out_fp32 == 1) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * C + v * 4) = y;
+          } else {
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * C + v * 4) =
+                make_uint2(pack16x2(y.x, y.y, out_fp32 == 2), pack16x2(y.z, y.w, out_fp32 == 2));
+          }
+        }
+      }
+    }
+  }
+}
+
 // One block per row, the row staged in shared memory (cols * 4 bytes).
 __global__ void softmax_rows_kernel(const float* __restrict__ scores, __nv_bfloat16* __restrict__ probs,
                                     int cols, float scale_log2) {
@@ -862,6 +951,22 @@ extern "C" int sdb_layernorm(const void* x, const float* gamma, const float* bet
     else SDB_LN(10);
 #undef SDB_LN
     return check_launch("layernorm_f32_kernel");
+  }
+  if (in_fp32 == 2 && aligned && C % 4 == 0 && C <= 1280) {
+    const int vpl = (C / 4 + 31) / 32;
+    const int rpw = vpl <= 6 ? 4 : 2;                         // rows per warp iteration
+    long long blocks = ((rows + rpw - 1) / rpw + warps - 1) / warps;
+    const long long cap = 148LL * 8;
+    if (blocks > cap) blocks = cap;
+    const __half* xh = reinterpret_cast<const __half*>(x);
+    cudaStream_t st = (cudaStream_t)stream;
+#define SDB_LNH(V, R) (void)launch_k(layernorm_h16_kernel<V, R>, dim3((unsigned)blocks), dim3(warps * 32), 0, st, 1, xh, gamma, beta, out, rows, C, eps, out_fp32)
+    if (vpl <= 3) SDB_LNH(3, 4);
+    else if (vpl <= 5) SDB_LNH(5, 4);
+    else if (vpl <= 6) SDB_LNH(6, 4);
+    else SDB_LNH(10, 2);
+#undef SDB_LNH
+    return check_launch("layernorm_h16_kernel");
   }
   const long long blocks = (rows + warps - 1) / warps;
   layernorm_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(

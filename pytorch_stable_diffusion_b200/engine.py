@@ -38,6 +38,11 @@ FUSE_SKIP_CONV = os.environ.get("SDB_NO_FUSE_SKIP") != "1"
 # value sees the 2^-11 rounding, 4 bytes per element less HBM traffic per resblock. (Round 1 tried bf16 here: 0.115 ms
 # per step for 6 % more RMS error - left off; half costs 1/8 of that error.) SDB_HID_FP32=1 restores the fp32 tensor.
 HID_F16 = os.environ.get("SDB_HID_FP32") != "1"
+# The token stream INSIDE a UNet attention block (t0 = conv_input, t1 = t0 + self-attention, t2 = t1 + cross-attention;
+# sd/diffusion.py:306-353) is IEEE half: each tensor is written once and read twice (LayerNorm + the next residual add),
+# so fp32 cost 12 bytes per element and block where half costs 6, and t2 is its own 16-bit GEMM operand (no shadow).
+# The block's input and output - the UNet's residual stream proper - stay fp32. SDB_TOK_FP32=1 restores fp32.
+TOK_F16 = os.environ.get("SDB_TOK_FP32") != "1"
 # self-attention of heads <= 112 channels: softmax denominator from a ones row in V^T (see pack_unet_attn)
 SUM_ROW_ATTENTION = os.environ.get("SDB_NO_SUM_ROW") != "1"
 # ... and the softmax row offset folded into Q.K^T through a ones column of k (heads padded to R columns)
@@ -223,6 +228,7 @@ def pack_unet_attn(m, dev, dt=torch.bfloat16):
     pk.wv2, pk.bv2 = pack_linear(m.attention_2.v_proj, dev)
     pk.wo2, pk.bo2 = pack_linear(m.attention_2.out_proj, dev)
     pk.ln3 = pack_norm(m.layernorm_3, dev)
+    pk.tok16 = False
     # the GEGLU gate half is dead in the reference (sd/diffusion.py:359-363): keep the first 4C rows only
     if FOLD_GEGLU:
         # composed in fp64 by our own CUDA-core kernel (ops.matmul_f64): no library GEMM anywhere, pack time included
@@ -243,7 +249,10 @@ def pack_unet_attn(m, dev, dt=torch.bfloat16):
             # two GEMMs with a bf16 round trip of t3 in between (sd/diffusion.py:355-381)
             wo = _f32(m.conv_output.weight.detach().reshape(c, c), dev)
             bo = m.conv_output.bias.detach().to(device=dev, dtype=torch.float64)
-            pk.w_ffout = torch.cat([ops.matmul_f64(wo, w21), wo.to(torch.float64)], dim=1).to(dt).contiguous()
+            # with a half token stream the second source IS the stream: this GEMM's operands are IEEE half at every level
+            pk.tok16 = TOK_F16
+            pk.w_ffout = torch.cat([ops.matmul_f64(wo, w21), wo.to(torch.float64)], dim=1) \
+                .to(torch.float16 if pk.tok16 else dt).contiguous()
             pk.b_ffout = (ops.matmul_f64(wo, b21.view(-1, 1).contiguous()).view(-1) + bo).to(torch.float32).contiguous()
     else:
         pk.wg1 = _bf16(m.linear_geglu_1.weight[:4 * c], dev, dt)
@@ -383,15 +392,16 @@ def context_kv(pk, ctx_pad):
 def unet_attn_prefix(pk, x):
     """UNET_AttentionBlock.forward up to (and including) the self-attention residual: GroupNorm, conv_input,
     LayerNorm, self-attention, out_proj (sd/diffusion.py:271-326). Nothing here depends on the text context - for a
-    classifier-free-guidance pair this half of the block is the same for both members. Returns the fp32 token stream
-    t1 [n*s, c]."""
+    classifier-free-guidance pair this half of the block is the same for both members. Returns the token stream
+    t1 [n*s, c] (IEEE half with TOK_F16, else fp32)."""
     n, h, w, c = x.shape
     s = h * w
     m = n * s
     d = c // pk.heads
     dev = x.f.device
     a = ops.groupnorm(x.f, pk.gn_w, pk.gn_b, eps=1e-6, silu=False, part0=x.gp, out_dtype=pk.dt)
-    t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=True)
+    tok = pk.tok16
+    t0 = ops.linear(a.view(m, c), pk.cin_w, bias=pk.cin_b, out_fp32=not tok, out16=torch.float16)
     l1 = ops.layernorm(t0, *pk.ln1)
     qk = ops.linear(l1, pk.wqk, bias=pk.bqk)
     vt, vt_ld = project_vt(pk.wv, pk.bv, l1, n, s)
@@ -401,12 +411,12 @@ def unet_attn_prefix(pk, x):
     ops.attention(qk, qk[:, cq:], vt, o, NB=n, heads=pk.heads, d=d, S=s, Skv=s, Skv_pad=s, vt_ld=vt_ld,
                   ldq=2 * cq, ldk=2 * cq, ldo=c, sum_row=pk.vt_rows > 0, q_prescaled=pk.vt_rows > 0,
                   qk_cols=pk.qk_cols, qk_fold=fold)
-    return ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=True)
+    return ops.linear(o, pk.wo1, bias=pk.bo1, residual=t0, out_fp32=not tok, out16=torch.float16)
 
 
 def unet_attn_suffix(pk, x, t1, kv, want_b16=False, out16=torch.bfloat16):
     """The rest of UNET_AttentionBlock.forward (sd/diffusion.py:328-381): cross-attention over the CLIP tokens,
-    feed-forward, conv_output, + block input x. t1: fp32 token stream after the self-attention, same batch as x."""
+    feed-forward, conv_output, + block input x. t1: token stream after the self-attention, same batch as x."""
     dt = pk.dt
     n, h, w, c = x.shape
     s = h * w
@@ -420,11 +430,13 @@ def unet_attn_suffix(pk, x, t1, kv, want_b16=False, out16=torch.bfloat16):
     ops.attention(q, k2, vt2, o2, NB=n, heads=pk.heads, d=d, S=s, Skv=77, Skv_pad=CTX_PAD,
                   ldq=c, ldk=c, ldo=c)
     ff_out = pk.wg1 is None and pk.w_ffout is not None
-    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=True, out2=True if ff_out else None, out16=dt)
+    tok = pk.tok16 and ff_out
+    t2 = ops.linear(o2, pk.wo2, bias=pk.bo2, residual=t1, out_fp32=not tok, out2=True if (ff_out and not tok) else None,
+                    out16=torch.float16 if tok else dt)
     # feed-forward: linear_geglu_2(linear_geglu_1(x)[:, :4C]) — gate unused, no GELU
     if ff_out:
-        t2, t2_b = t2
-        l3 = ops.layernorm(t2, *pk.ln3, out_dtype=dt)
+        t2, t2_b = (t2, t2) if tok else t2
+        l3 = ops.layernorm(t2, *pk.ln3, out_dtype=torch.float16 if tok else dt)
         out = ops.gemm(l3, pk.w_ffout, c, a1=t2_b, M=m, c0=c, c1=c, bias=pk.b_ffout, residual=x.f.view(m, c),
                        out_fp32=True, out2=True if want_b16 else None, gn_samples=_gn_samples(n, s, c), out16=out16)
         return _stream(out, (n, h, w, c))
@@ -440,7 +452,7 @@ def unet_attn_suffix(pk, x, t1, kv, want_b16=False, out16=torch.bfloat16):
 
 
 def run_unet_attn(pk, x, kv, want_b16=False, out16=torch.bfloat16):
-    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is fp32."""
+    """UNET_AttentionBlock.forward (sd/diffusion.py:271-381); the token stream t0..t2 is IEEE half (TOK_F16) or fp32."""
     return unet_attn_suffix(pk, x, unet_attn_prefix(pk, x), kv, want_b16=want_b16, out16=out16)
 
 

@@ -165,10 +165,10 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
     args.a0, args.a1, args.w = _p(a0), _p(a1), _p(w)
     args.bias = _p(_chk(bias, torch.float32, "bias")) if bias is not None else None
     if residual is not None:
-        if residual.dtype not in (torch.bfloat16, torch.float32):
-            raise ValueError("residual must be bf16 or fp32")
+        if residual.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+            raise ValueError("residual must be bf16, fp32 or IEEE half")
         args.residual = _p(residual)
-        args.res_fp32 = 1 if residual.dtype == torch.float32 else 0
+        args.res_fp32 = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}[residual.dtype]
     if kind == GEMM_LINEAR:
         if M is None:
             M = a0.shape[0] if a0.dim() == 2 else a0.numel() // a0.shape[-1]
@@ -251,7 +251,7 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         k_total = ntaps * (c0 + c1) + cx0 + cx1
         res_b = residual.element_size() if residual is not None else 0
         shape = (f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps} cx={cx0 + cx1} "
-                 f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={('f32', 'bf16')[res_b == 2] if res_b else 'none'} "
+                 f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={str(residual.dtype).replace('torch.', '').replace('float', 'f') if res_b else 'none'} "
                  f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit} "
                  f"ab={'f16' if op16 == torch.float16 else 'bf16'}"
                  + (f" hw={rows // conv_dims[0]}" if conv_dims is not None else ""))
@@ -400,13 +400,13 @@ def layernorm(x, gamma, beta, eps=1e-5, out_fp32=False, out_dtype=torch.bfloat16
     rows = x.numel() // c
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32 if out_fp32 else out_dtype)
     kind = 1 if out_fp32 else (2 if out_dtype == torch.float16 else 0)
+    in_kind = {torch.bfloat16: 0, torch.float32: 1, torch.float16: 2}[x.dtype]
 
     def launch():
-        _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps),
-                                     1 if x.dtype == torch.float32 else 0, kind, _stream()),
+        _ext.check(lib.sdb_layernorm(_p(x), _p(gamma), _p(beta), _p(out), rows, c, float(eps), in_kind, kind, _stream()),
                    "sdb_layernorm")
     ev = _prof("layernorm", 0.0, x.numel() * x.element_size() + out.numel() * out.element_size(),
-               shape=f"rows={rows} c={c} in={'f32' if x.dtype == torch.float32 else 'bf16'} "
+               shape=f"rows={rows} c={c} in={('bf16', 'f32', 'f16')[in_kind]} "
                      f"out={'f32' if out_fp32 else 'bf16'}", relaunch=launch)
     launch()
     _prof_end(ev)

@@ -157,6 +157,18 @@ def test_linear_tma_epilogue(M, K, N, block_n):
     if N % 32 == 0:
         got = ops.linear(a, w, bias=b, out_f16=True, epi_mode=2, **kw)
         report(f"tma-epi f16 {M}x{K}x{N}", got, ref, 2e-3)
+    # IEEE-half residual + 16-bit result (the token stream of the attention blocks): TMA epilogue with 2 KB residual
+    # slots, bit for bit equal to the per-lane epilogue
+    rh = r.half()
+    for o16, tol in ((torch.float16, 2e-3), (torch.bfloat16, 1e-2)):
+        got = ops.linear(a, w, bias=b, residual=rh, out16=o16, epi_mode=2, **kw)
+        assert got.dtype == o16
+        report(f"tma-epi {o16} + half residual {M}x{K}x{N}", got, ref + rh.float(), tol)
+        assert torch.equal(got, ops.linear(a, w, bias=b, residual=rh, out16=o16, epi_mode=1, **kw))
+    got = ops.linear(a, w, bias=b, residual=rh, out16=torch.float16, act=ops.ACT_QUICK_GELU, epi_mode=2, **kw)
+    report(f"tma-epi f16 qgelu + half residual {M}x{K}x{N}", got, ref * torch.sigmoid(1.702 * ref) + rh.float(), 2e-3)
+    got = ops.linear(a, w, bias=b, residual=rh, out_fp32=True, **kw)     # fp32 out + half residual: per-lane path
+    report(f"fp32 out + half residual {M}x{K}x{N}", got, ref + rh.float(), 2e-3)
 
 
 def test_linear_tma_epilogue_row_bias_and_strided_out():
@@ -485,6 +497,11 @@ def test_layernorm(rows, C):
     ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
     report(f"layernorm {rows}x{C}", ops.layernorm(x, g, b), ref, 6e-3)
     report(f"layernorm fp32 {rows}x{C}", ops.layernorm(x, g, b, out_fp32=True), ref, 1e-5)
+    xh = (rnd(rows + 3, C, seed=6) * 3 + 1).half()                        # IEEE-half rows (ragged row count)
+    refh = F.layer_norm(xh.float(), (C,), g, b, 1e-5)
+    report(f"layernorm half in {rows}x{C}", ops.layernorm(xh, g, b, out_dtype=torch.float16), refh, 2e-3)
+    report(f"layernorm half in, bf16 out {rows}x{C}", ops.layernorm(xh, g, b), refh, 6e-3)
+    report(f"layernorm half in, fp32 out {rows}x{C}", ops.layernorm(xh, g, b, out_fp32=True), refh, 1e-5)
 
 
 def test_softmax_rows():
