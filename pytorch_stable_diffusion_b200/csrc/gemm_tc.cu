@@ -34,7 +34,7 @@ constexpr int GEMM_EPI_STAGE_BYTES = 32 * 32 * 4;          // one 32x32 fp32 chu
 constexpr int GEMM_RES_RING = 3;                           // residual chunks in flight per epilogue warp (+1)
 constexpr int GEMM_BAR_BYTES = 512;                        // mbarriers + TMEM slot at the end of shared memory
 constexpr int GEMM_EPI16_BYTES = 32 * 32 * 2;              // one 32x32 16-bit chunk
-constexpr int GEMM_BIAS_LINES = 5;                         // TMA epilogue: 128-byte bias lines per warp (its <= 5 chunks of a tile)
+constexpr int GEMM_BIAS_LINES = 6;                         // TMA epilogue: 128-byte bias lines per warp (its <= 6 32-column chunks of a tile)
 
 struct GemmTcParams {
   CUtensorMap map_a0;
@@ -131,6 +131,7 @@ struct GemmTcParams {
   int epi_bytes;           // shared memory of all epilogue warps (either path)
   int epi_warp_bytes;      // per warp: epi_nslot fp32 slots of 4 KiB, then two 2 KiB 16-bit buffers (if any)
   int epi_nslot;           // fp32 slots per warp (residual in, result out, in place): 0, 2, 3 or 4
+  int epi_w64;             // 16-bit-only outputs: a warp owns PAIRS of 32-column chunks and stores 64-column boxes (128-byte rows)
   int8_t slab_w0[4], slab_h0[4], slab_n0[4];   // origin of TMEM lane quadrant q's 32 rows inside the tile box
   int8_t slab_ok[4];       // quadrant holds rows of the tile at all
   CUtensorMap map_out;     // boxes of 32 columns x 32 rows (rank 2: [M][N]; rank 4: [NB][HO][WO][N])
@@ -200,66 +201,97 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
 // the 32-element body free of branches.
 template <bool ACT, bool RES, bool F32, bool F16>
 __device__ __forceinline__ void epi_rows(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t srow, uint32_t sx,
-                                         uint32_t bias_line, float rowb, int act) {
+                                         uint32_t bias_line, float rowb, int act) {   // fp32 slots: 32-column chunks only
+  // All shared-memory loads of a phase are issued back to back BEFORE their first use (the asm statements are
+  // volatile, i.e. kept in program order: a load -> add -> load -> add sequence paid one shared-memory latency per
+  // 4 columns - 477 clocks for this function on the epilogue's critical path, tools/gemm_trace.py --mode 8).
+  float x[32];
+  {
+    float4 b4[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w)
+                   : "r"(bias_line + (uint32_t)(j * 16)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[4 * j] = __uint_as_float(v[4 * j]) + (b4[j].x + rowb);
+      x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + (b4[j].y + rowb);
+      x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + (b4[j].z + rowb);
+      x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + (b4[j].w + rowb);
+    }
+  }
+  if (ACT) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], act);
+  }
+  if (RES) {
+    float4 rr[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(rr[j].x), "=f"(rr[j].y), "=f"(rr[j].z), "=f"(rr[j].w)
+                   : "r"(srow + ((((uint32_t)j) ^ sx) << 4)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[4 * j] += rr[j].x; x[4 * j + 1] += rr[j].y; x[4 * j + 2] += rr[j].z; x[4 * j + 3] += rr[j].w;
+    }
+  }
+  if (F32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((((uint32_t)j) ^ sx) << 4)),
+                   "f"(x[4 * j]), "f"(x[4 * j + 1]), "f"(x[4 * j + 2]), "f"(x[4 * j + 3])
+                   : "memory");
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float4 b4;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
-                 : "r"(bias_line + (uint32_t)(j * 16)));
-    float4 x = make_float4(__uint_as_float(v[4 * j]) + (b4.x + rowb), __uint_as_float(v[4 * j + 1]) + (b4.y + rowb),
-                           __uint_as_float(v[4 * j + 2]) + (b4.z + rowb), __uint_as_float(v[4 * j + 3]) + (b4.w + rowb));
-    if (ACT) {
-      x.x = apply_act(x.x, act); x.y = apply_act(x.y, act);
-      x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
-    }
-    const uint32_t piece = srow + ((((uint32_t)j) ^ sx) << 4);
-    if (RES) {
-      float4 rr;
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
-                   : "r"(piece));
-      x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-    }
-    if (F32)
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(piece), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w)
-                   : "memory");
-    if (F16) { pk[2 * j] = pack_f16x2_sat(x.x, x.y); pk[2 * j + 1] = pack_f16x2_sat(x.z, x.w); }
-    else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
+    if (F16) { pk[2 * j] = pack_f16x2_sat(x[4 * j], x[4 * j + 1]); pk[2 * j + 1] = pack_f16x2_sat(x[4 * j + 2], x[4 * j + 3]); }
+    else { pk[2 * j] = pack_bf16x2(x[4 * j], x[4 * j + 1]); pk[2 * j + 1] = pack_bf16x2(x[4 * j + 2], x[4 * j + 3]); }
   }
 }
 
 // The same row with an IEEE-half residual and a 16-bit result only (the token stream inside an attention block): the
 // residual chunk is a 32 x 32 x 2-byte box in a 64B-swizzled slot (16-byte piece j of row r at (j ^ ((r >> 1) & 3))),
-// nothing is written back to the slot.
+// or half of a 64-column row of a 128B-swizzled slot (piece (sub4 + j) ^ (r & 7)); nothing is written back.
 template <bool ACT, bool F16>
 __device__ __forceinline__ void epi_rows16(const uint32_t (&v)[32], uint32_t (&pk)[16], uint32_t rrow, uint32_t hx,
-                                           uint32_t bias_line, float rowb, int act) {
+                                           uint32_t sub4, uint32_t bias_line, float rowb, int act) {
+  uint32_t r[16];
 #pragma unroll
-  for (int j4 = 0; j4 < 4; ++j4) {
-    uint32_t r[4];
+  for (int j4 = 0; j4 < 4; ++j4)
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(rrow + ((((uint32_t)j4) ^ hx) << 4)));
+                 : "=r"(r[4 * j4]), "=r"(r[4 * j4 + 1]), "=r"(r[4 * j4 + 2]), "=r"(r[4 * j4 + 3])
+                 : "r"(rrow + (((sub4 + (uint32_t)j4) ^ hx) << 4)));
+  float x[32];
+  {
+    float4 b4[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int j = 2 * j4 + h;
-      float4 b4;
+    for (int j = 0; j < 8; ++j)
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                   : "=f"(b4[j].x), "=f"(b4[j].y), "=f"(b4[j].z), "=f"(b4[j].w)
                    : "r"(bias_line + (uint32_t)(j * 16)));
-      float4 x = make_float4(__uint_as_float(v[4 * j]) + (b4.x + rowb), __uint_as_float(v[4 * j + 1]) + (b4.y + rowb),
-                             __uint_as_float(v[4 * j + 2]) + (b4.z + rowb), __uint_as_float(v[4 * j + 3]) + (b4.w + rowb));
-      if (ACT) {
-        x.x = apply_act(x.x, act); x.y = apply_act(x.y, act);
-        x.z = apply_act(x.z, act); x.w = apply_act(x.w, act);
-      }
-      const float2 ra = __half22float2(*reinterpret_cast<const __half2*>(&r[2 * h]));
-      const float2 rb = __half22float2(*reinterpret_cast<const __half2*>(&r[2 * h + 1]));
-      x.x += ra.x; x.y += ra.y; x.z += rb.x; x.w += rb.y;
-      if (F16) { pk[2 * j] = pack_f16x2_sat(x.x, x.y); pk[2 * j + 1] = pack_f16x2_sat(x.z, x.w); }
-      else { pk[2 * j] = pack_bf16x2(x.x, x.y); pk[2 * j + 1] = pack_bf16x2(x.z, x.w); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[4 * j] = __uint_as_float(v[4 * j]) + (b4[j].x + rowb);
+      x[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + (b4[j].y + rowb);
+      x[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + (b4[j].z + rowb);
+      x[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + (b4[j].w + rowb);
     }
+  }
+  if (ACT) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], act);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&r[i]));
+    x[2 * i] += h.x; x[2 * i + 1] += h.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (F16) { pk[2 * j] = pack_f16x2_sat(x[4 * j], x[4 * j + 1]); pk[2 * j + 1] = pack_f16x2_sat(x[4 * j + 2], x[4 * j + 3]); }
+    else { pk[2 * j] = pack_bf16x2(x[4 * j], x[4 * j + 1]); pk[2 * j + 1] = pack_bf16x2(x[4 * j + 2], x[4 * j + 3]); }
   }
 }
 
@@ -606,14 +638,25 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const bool b16out = (!f32out) || (p.out2 != nullptr);
     const CUtensorMap* map16 = f32out ? &p.map_out2 : &p.map_out;
     const bool res16 = has_res && p.res_fp32 == 2;      // IEEE-half residual: 2 KB slots (64B swizzle), read only
-    const uint32_t slot_bytes = res16 ? (uint32_t)GEMM_EPI16_BYTES : (uint32_t)GEMM_EPI_STAGE_BYTES;
+    // w64 (16-bit result only): the unit of ownership, residual prefetch and store is a PAIR of 32-column chunks - one
+    // 64-column box with 128-byte rows (128B swizzle) - so the per-store costs (proxy fence, warp sync, bulk-store
+    // issue, read-completion wait) are paid once per 64 columns and every store writes whole 128-byte lines
+    const bool w64 = p.epi_w64 != 0;
+    const int cw = w64 ? 64 : 32;                        // columns per owned unit
+    const int nunits = (p.block_n + cw - 1) / cw;
+    const uint32_t b16_bytes = (uint32_t)GEMM_EPI16_BYTES * (w64 ? 2u : 1u);
+    const uint32_t slot_bytes = res16 ? b16_bytes : (uint32_t)GEMM_EPI_STAGE_BYTES;
+    const uint32_t row16 = w64 ? 128u : 64u;             // bytes per row of a 16-bit buffer / half residual slot
+    const uint32_t key16 = w64 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);   // its swizzle key for this lane's row
     const uint32_t wblk = smem_u32(epi_smem) + (uint32_t)(e * p.epi_warp_bytes);
     const uint32_t b16_base = wblk + (uint32_t)nslot * slot_bytes;
     const uint32_t rbar0 = smem_u32(res_bar + e * 4);
     const uint32_t bias_line = smem_u32(epi_smem) + (uint32_t)(GEMM_EPI_WARPS * p.epi_warp_bytes + e * (GEMM_BIAS_LINES * 128));
     const bool slab_ok = p.slab_ok[q] != 0;
     const int sw0 = p.slab_w0[q], sh0 = p.slab_h0[q], sn0 = p.slab_n0[q];
-    const int pfd = nslot - 2;                 // residual prefetch distance in chunks (slots: ahead | current | draining)
+    // residual prefetch distance in units (fp32 slots: ahead | current | draining - the result is stored from the slot;
+    // half slots are only read: ahead | current)
+    const int pfd = (has_res && p.res_fp32 == 2) ? nslot - 1 : nslot - 2;
     // prefetch cursor: the same (tile, chunk) sequence as the main loop, pfd chunks ahead
     int pf_tile = first_tile, pf_lt = 0, pf_ch = half, pf_slot = 0;
     int pf_n0 = 0, pf_c1 = 0, pf_c2 = 0, pf_c3 = 0;
@@ -624,7 +667,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       }
     };
     auto pf_settle = [&]() {       // move to the next existing chunk at or after (pf_tile, pf_ch)
-      while (pf_tile < p.total_tiles && !(pf_ch < nchunks && pf_n0 + pf_ch * 32 < p.N)) {
+      while (pf_tile < p.total_tiles && !(pf_ch < nunits && pf_n0 + pf_ch * cw < p.N)) {
         pf_tile += tile_step; ++pf_lt; pf_ch = (half + pf_lt) & 1;
         pf_decode();
       }
@@ -635,8 +678,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const uint32_t bar = rbar0 + (uint32_t)(pf_slot * 8);
           const uint32_t dst = wblk + (uint32_t)pf_slot * slot_bytes;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(slot_bytes) : "memory");
-          if (p.a_rank == 2) tma_load_2d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1);
-          else tma_load_4d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * 32, pf_c1, pf_c2, pf_c3);
+          if (p.a_rank == 2) tma_load_2d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * cw, pf_c1);
+          else tma_load_4d_u32(&p.map_res, bar, dst, pf_n0 + pf_ch * cw, pf_c1, pf_c2, pf_c3);
         }
         if (++pf_slot == nslot) pf_slot = 0;
         pf_ch += 2;
@@ -666,8 +709,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         float cb[GEMM_BIAS_LINES];
 #pragma unroll
         for (int k = 0; k < GEMM_BIAS_LINES; ++k) {
-          const int col = t.n0 + (ch_first + 2 * k) * 32 + lane;
-          cb[k] = (ch_first + 2 * k < nchunks && col < p.N) ? __ldg(p.bias + col) : 0.f;
+          // k-th 32-column chunk of this warp: ch_first + 2k, or (w64) half k & 1 of unit ch_first + 2 (k >> 1)
+          const int ck = w64 ? 2 * (ch_first + 2 * (k >> 1)) + (k & 1) : ch_first + 2 * k;
+          const int col = t.n0 + ck * 32 + lane;
+          cb[k] = (ck < nchunks && col < p.N) ? __ldg(p.bias + col) : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < GEMM_BIAS_LINES; ++k)
@@ -706,29 +751,35 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       };
       // chunk prologue: free the buffers of the chunk before the previous one and request the next residual -
       // everything that does not need the accumulator
+      // in w64 mode `ch` still counts 32-column chunks; unit = ch >> 1, half = ch & 1
+      auto first_of_unit = [&](int ch) { return !w64 || (ch & 1) == 0; };
+      auto last_of_unit = [&](int ch) { return !w64 || (ch & 1) == 1 || !valid(ch + 1); };
+      auto next_chunk = [&](int ch) { return w64 ? ((ch & 1) ? ch + 3 : ch + 1) : ch + 2; };
       auto pre = [&](int ch) {
-        // stores of the chunk before the previous one have left shared memory: its slot / 16-bit buffer
-        // are free again (and the slot the prefetch below targets is the one that chunk used)
+        // stores of the unit before the previous one have left shared memory: its slot / 16-bit buffer
+        // are free again (and the slot the prefetch below targets is the one that unit used)
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
         if (has_res) issue_prefetch();
       };
       // chunk body: accumulator row in v (loaded and waited for)
       auto post = [&](const uint32_t (&v)[32], int ch) {
-        const int col0 = t.n0 + ch * 32;
-        const uint32_t bline = bias_line + (uint32_t)(((ch - ch_first) >> 1) * 128);
-        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 2);
-        const uint32_t srow = wblk + (uint32_t)slot * slot_bytes + (uint32_t)(lane * (res16 ? 64 : 128));
-        if (has_res) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
-        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 3);
+        const uint32_t sub4 = w64 ? (uint32_t)((ch & 1) * 4) : 0u;           // first 16-byte piece of this chunk in its row
+        const int col0 = t.n0 + (w64 ? (ch & ~1) : ch) * 32;               // first column of the unit's store
+        const int ord = w64 ? 2 * (((ch >> 1) - ch_first) >> 1) + (ch & 1) : (ch - ch_first) >> 1;
+        const uint32_t bline = bias_line + (uint32_t)(ord * 128);
+        const bool t0 = e == 0 && lane == 0 && ord == 0;
+        if (t0) trace_epi(trc, lt, 2);
+        const uint32_t srow = wblk + (uint32_t)slot * slot_bytes + (uint32_t)lane * (res16 ? row16 : 128u);
+        if (has_res && first_of_unit(ch)) mbar_wait(res_bar + e * 4 + slot, rphase, 7);
+        if (t0) trace_epi(trc, lt, 3);
         uint32_t pk[16];
         if (res16) {
-          const uint32_t hx16 = (uint32_t)((lane >> 1) & 3);
           switch ((p.act != 0 ? 1 : 0) | (p.out_f16 ? 2 : 0)) {
-            case 0: epi_rows16<false, false>(v, pk, srow, hx16, bline, rowb, p.act); break;
-            case 1: epi_rows16<true, false>(v, pk, srow, hx16, bline, rowb, p.act); break;
-            case 2: epi_rows16<false, true>(v, pk, srow, hx16, bline, rowb, p.act); break;
-            default: epi_rows16<true, true>(v, pk, srow, hx16, bline, rowb, p.act); break;
+            case 0: epi_rows16<false, false>(v, pk, srow, key16, sub4, bline, rowb, p.act); break;
+            case 1: epi_rows16<true, false>(v, pk, srow, key16, sub4, bline, rowb, p.act); break;
+            case 2: epi_rows16<false, true>(v, pk, srow, key16, sub4, bline, rowb, p.act); break;
+            default: epi_rows16<true, true>(v, pk, srow, key16, sub4, bline, rowb, p.act); break;
           }
         } else {
           const uint32_t sx = (uint32_t)(lane & 7);
@@ -751,20 +802,20 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             default: epi_rows<true, true, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
           }
         }
-        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 6);
-        const uint32_t hbuf = b16_base + (uint32_t)(b16 * GEMM_EPI16_BYTES);
+        if (t0) trace_epi(trc, lt, 6);
+        const uint32_t hbuf = b16_base + (uint32_t)b16 * b16_bytes;
         if (b16out) {
-          const uint32_t hrow = hbuf + (uint32_t)(lane * 64);
-          const uint32_t hx = (uint32_t)((lane >> 1) & 3);
+          const uint32_t hrow = hbuf + (uint32_t)lane * row16;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + ((((uint32_t)j) ^ hx) << 4)),
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hrow + (((sub4 + (uint32_t)j) ^ key16) << 4)),
                          "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                          : "memory");
         }
+        if (!last_of_unit(ch)) return;            // w64: the second half of the row follows, one store for both
         fence_proxy_async();
         __syncwarp();
-        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 7);
+        if (t0) trace_epi(trc, lt, 7);
         if (p.gn_part != nullptr) {
           // GroupNorm statistics of the chunk (rank-2 outputs, fp32 result resident in the slot): lane = column,
           // 32 conflict-free reads down the swizzled rows
@@ -796,31 +847,34 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           }
           bulk_commit();
         }
-        if (e == 0 && lane == 0 && ch == ch_first) trace_epi(trc, lt, 4);
+        if (t0) trace_epi(trc, lt, 4);
         if (nslot > 0 && ++slot == nslot) { slot = 0; rphase ^= 1u; }
         b16 ^= 1;
       };
-      if (slab_ok && valid(ch_first)) {
+      const int ch0 = w64 ? 2 * ch_first : ch_first;
+      if (slab_ok && valid(ch0)) {
         // two register buffers: the accumulator chunk after this one is in flight (tcgen05.ld) while this one
         // goes through bias / residual / staging
         uint32_t va[32], vb[32];
-        int ch = ch_first;
+        int ch = ch0;
         tmem_ld32(taddr(ch), va);
         for (;;) {
-          pre(ch);
+          if (first_of_unit(ch)) pre(ch);
           tmem_ld_wait();
-          const bool n1 = valid(ch + 2);
-          if (n1) tmem_ld32(taddr(ch + 2), vb); else release_acc();
+          const int ch_b = next_chunk(ch);
+          const bool n1 = valid(ch_b);
+          if (n1) tmem_ld32(taddr(ch_b), vb); else release_acc();
           post(va, ch);
           if (!n1) break;
-          ch += 2;
-          pre(ch);
+          ch = ch_b;
+          if (first_of_unit(ch)) pre(ch);
           tmem_ld_wait();
-          const bool n2 = valid(ch + 2);
-          if (n2) tmem_ld32(taddr(ch + 2), va); else release_acc();
+          const int ch_a = next_chunk(ch);
+          const bool n2 = valid(ch_a);
+          if (n2) tmem_ld32(taddr(ch_a), va); else release_acc();
           post(vb, ch);
           if (!n2) break;
-          ch += 2;
+          ch = ch_a;
         }
       } else {
         release_acc();
@@ -1625,25 +1679,35 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     if (a->residual)
       ok = ok && (reinterpret_cast<uintptr_t>(a->residual) & 15u) == 0 &&
            (res16 ? (!f32o && ldr_eff % 8 == 0) : (a->res_fp32 == 1 && ldr_eff % 4 == 0));
-    const int slot_bytes = res16 ? GEMM_EPI16_BYTES : GEMM_EPI_STAGE_BYTES;
+    // 16-bit result only and 64-column tile boundaries: pairs of chunks per store (epi_w64)
+    static int no_w64 = -1;
+    if (no_w64 < 0) { const char* ev = getenv("SDB_NO_EPI_W64"); no_w64 = (ev && ev[0] == '1') ? 1 : 0; }
+    const bool w64 = !no_w64 && !f32o && a->out2 == nullptr && (a->residual == nullptr || res16) && block_n % 64 == 0 &&
+                     a->gn_part == nullptr;
+    const int b16_bytes = GEMM_EPI16_BYTES * (w64 ? 2 : 1);
+    const int slot_bytes = res16 ? b16_bytes : GEMM_EPI_STAGE_BYTES;
     if (a->bias)
       ok = ok && (a->bias_per_row ? (kind == SDB_GEMM_LINEAR) : ((reinterpret_cast<uintptr_t>(a->bias) & 15u) == 0));
     const int rows = p.bw * p.bh * p.bn, plane = p.bw * p.bh;
     if (p.a_rank == 5)
       ok = ok && ((p.bw % 32 == 0) || (32 % p.bw == 0)) && ((plane % 32 == 0) || (32 % plane == 0)) && (rows % 32 == 0);
     if (ok) {
-      int nslot = a->residual ? 4 : (f32o ? 2 : 0);
+      // residual slots per warp: fp32 (in place: ahead | current | draining) 4, else 3; half (read only: ahead |
+      // current) 3, else 2 - the smaller count when the pipeline would otherwise be left with fewer than 3 stages
+      int nslot = a->residual ? (res16 ? 3 : 4) : (f32o ? 2 : 0);
+      const int nslot_min = a->residual ? (res16 ? 2 : 3) : nslot;
       for (;;) {
-        p.epi_warp_bytes = nslot * slot_bytes + (has16 ? 2 * GEMM_EPI16_BYTES : 0);
+        p.epi_warp_bytes = nslot * slot_bytes + (has16 ? 2 * b16_bytes : 0);
         fixed_bytes = GEMM_EPI_WARPS * (p.epi_warp_bytes + GEMM_BIAS_LINES * 128) + 1024 + GEMM_BAR_BYTES;   // + the bias lines of a warp
         stages = (smem_budget - fixed_bytes) / stage_bytes;
-        if (stages >= 3 || !(a->residual && nslot == 4)) break;
-        nslot = 3;
+        if (stages >= 3 || nslot == nslot_min) break;
+        --nslot;
       }
       if (stages >= 2) {
         p.epi_tma = 1;
         p.epi_nslot = nslot;
-        uint32_t box[4] = {32, 32, 1, 1};
+        p.epi_w64 = w64 ? 1 : 0;
+        uint32_t box[4] = {w64 ? 64u : 32u, 32, 1, 1};
         for (int q = 0; q < 4; ++q) {
           const int r0 = q * 32;
           if (p.a_rank == 2) { p.slab_w0[q] = (int8_t)r0; p.slab_ok[q] = 1; }
@@ -1663,11 +1727,11 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
           if (p.a_rank == 2) {
             uint64_t dims[2] = {(uint64_t)a->Cout, (uint64_t)a->M};
             uint64_t str[1] = {(uint64_t)ld * esz};
-            return make_tmap(m, base, esz, esz == 4 ? 128 : 64, 2, dims, str, box, what);
+            return make_tmap(m, base, esz, (esz == 4 || w64) ? 128 : 64, 2, dims, str, box, what);
           }
           uint64_t dims[4] = {(uint64_t)a->Cout, (uint64_t)p.WO, (uint64_t)p.HO, (uint64_t)p.NB};
           uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)ld * esz * p.WO, (uint64_t)ld * esz * p.WO * p.HO};
-          return make_tmap(m, base, esz, esz == 4 ? 128 : 64, 4, dims, str, box, what);
+          return make_tmap(m, base, esz, (esz == 4 || w64) ? 128 : 64, 4, dims, str, box, what);
         };
         if ((rc = mk(&p.map_out, a->out, f32o ? 4 : 2, ldo_eff, "gemm out"))) return rc;
         if (a->out2 && (rc = mk(&p.map_out2, a->out2, 2, ldo_eff, "gemm out2"))) return rc;

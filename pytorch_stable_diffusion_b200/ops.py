@@ -75,6 +75,7 @@ def _chk(t, dtype, name):
 
 
 import os as _os
+_NO_EPI_W64 = _os.environ.get("SDB_NO_EPI_W64") == "1"   # A/B switch (also read by the library): 32-column stores only
 _NO_WIDE = _os.environ.get("SDB_NO_WIDE") == "1"     # A/B switch: never pick the wide (320-column) tiles
 _A3_CHOOSER = _os.environ.get("SDB_A3_CHOOSER") != "0"   # A/B switch: the tile chooser ignores filter-column staging
 
@@ -110,6 +111,12 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0, a3_bytes=0):
             cands.append(small)
     if cout % 320 == 0 and not _NO_WIDE:
         cands.append(320)
+    # 16-bit result only (no fp32 tensor, no fp32 residual) and a short reduction: the TMA epilogue stores 64-column
+    # units when the tile boundaries allow it (sdb_gemm_args: epi_w64) - 256-column tiles then beat the 160-column ones
+    # from 640 output channels up (tools/epi16_probe.py: 65536 x 320 x 1280 94 -> 79 us, x 640 50 -> 47 us)
+    w64 = out_bytes == 2 and res_bytes in (0, 2) and nkb <= 32 and not _NO_EPI_W64
+    if w64 and cout % 160 == 0 and cout >= 640 and 256 not in cands:
+        cands.append(256)
     best = None
     for bn in cands:
         n_tiles = (cout + bn - 1) // bn
@@ -120,7 +127,7 @@ def _choose_tiling(rows, cout, nkb, out_bytes=2, res_bytes=0, a3_bytes=0):
             tiles = row_tiles * n_tiles * ((nkb + per - 1) // per)
             rounds = (tiles + slots - 1) // slots
             epi_bytes = 128.0 * bn * ((4 if ns > 1 else out_bytes) + (0 if ns > 1 else res_bytes))
-            epi = epi_bytes / 20.0 + 1500.0
+            epi = epi_bytes / 20.0 + (1000.0 if (w64 and bn % 64 == 0 and ns == 1) else 1500.0)
             if bn == 320:
                 tile = per * 8 * 88.0 + 1500.0 + epi
             else:

@@ -30,6 +30,7 @@ for N in (320, 640, 768, 1280):
     w = (torch.randn(N, K, device=DEV) * K ** -0.5).bfloat16()
     b = torch.randn(N, device=DEV)
     r = torch.randn(M, N, device=DEV)
+    rh = r.half()
     i = [0]
     def A():
         i[0] ^= 1
@@ -37,6 +38,16 @@ for N in (320, 640, 768, 1280):
     for name, kw, nbytes in (
             ("bf16 out            ", dict(), M * K * 2 + M * N * 2),
             ("bf16 out epi_mode=1 ", dict(epi_mode=1), M * K * 2 + M * N * 2),
+            ("bf16 out bn=320     ", dict(block_n=320, nsplit=1), M * K * 2 + M * N * 2),
+            ("bf16 out bn=256     ", dict(block_n=256, nsplit=1), M * K * 2 + M * N * 2),
+            ("bf16 out bn=192     ", dict(block_n=192, nsplit=1), M * K * 2 + M * N * 2),
+            ("bf16 out bn=160     ", dict(block_n=160, nsplit=1), M * K * 2 + M * N * 2),
+            ("f16 out + f16 res        ", dict(residual=rh, out16=torch.float16), M * K * 2 + M * N * 4),
+            ("f16 out + f16 res bn=320 ", dict(residual=rh, out16=torch.float16, block_n=320, nsplit=1), M * K * 2 + M * N * 4),
+            ("f16 out + f16 res bn=256 ", dict(residual=rh, out16=torch.float16, block_n=256, nsplit=1), M * K * 2 + M * N * 4),
+            ("f16 out + f16 res bn=192 ", dict(residual=rh, out16=torch.float16, block_n=192, nsplit=1), M * K * 2 + M * N * 4),
+            ("f16 out + f16 res bn=160 ", dict(residual=rh, out16=torch.float16, block_n=160, nsplit=1), M * K * 2 + M * N * 4),
+            ("f16 out + f16 res bn=128 ", dict(residual=rh, out16=torch.float16, block_n=128, nsplit=1), M * K * 2 + M * N * 4),
             ("bf16 out bn=128     ", dict(block_n=128, nsplit=1), M * K * 2 + M * N * 2),
             ("bf16 out bn=64      ", dict(block_n=64, nsplit=1), M * K * 2 + M * N * 2),
             ("fp32 out            ", dict(out_fp32=True), M * K * 2 + M * N * 4),
