@@ -96,7 +96,8 @@ typedef struct sdb_gemm_args {
   const void* ax1;        /* resblock's skip convolution (sd/diffusion.py:138-143,208): bf16 NHWC             */
   int Cx0, Cx1;           /* [NB, HI, WI, Cx0] (++ [.., Cx1]); w rows then hold 9*(C0+C1) + Cx0 + Cx1 values,  */
                           /* the 1x1 weights last; multiples of 64. NULL = off.                               */
-  int up_phase;           /* CONV2X2_UP: 2a + b. With gn_part the four phases share one partial-sum tensor
+  int up_phase;           /* CONV2X2_UP: 2a + b, or 4 = all four phases in one launch (w = [4][Cout][4 * C0], phase-major;
+                             the tile index carries the phase). With gn_part the four phases share one partial-sum tensor
                              [samples][4 * K][Cout][2], K = sdb_gemm_gn_slabs(SDB_GEMM_CONV2X2_UP, NB, HI, WI, 0, 0)      */
   int ab_f16;             /* every 16-bit operand (a0, a1, ax0, ax1, w) is IEEE half instead of bf16: 11 instead of 8
                              significand bits at the same width and tensor-core rate (tcgen05 kind::f16 takes either),

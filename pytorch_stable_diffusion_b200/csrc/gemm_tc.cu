@@ -118,6 +118,7 @@ struct GemmTcParams {
   int gn_K;                // slabs per sample
   int gn_hw;               // rank-2 outputs: rows per sample (multiple of 32)
   int gn_spq;              // conv outputs: slabs of one sample inside a tile = min(4, bw*bh/32)
+  int up_all;              // CONV2X2_UP: all four parity phases in ONE launch - the tile's z index is the phase (up_phase = 4)
   int gn_stride, gn_off;   // slab index = sample * gn_stride + gn_off + ...: gn_K and 0, or 4 * gn_K and phase * gn_K for
                            // the four phase launches of an up-sampling conv that share one partial-sum tensor
   // Nearest-neighbour x2 up-sampling folded into the following 3x3 conv (SDB_GEMM_CONV2X2_UP): the output pixels of
@@ -159,7 +160,13 @@ __device__ int g_gemm_trace_on = 0;
 // `trc` is the trace mode read ONCE per kernel (0 for every CTA but the first): the stamps sit next to
 // the single-thread issue loops, where a global load per call would itself distort the timeline.
 __device__ __forceinline__ void trace_stamp(int trc, int tile_local, int slot) {
-  if (trc && !(trc & 8) && tile_local < GEMM_TRACE_TILES) g_gemm_trace[tile_local * 8 + slot] = clock64();
+  if (trc && !(trc & 24) && tile_local < GEMM_TRACE_TILES) g_gemm_trace[tile_local * 8 + slot] = clock64();
+}
+// mode 16: warp 2 / lane 0, the SECOND chunk it processes in every tile (steady state of the TMA epilogue's chain):
+// 0 previous chunk's store issued, 1 buffers free + residual requested, 2 tcgen05.ld landed, 3 accumulator released (last chunk),
+// 4 rows done, 5 16-bit rows in shared memory, 6 proxy fence + warp sync, 7 store issued
+__device__ __forceinline__ void trace_m16(int trc, int tile_local, int slot) {
+  if ((trc & 16) && tile_local < GEMM_TRACE_TILES) g_gemm_trace[tile_local * 8 + slot] = clock64();
 }
 // mode 8: epilogue-internal stamps of warp 2 / lane 0 for the first chunk of every tile
 __device__ __forceinline__ void trace_epi(int trc, int tile_local, int slot) {
@@ -190,7 +197,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmTcParams& p, int tile
   t.h0 = th_i * p.bh;
   t.nb0 = tn_i * p.bn;
   t.n0 = n_tile * p.block_n;
-  t.kb_begin = t.z * p.per_split;
+  t.kb_begin = p.up_all ? 0 : t.z * p.per_split;       // up_all: z is the up-sampling phase, every tile reduces over all of k
   t.nkb = min(p.nkb_total, t.kb_begin + p.per_split) - t.kb_begin;
   return t;
 }
@@ -391,7 +398,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step, ++ltp) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         trace_stamp(trc, ltp, 0);
-        const int wn = t.n0 + cta_rank * b_rows;
+        // up_all: phase z = 2a + b reads the input at rows a - 1 + u, columns b - 1 + v and its own Cout weight rows
+        const int wn = t.n0 + cta_rank * b_rows + (p.up_all ? t.z * p.N : 0);
+        const int a3h = p.up_all ? (t.z >> 1) - 1 : p.a3_h0, a3w = p.up_all ? (t.z & 1) - 1 : p.a3_w0;
         int cb = 0, kx = 0;
         bool extra = false;
         for (int i = 0; i < p.a3_iters; ++i) {
@@ -407,7 +416,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
               if (leader) mbar_arrive_expect_tx(&full_bar[s], tx3);
               const int wk = kx * ctot + cb * GEMM_BK;                    // tap (ky, kx) starts at (ncol ky + kx) * ctot
               if constexpr (CG == 2) {
-                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0 + kx + p.a3_w0, 0, t.h0 + p.a3_h0, t.nb0);
+                tma_load_5d_pair(ma, &full_bar[s], a_dst, c, t.w0 + kx + a3w, 0, t.h0 + a3h, t.nb0);
                 for (int ky = 0; ky < nrow; ++ky) {
                   tma_load_2d_pair(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + ncol * ky * ctot, wn);
                   if (p.n_acc == 2)
@@ -415,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                                      wk + ncol * ky * ctot, wn + p.acc_n);
                 }
               } else {
-                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0 + kx + p.a3_w0, 0, t.h0 + p.a3_h0, t.nb0);
+                tma_load_5d(ma, &full_bar[s], a_dst, c, t.w0 + kx + a3w, 0, t.h0 + a3h, t.nb0);
                 for (int ky = 0; ky < nrow; ++ky) {
                   tma_load_2d(&p.map_w, &full_bar[s], b_dst + ky * b_stage_bytes, wk + ncol * ky * ctot, wn);
                   if (p.n_acc == 2)
@@ -465,7 +474,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       int tap = t.kb_begin / p.cblocks;
       int cb = t.kb_begin - tap * p.cblocks;
       if (tap >= p.ntaps) { tap = p.ntaps; cb = t.kb_begin - p.ntaps * p.cblocks; }    // inside the extra 1x1 source
-      const int wn = t.n0 + cta_rank * b_rows;
+      const int wn = t.n0 + cta_rank * b_rows + (p.up_all ? t.z * p.N : 0);
+      const int up_dh = p.up_all ? (t.z >> 1) : 0, up_dw = p.up_all ? (t.z & 1) : 0;   // tap_dh / tap_dw hold phase 0's offsets
       for (int i = 0; i < t.nkb; ++i) {
         mbar_wait(&empty_bar[s], ph, 1);
         uint8_t* a_dst = smem + s * stage_bytes;
@@ -477,9 +487,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int c = (second ? (cb - cbl0) : cb) * GEMM_BK;
         const int wk = tap * ctot + cb * GEMM_BK;
         const int ca = c + p.tap_dc_sel[tap] * p.tap_dc_unit;
-        const int cw = t.w0 + p.tap_dw[tap];
+        const int cw = t.w0 + p.tap_dw[tap] + up_dw;
         const int c2 = p.tap_d2[tap];
-        const int chh = t.h0 + p.tap_dh[tap];
+        const int chh = t.h0 + p.tap_dh[tap] + up_dh;
         if (elect_one()) {
           // the leader's barrier collects the bytes of both CTAs
           if (leader) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
@@ -751,6 +761,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
       };
       // chunk prologue: free the buffers of the chunk before the previous one and request the next residual -
       // everything that does not need the accumulator
+      bool tr16 = false;                           // trace mode 16: the chunk being processed is the stamped one
+      const bool tr16_lane = (trc & 16) && e == 0 && lane == 0;
       // in w64 mode `ch` still counts 32-column chunks; unit = ch >> 1, half = ch & 1
       auto first_of_unit = [&](int ch) { return !w64 || (ch & 1) == 0; };
       auto last_of_unit = [&](int ch) { return !w64 || (ch & 1) == 1 || !valid(ch + 1); };
@@ -763,7 +775,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         if (has_res) issue_prefetch();
       };
       // chunk body: accumulator row in v (loaded and waited for)
-      auto post = [&](const uint32_t (&v)[32], int ch) {
+      auto post = [&](uint32_t (&v)[32], int ch, int ch_next, bool more) {
         const uint32_t sub4 = w64 ? (uint32_t)((ch & 1) * 4) : 0u;           // first 16-byte piece of this chunk in its row
         const int col0 = t.n0 + (w64 ? (ch & ~1) : ch) * 32;               // first column of the unit's store
         const int ord = w64 ? 2 * (((ch >> 1) - ch_first) >> 1) + (ch & 1) : (ch - ch_first) >> 1;
@@ -802,7 +814,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             default: epi_rows<true, true, true, true>(v, pk, srow, sx, bline, rowb, p.act); break;
           }
         }
+        // the row is in x / pk now: the next chunk's tcgen05.ld goes into the SAME registers and lands while this chunk
+        // is staged, fenced and stored
+        if (more) tmem_ld32(taddr(ch_next), v);
         if (t0) trace_epi(trc, lt, 6);
+        if (tr16) trace_m16(trc, lt, 4);
         const uint32_t hbuf = b16_base + (uint32_t)b16 * b16_bytes;
         if (b16out) {
           const uint32_t hrow = hbuf + (uint32_t)lane * row16;
@@ -812,10 +828,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                          "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3])
                          : "memory");
         }
+        if (tr16) trace_m16(trc, lt, 5);
         if (!last_of_unit(ch)) return;            // w64: the second half of the row follows, one store for both
         fence_proxy_async();
         __syncwarp();
         if (t0) trace_epi(trc, lt, 7);
+        if (tr16) trace_m16(trc, lt, 6);
         if (p.gn_part != nullptr) {
           // GroupNorm statistics of the chunk (rank-2 outputs, fp32 result resident in the slot): lane = column,
           // 32 conflict-free reads down the swizzled rows
@@ -848,33 +866,37 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           bulk_commit();
         }
         if (t0) trace_epi(trc, lt, 4);
+        if (tr16) trace_m16(trc, lt, 7);
         if (nslot > 0 && ++slot == nslot) { slot = 0; rphase ^= 1u; }
         b16 ^= 1;
       };
       const int ch0 = w64 ? 2 * ch_first : ch_first;
       if (slab_ok && valid(ch0)) {
-        // two register buffers: the accumulator chunk after this one is in flight (tcgen05.ld) while this one
-        // goes through bias / residual / staging
-        uint32_t va[32], vb[32];
+        // ONE register buffer and one copy of the chunk body: the next chunk's tcgen05.ld is issued as soon as the
+        // current rows have been consumed. (The first form kept two buffers and two unrolled copies of the body; ncu
+        // on the 65536 x 320 x 320 projection: 27 % of the stall samples "no instruction", instruction-cache hit rate
+        // 85 % - two warps per sub-partition walking ~25 KB of straight-line code. Half the code, 32 registers less.)
+        uint32_t v[32];
         int ch = ch0;
-        tmem_ld32(taddr(ch), va);
+        int nth = 0;
+        tmem_ld32(taddr(ch), v);
         for (;;) {
+          const bool stamp = tr16_lane && nth == 1;          // trace mode 16: this warp's second chunk of the tile
           if (first_of_unit(ch)) pre(ch);
+          if (stamp) trace_m16(trc, lt, 1);
           tmem_ld_wait();
-          const int ch_b = next_chunk(ch);
-          const bool n1 = valid(ch_b);
-          if (n1) tmem_ld32(taddr(ch_b), vb); else release_acc();
-          post(va, ch);
-          if (!n1) break;
-          ch = ch_b;
-          if (first_of_unit(ch)) pre(ch);
-          tmem_ld_wait();
-          const int ch_a = next_chunk(ch);
-          const bool n2 = valid(ch_a);
-          if (n2) tmem_ld32(taddr(ch_a), va); else release_acc();
-          post(vb, ch);
-          if (!n2) break;
-          ch = ch_a;
+          if (stamp) trace_m16(trc, lt, 2);
+          const int ch_next = next_chunk(ch);
+          const bool more = valid(ch_next);
+          if (!more) release_acc();                          // all tcgen05.ld of this accumulator have completed
+          if (stamp) trace_m16(trc, lt, 3);
+          tr16 = stamp;
+          post(v, ch, ch_next, more);
+          tr16 = false;
+          if (!more) break;
+          if (tr16_lane && nth == 0) trace_m16(trc, lt, 0);
+          ch = ch_next;
+          ++nth;
         }
       } else {
         release_acc();
@@ -928,7 +950,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         const int ww = t.w0 + (rdec[i] & 0xff), hh = t.h0 + ((rdec[i] >> 8) & 0xff), nn = t.nb0 + dn;
         const bool ok = (dn < p.bn) && (ww < p.WO) && (hh < p.HO) && (nn < p.NB);
         // output row index, -1 = outside the tensor (up-sampling phases scatter into the 2x larger output)
-        mr[i] = !ok ? -1 : (p.up ? ((nn * p.HO + hh) * 2 + p.up_a) * (2 * p.WO) + 2 * ww + p.up_b
+        const int ua = p.up_all ? (t.z >> 1) : p.up_a, ub = p.up_all ? (t.z & 1) : p.up_b;
+        mr[i] = !ok ? -1 : (p.up ? ((nn * p.HO + hh) * 2 + ua) * (2 * p.WO) + 2 * ww + ub
                                  : (nn * p.HO + hh) * p.WO + ww);
       }
     };
@@ -996,7 +1019,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
           const int dn = r0 / plane;
           const int sn = t.nb0 + dn;
           gn_ok = (dn < p.bn) && (sn < p.NB);
-          gn_slab = (long long)sn * p.gn_stride + p.gn_off + t.sp * p.gn_spq + (r0 - dn * plane) / 32;
+          gn_slab = (long long)sn * p.gn_stride + (p.up_all ? t.z * p.gn_K : p.gn_off) + t.sp * p.gn_spq + (r0 - dn * plane) / 32;
         }
       }
       if (e == 0 && lane == 0) { trace_stamp(trc, lt, 5); trace_epi(trc, lt, 0); }
@@ -1498,8 +1521,9 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
       set_error("sdb_gemm_tc: stride-2 conv needs even H, W and a single source");
       return SDB_ERR_UNSUPPORTED;
     }
-    if (up && (a->up_phase < 0 || a->up_phase > 3 || a->nsplit > 1 || a->residual != nullptr)) {
-      set_error("sdb_gemm_tc: CONV2X2_UP needs up_phase in 0..3, no split-K and no residual");
+    if (up && (a->up_phase < 0 || a->up_phase > 4 || a->nsplit > 1 || a->residual != nullptr)) {
+      set_error("sdb_gemm_tc: CONV2X2_UP needs up_phase in 0..3 (or 4: all phases, w = [4][Cout][4 C]), no split-K and "
+                "no residual");
       return SDB_ERR_UNSUPPORTED;
     }
     if (a->C0 % 64 != 0) { set_error("sdb_gemm_tc: conv needs C0 %% 64 == 0"); return SDB_ERR_UNSUPPORTED; }
@@ -1507,7 +1531,8 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     p.ntaps = up ? 4 : 9;
     if (pick_tile_box(p.NB, p.HO, p.WO, &p.bw, &p.bh, &p.bn)) { set_error("tile box"); return SDB_ERR_ARG; }
     if (up) {
-      p.up = 1; p.up_a = a->up_phase >> 1; p.up_b = a->up_phase & 1;
+      p.up = 1; p.up_all = (a->up_phase == 4) ? 1 : 0;
+      p.up_a = p.up_all ? 0 : a->up_phase >> 1; p.up_b = p.up_all ? 0 : a->up_phase & 1;
       for (int u = 0; u < 2; ++u)
         for (int v = 0; v < 2; ++v) {
           const int t = u * 2 + v;
@@ -1604,7 +1629,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
   if (a->cta_pair == 1) cg = 1;
   if (a->cta_pair == 2) cg = 2;
   {
-    uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)a->Cout};
+    uint64_t dims[2] = {(uint64_t)p.ktot, (uint64_t)a->Cout * (p.up_all ? 4u : 1u)};     // up_all: the four phases' rows
     const long long ldw = a->ldw ? a->ldw : p.ktot;
     uint64_t str[1] = {(uint64_t)ldw * 2};
     uint32_t box[2] = {64, (uint32_t)(p.acc_n / cg)};
@@ -1808,7 +1833,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     p.gn_part = a->gn_part;
     p.gn_K = K;
     p.gn_stride = p.up ? 4 * K : K;
-    p.gn_off = p.up ? a->up_phase * K : 0;
+    p.gn_off = (p.up && !p.up_all) ? a->up_phase * K : 0;
     p.gn_hw = a->gn_hw;
     const int plane = p.bw * p.bh;
     p.gn_spq = (p.a_rank == 5) ? (plane / 32 < 4 ? plane / 32 : 4) : 0;
@@ -1828,7 +1853,7 @@ extern "C" int sdb_gemm_tc(const sdb_gemm_args* a, void* stream_) {
     }
   }
   const long long row_tiles = (m_tiles + cg - 1) / cg;        // 256-row tiles in pair mode
-  const long long total_tiles = row_tiles * n_tiles * nsplit;
+  const long long total_tiles = row_tiles * n_tiles * (p.up_all ? 4 : nsplit);
   if (total_tiles > 2147483647LL) { set_error("sdb_gemm_tc: too many tiles"); return SDB_ERR_UNSUPPORTED; }
   p.m_tiles = (int)row_tiles;
   p.n_tiles = n_tiles;

@@ -75,6 +75,7 @@ def _chk(t, dtype, name):
 
 
 import os as _os
+_UP_SEPARATE = _os.environ.get("SDB_UP_SEPARATE") == "1"   # A/B switch: four launches per up-sampling conv (one per phase)
 _NO_EPI_W64 = _os.environ.get("SDB_NO_EPI_W64") == "1"   # A/B switch (also read by the library): 32-column stores only
 _NO_WIDE = _os.environ.get("SDB_NO_WIDE") == "1"     # A/B switch: never pick the wide (320-column) tiles
 _A3_CHOOSER = _os.environ.get("SDB_A3_CHOOSER") != "0"   # A/B switch: the tile chooser ignores filter-column staging
@@ -256,16 +257,17 @@ def gemm(a0, w, cout, *, kind=GEMM_LINEAR, a1=None, bias=None, residual=None, ac
         # one key per launch VARIANT: everything that changes the FLOPs or the bytes of the launch is in it, so the
         # per-shape averages bench.py reports are averages over identical launches
         k_total = ntaps * (c0 + c1) + cx0 + cx1
+        nph = 4 if (kind == GEMM_CONV2X2_UP and up_phase == 4) else 1       # phases computed by this launch
         res_b = residual.element_size() if residual is not None else 0
         shape = (f"rows={rows} cin={c0 + c1} cout={cout} taps={ntaps} cx={cx0 + cx1} "
                  f"out={'f32' if out_fp32 else ('f16' if out_f16 else 'bf16')} res={str(residual.dtype).replace('torch.', '').replace('float', 'f') if res_b else 'none'} "
                  f"out2={1 if out2 is not None else 0} gn={1 if part is not None else 0} bn={block_n} split={nsplit} "
                  f"ab={'f16' if op16 == torch.float16 else 'bf16'}"
-                 + (f" hw={rows // conv_dims[0]}" if conv_dims is not None else ""))
+                 + (f" hw={rows // conv_dims[0]}" if conv_dims is not None else "") + (" phases=4" if nph == 4 else ""))
         keep = (a0, a1, w, bias, residual, out, out2, ws, part, ax0, ax1)     # the relaunch closure owns its operands
         ev = _prof("gemm_tc_conv3x3" if ntaps != 1 else "gemm_tc_linear",
-                   2.0 * rows * cout * k_total,
-                   2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * k_total) + out.numel() * out.element_size()
+                   2.0 * rows * cout * k_total * nph,
+                   2.0 * (rows * (c0 + c1 + cx0 + cx1) + cout * k_total * nph) + out.numel() * out.element_size()
                    + rows * cout * res_b + (rows * cout * 2 if out2 is not None else 0),
                    shape=shape,
                    relaunch=lambda: (keep, _ext.check(lib.sdb_gemm_tc(ctypes.byref(args), _stream()), "sdb_gemm_tc"))[1])
@@ -309,9 +311,15 @@ def conv_up2x(x, w4, cout, bias=None, *, out2=False, gn_samples=None, out16=torc
         k = lib.sdb_gemm_gn_slabs(GEMM_CONV2X2_UP, n, h, wd, 0, 0)
         if k > 0:
             part = torch.empty((n, 4 * k, cout, 2), device=x.device, dtype=torch.float32)
-    for phase in range(4):
-        gemm(x, w4[phase], cout, kind=GEMM_CONV2X2_UP, bias=bias, conv_dims=(n, h, wd), c0=c, out=out, out_fp32=True,
-             out2=o2, out16=out16, up_phase=phase, gn_part=part, block_n=block_n)
+    if _UP_SEPARATE:                             # A/B switch: one launch per phase
+        for phase in range(4):
+            gemm(x, w4[phase], cout, kind=GEMM_CONV2X2_UP, bias=bias, conv_dims=(n, h, wd), c0=c, out=out,
+                 out_fp32=True, out2=o2, out16=out16, up_phase=phase, gn_part=part, block_n=block_n)
+    else:
+        # up_phase = 4: ONE launch, the tile index carries the phase (4x the tiles: the 8x8 -> 16x16 layer of a batch of
+        # 16 has 32 tiles per phase for 74 CTA-pair slots)
+        gemm(x, w4.view(4 * cout, -1), cout, kind=GEMM_CONV2X2_UP, bias=bias, conv_dims=(n, h, wd), c0=c, out=out,
+             out_fp32=True, out2=o2, out16=out16, up_phase=4, gn_part=part, block_n=block_n)
     return out, o2, part
 
 

@@ -952,3 +952,13 @@ def test_conv_up2x_phases(N, H, W, Cin, Cout, dt):
     assert out2.dtype == dt and torch.equal(out2, out.to(dt))
     if part is not None:
         _check_partials(part, out.reshape(-1, Cout), N, "conv_up2x")
+    # the single launch over all four phases (up_phase = 4) equals four per-phase launches bit for bit
+    sep = torch.empty_like(out)
+    sep2 = torch.empty_like(out2)
+    part_sep = torch.zeros_like(part) if part is not None else None
+    for phase in range(4):
+        ops.gemm(x, w4[phase], Cout, kind=ops.GEMM_CONV2X2_UP, bias=b, conv_dims=(N, H, W), c0=Cin, out=sep,
+                 out_fp32=True, out2=sep2, out16=dt, up_phase=phase, gn_part=part_sep)
+    assert torch.equal(out, sep) and torch.equal(out2, sep2)
+    if part is not None:
+        assert torch.equal(part, part_sep)
