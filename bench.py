@@ -553,7 +553,11 @@ def main():
             k_conv = top([kv for kv in convs if size_of(kv) == dom_size])
             k_attn = top(fam("attention"))
             k_lin = top([kv for kv in fam("gemm_tc_linear") if kv[1]["flops"] / max(kv[1]["bytes"], 1.0) < ridge])
-            k_gn, k_ln = top(fam("groupnorm")), top(fam("layernorm"))
+            # GroupNorm / LayerNorm: the variant that moves the most algorithmic bytes per evaluation (a deterministic
+            # choice; by time the 8 x 8 level's one-pass GroupNorm - 10 MB per launch, L2-resident, launch-latency-bound -
+            # can come out on top and says nothing about HBM)
+            top_bytes = lambda kvs: max(kvs, key=lambda kv: kv[1]["bytes"])[0] if kvs else None
+            k_gn, k_ln = top_bytes(fam("groupnorm")), top_bytes(fam("layernorm"))
             roof = roof_of(k_conv, "tensor")
             gemm = [v for k, v in summ.items() if k.startswith("gemm_tc")]
             roof["all_gemm_tc_launches"] = {"launches": sum(v["launches"] for v in gemm), "ms": sum(v["ms"] for v in gemm),
@@ -571,7 +575,7 @@ def main():
                 {"shape": f"{k[0]} {k[1]}", "launches": v["launches"], "us": round(1e3 * v["ms"] / v["launches"], 1),
                  "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None,
                  "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)}
-                for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:32]]
+                for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:80]]
             del prof, relaunch, shapes, summ
 
     fault = _ext.read_fault()
@@ -602,6 +606,9 @@ def main():
                        "cfg_scale": CFG, "parallelism": f"seed-sharded x{world}, no collective",
                        "geglu_folded": bool(engine.FOLD_GEGLU), "upsample_folded": bool(engine.FOLD_UPSAMPLE),
                        "cfg_prefix_shared": bool(engine.SHARE_CFG_PREFIX),
+                       "storage": "fp32 residual stream, latents and noise; 16-bit tensor-core operands (IEEE half at "
+                                  "the full-resolution level, bf16 below); IEEE-half resblock hidden tensor "
+                                  f"({bool(engine.HID_F16)}) and attention-block token stream ({bool(engine.TOK_F16)})",
                        "unet_gflop_per_image_step_algorithmic": UNET_GFLOP_PER_IMAGE_STEP,
                        "l2": "inputs larger than L2: 1.7 GB of bf16 weights streamed per UNet evaluation"},
             "clocks": clk, "e2e": e2e, "gpu_launches": gpu_launches,

@@ -29,27 +29,38 @@ def cases(B):
     N = 2 * B
     out = []
 
-    def lin(name, S, K, Cout, count, res=False, fp32=False):
+    def lin(name, S, K, Cout, count, res=False, fp32=False, half=False):
+        """half=True: IEEE-half residual and output (the attention blocks' token stream)."""
         M = N * S
         a = bf(M, K)
         w = bf(Cout, K, scale=K ** -0.5)
         b = torch.randn(Cout, device=DEV)
         r = torch.randn(M, Cout, device=DEV) if res else None
+        if half and r is not None:
+            r = r.half()
         fl = 2.0 * M * K * Cout
         out.append((f"linear_{name}_{M}x{K}x{Cout}", count, fl,
-                    lambda: ops.linear(a, w, bias=b, residual=r, out_fp32=fp32, cta_pair=PAIR)))
+                    lambda: ops.linear(a, w, bias=b, residual=r, out_fp32=fp32, cta_pair=PAIR,
+                                       out16=torch.float16 if half else torch.bfloat16)))
 
-    def conv(name, Hh, C0, C1, Cout, count, kind=ops.GEMM_CONV3X3_S1, res=False):
-        x0 = bf(N, Hh, Hh, C0)
-        x1 = bf(N, Hh, Hh, C1) if C1 else None
-        w = bf(Cout, 9 * (C0 + C1), scale=(9 * (C0 + C1)) ** -0.5)
+    def conv(name, Hh, C0, C1, Cout, count, kind=ops.GEMM_CONV3X3_S1, res=False, cx=0, f16=False):
+        """cx > 0: conv_merged of a channel-changing resblock - the 1x1 skip convolution of a cx-channel block input
+        rides as extra k-blocks, IEEE-half operands, fp32 output with GroupNorm partial sums (the launch bench.py's
+        `roofline` reports)."""
+        dt = torch.float16 if f16 else torch.bfloat16
+        x0 = bf(N, Hh, Hh, C0).to(dt)
+        x1 = bf(N, Hh, Hh, C1).to(dt) if C1 else None
+        ax = bf(N, Hh, Hh, cx).to(dt) if cx else None
+        ktot = 9 * (C0 + C1) + cx
+        w = bf(Cout, ktot, scale=ktot ** -0.5).to(dt)
         b = torch.randn(Cout, device=DEV)
         ho = Hh // 2 if kind != ops.GEMM_CONV3X3_S1 else Hh
-        fl = 2.0 * N * ho * ho * Cout * 9 * (C0 + C1)
+        fl = 2.0 * N * ho * ho * Cout * ktot
         r = torch.randn(N * ho * ho, Cout, device=DEV) if res else None
         out.append((f"conv3x3_{name}_{C0 + C1}_{Cout}_{Hh}", count, fl,
                     lambda: ops.gemm(x0, w, Cout, kind=kind, a1=x1, bias=b, conv_dims=(N, Hh, Hh), c0=C0, c1=C1,
-                                     residual=r, out_fp32=True, out2=True if res else None, cta_pair=PAIR)))
+                                     residual=r, out_fp32=True, out2=True if res else None, cta_pair=PAIR, ax0=ax,
+                                     gn_samples=N if cx else None)))
 
     def attn(name, S, Skv, d, count):
         heads = 8
@@ -93,11 +104,24 @@ def cases(B):
         out.append((f"groupnorm_{name}_{C0 + C1}_{Hh}_{'f32' if fp32 else 'bf16'}", count, nbytes * 1e3,   # "flops" column = bytes*1e3 -> reads as GB/s
                     lambda: ops.groupnorm(x0, g, b, x1=x1, silu=True)))
 
-    def lnorm(S, C, count):
+    def lnorm(S, C, count, half=False):
         x = torch.randn(N * S, C, device=DEV)
+        x = x.half() if half else x
         g = torch.randn(C, device=DEV)
         b = torch.randn(C, device=DEV)
-        out.append((f"layernorm_{N * S}x{C}", count, 6.0 * N * S * C * 1e3, lambda: ops.layernorm(x, g, b)))
+        out.append((f"layernorm_{'h16_' if half else ''}{N * S}x{C}", count, (4.0 if half else 6.0) * N * S * C * 1e3,
+                    lambda: ops.layernorm(x, g, b)))
+
+    def gnorm_parts(name, Hh, C0, count):
+        """IEEE-half input, statistics from epilogue partial sums (the resblock's hidden tensor): reduce + apply."""
+        x0 = torch.randn(N, Hh, Hh, C0, device=DEV).half()
+        k = max(1, Hh * Hh // 128)
+        xs = x0.float().view(N, k, -1, C0)
+        part = torch.stack([xs.sum(2), (xs * xs).sum(2)], dim=-1).contiguous()
+        g = torch.randn(C0, device=DEV)
+        b = torch.randn(C0, device=DEV)
+        out.append((f"groupnorm_{name}_{C0}_{Hh}_f16", count, 4.0 * N * Hh * Hh * C0 * 1e3,
+                    lambda: ops.groupnorm(x0, g, b, silu=True, part0=part, out_dtype=torch.float16, fused=False)))
 
     gnorm("x", 64, 320, 0, 13)
     gnorm("hid", 64, 320, 0, 7, fp32=False)
@@ -110,17 +134,24 @@ def cases(B):
     gnorm("cat", 16, 1280, 1280, 3)
     gnorm("x", 8, 1280, 0, 6)
     gnorm("cat", 8, 1280, 1280, 3)
+    gnorm_parts("hidparts", 64, 320, 7)
+    gnorm_parts("hidparts", 32, 640, 6)
     lnorm(4096, 320, 15)
     lnorm(1024, 640, 15)
     lnorm(256, 1280, 15)
+    lnorm(4096, 320, 15, half=True)
+    lnorm(1024, 640, 15, half=True)
+    lnorm(256, 1280, 15, half=True)
     for S, C in ((4096, 320), (1024, 640), (256, 1280)):
-        lin("proj", S, C, C, 15, res=True, fp32=True)     # out_proj x2, q_proj, conv_in/out
+        lin("proj", S, C, C, 15, res=True, fp32=True)     # conv_output / block outputs: fp32 residual stream
+        lin("tok", S, C, C, 10, res=True, half=True)      # out_proj x2: IEEE-half token stream
         lin("qk", S, C, 2 * C, 5)
         lin("geglu1", S, C, 4 * C, 5)
         lin("geglu2", S, 4 * C, C, 5, res=True)
         attn("self", S, S, C // 8, 5)
         attn("cross", S, 77, C // 8, 5)
     conv("res", 64, 320, 0, 320, 4)
+    conv("mergedskip640", 64, 320, 0, 320, 2, cx=640, f16=True)   # decoders 10/11: conv_merged + 1x1 skip of 640 channels
     conv("merged", 64, 320, 0, 320, 5, res=True)      # conv_merged: fp32 residual in, fp32 + bf16 out
     conv("res", 32, 640, 0, 640, 3)
     conv("merged", 32, 640, 0, 640, 5, res=True)

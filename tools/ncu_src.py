@@ -19,7 +19,10 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg",
         "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
-        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem"]
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+        "sm__icc_request_hit_rate.pct", "smsp__pcsamp_sample_count", "smsp__pcsamp_warps_issue_stalled_no_instructions",
+        "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
+        "smsp__pcsamp_warps_issue_stalled_wait", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 for i, n in enumerate(h):
     if n in want:
         print(f"{n:75s} {u[i]:10s} {v[i]}")
