@@ -322,6 +322,10 @@ def _gn_samples(n, hw, c):
     (the small levels take the one-pass kernel, which reads the tensor once anyway)."""
     if not GN_EPILOGUE_STATS:
         return None
+    if hw >= ops.GN_PARTS_MIN_HW:
+        # from the 16 x 16 level up the epilogue statistics + the apply kernel beat the one-pass kernel (9.9 - 12.4 us
+        # against 14.9 us for 16 x 256 x 1280), and a skip concatenation needs the partial sums of BOTH its sources
+        return n
     from . import _ext
     return n if _ext.lib().sdb_groupnorm_fused_supported(hw, c, 0, 32) != 2 else None
 

@@ -354,6 +354,9 @@ def attention(q, k, vt, out, *, NB, heads, d, S, Skv, Skv_pad, ldq, ldk, ldo, ca
 
 
 _NO_GN_FUSED = _os.environ.get("SDB_NO_GN_FUSED") == "1"     # A/B switch: always stats + apply
+# pixels per sample from which a GroupNorm prefers the producers' epilogue statistics + the apply kernel over the
+# one-pass kernel when both are possible (A/B: SDB_GN_PARTS_MIN_HW=1000000 restores "one-pass wherever it fits")
+GN_PARTS_MIN_HW = int(_os.environ.get("SDB_GN_PARTS_MIN_HW", "256"))
 _NO_GN_EPI = _os.environ.get("SDB_NO_GN_EPI") == "1"         # A/B switch: ignore epilogue partial statistics
 
 
@@ -372,8 +375,9 @@ def groupnorm(x0, gamma, beta, *, x1=None, groups=32, eps=1e-5, silu=False, fuse
     hw = x0.numel() // (n * c0)
     c1 = x1.shape[-1] if x1 is not None else 0
     if fused is None:
+        parts_ok = part0 is not None and (x1 is None or part1 is not None) and not _NO_GN_EPI
         fused = (not _NO_GN_FUSED) and f0 == 1 and (x1 is None or f1 == 1) and \
-            lib.sdb_groupnorm_fused_supported(hw, c0, c1, groups) == 2
+            not (parts_ok and hw >= GN_PARTS_MIN_HW) and lib.sdb_groupnorm_fused_supported(hw, c0, c1, groups) == 2
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=out_dtype)
     nel0, nel1 = n * hw * c0, n * hw * c1
     in_bytes = nel0 * x0.element_size() + (nel1 * x1.element_size() if x1 is not None else 0)
