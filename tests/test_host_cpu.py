@@ -342,3 +342,29 @@ def test_resample_tables_reproduce_pillow():
     for w, h in ((768, 768), (300, 200), (1024, 520)):
         got = one_pass(one_pass(img, w, 1), h, 0)
         assert np.array_equal(got, np.array(dog.resize((w, h)))), (w, h)
+
+
+def test_tile_chooser_rules():
+    """ops._choose_tiling is pure host arithmetic: the rules the GPU measurements fixed hold -
+    160-column tiles for the UNet's channel counts, 256-column tiles for 16-bit-only results from 640 channels up (the
+    TMA epilogue then stores 64-column units), split-K only for long reductions on few row tiles, never a tile wider
+    than the output, and every choice is a width the kernel accepts."""
+    from pytorch_stable_diffusion_b200 import ops
+    valid = lambda bn: (bn % 16 == 0 and 16 <= bn <= 256) or bn == 320
+    # 16-bit result only, short reduction: 64-column store units want tile widths that are multiples of 64
+    assert ops._choose_tiling(65536, 1280, 5, 2, 0) == (256, 1)
+    assert ops._choose_tiling(16384, 640, 10, 2, 2) == (256, 1)
+    assert ops._choose_tiling(65536, 320, 5, 2, 2) == (160, 1)
+    # an fp32 tensor or an fp32 residual is involved: the 160-column tiles of the timelines
+    assert ops._choose_tiling(65536, 640, 10, 4 + 2, 4)[0] == 160
+    assert ops._choose_tiling(65536, 320, 45, 4, 0) == (160, 1)
+    # the 8 x 8 level: 4 row-tile pairs for 74 slots -> the long reduction is split
+    bn, ns = ops._choose_tiling(1024, 1280, 180, 4, 0)
+    assert ns > 1 and valid(bn)
+    for rows in (77, 1024, 4096, 16384, 65536, 147456):
+        for cout in (4, 48, 96, 320, 640, 768, 1280, 2560):
+            for nkb in (1, 5, 20, 45, 180):
+                for ob, rb in ((2, 0), (2, 2), (4, 4), (6, 4)):
+                    bn, ns = ops._choose_tiling(rows, cout, nkb, ob, rb)
+                    assert valid(bn) and ns >= 1 and ns <= max(1, nkb), (rows, cout, nkb, ob, rb, bn, ns)
+                    assert bn <= max(16, (cout + 15) // 16 * 16) or bn == 320 and cout % 320 == 0
