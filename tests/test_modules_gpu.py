@@ -297,6 +297,30 @@ def test_768_config(models, weights, oracle):
     assert p >= 35.0
 
 
+def test_non_square_image(models, weights, oracle):
+    """A non-square size (384 x 640 pixels: 48 x 80 latent; token counts 3840 / 960 / 240 / 60, tile boxes with
+    bw != bh, ragged 128-row tiles at the 6 x 10 level): one UNet evaluation for three samples and a 2-step generate
+    against the oracle. The reference accepts only 512 x 512 (WIDTH / HEIGHT are module constants, sd/pipeline.py:8-11);
+    height / width are keyword extensions, so this pins the extension rather than a reference behaviour."""
+    from pytorch_stable_diffusion_b200 import pipeline
+    from pytorch_stable_diffusion_b200.pipeline import get_time_embedding
+    gen = torch.Generator().manual_seed(57)
+    lat = torch.randn(3, 4, 48, 80, generator=gen).to(DEV)
+    ctx = torch.randn(3, 77, 768, generator=gen).to(DEV)
+    temb = get_time_embedding(420).to(DEV)
+    with torch.no_grad():
+        ref = oracle.diffusion_forward(weights["diffusion"], lat, ctx, temb)
+        report("Diffusion 48x80 latent, 3 samples", models["diffusion"](lat, ctx, temb), ref, TOL)
+    cond, uncond = canonical_tokens()
+    ref_img, _ = oracle.generate(weights, cond, uncond, seed=7, n_inference_steps=2, latent_hw=(48, 80), device=DEV)
+    img = pipeline.generate("a", "b", models=models, seeds=[7], n_inference_steps=2, device=DEV,
+                            tokenizer=StubTokenizer(), height=384, width=640)
+    assert img.shape == (384, 640, 3)
+    p = _psnr(oracle, img, ref_img)
+    print(f"[384x640 txt2img 2 steps] PSNR vs oracle = {p:.2f} dB", flush=True)
+    assert p >= 35.0
+
+
 def test_generate_without_cfg_and_prompt_lists(models, weights, oracle):
     """do_cfg=False (sd/pipeline.py:123-131) and per-sample prompts in one batch."""
     from pytorch_stable_diffusion_b200 import pipeline
