@@ -3,7 +3,7 @@
  * sampling path (CLIP -> [VAE encoder] -> DDPM/UNet loop with CFG -> VAE decoder).
  *
  * The reference (dawmro/pytorch_stable_diffusion) has no FFI layer: every arithmetic call is a
- * torch.nn / torch.nn.functional call inside sd/*.py. Each entry point below names the reference
+ * torch.nn / torch.nn.functional call inside the sd/ modules. Each entry point below names the reference
  * call sites it replaces (paths relative to the reference checkout). Conventions:
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked "host";
  *   - activations are NHWC (tokens x channels) bf16 unless stated otherwise; weights are bf16,
