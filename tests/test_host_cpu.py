@@ -368,3 +368,26 @@ def test_tile_chooser_rules():
                     bn, ns = ops._choose_tiling(rows, cout, nkb, ob, rb)
                     assert valid(bn) and ns >= 1 and ns <= max(1, nkb), (rows, cout, nkb, ob, rb, bn, ns)
                     assert bn <= max(16, (cout + 15) // 16 * 16) or bn == 320 and cout % 320 == 0
+
+
+def test_header_is_plain_c_and_matches_the_bindings(tmp_path):
+    """include/sdb200.h is the boundary a non-Python host binds to: it must compile as C99 on its own (no C++ / CUDA /
+    torch types), warning-free, and the struct sizes a C compiler computes must equal the ctypes mirrors in _ext.py."""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from pytorch_stable_diffusion_b200 import _ext
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "sdb200.h"\n'
+                   'int main(void) { printf("%d %zu %zu\\n", SDB_ABI_VERSION, sizeof(struct sdb_gemm_args), '
+                   'sizeof(struct sdb_attn_args)); return 0; }\n')
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ver, gemm, attn = (int(t) for t in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
+    assert gemm == ctypes.sizeof(_ext.GemmArgs) and attn == ctypes.sizeof(_ext.AttnArgs)
+    assert ver == _ext.lib().sdb_abi_version()        # the library was built from this header
