@@ -1,10 +1,13 @@
-"""Execution engine: packs module parameters into kernel-friendly bf16 device tensors and runs
-the four networks as sequences of C-ABI kernel launches over NHWC bf16 activations.
+"""Execution engine: packs module parameters into kernel-friendly 16-bit device tensors and runs
+the four networks as sequences of C-ABI kernel launches over NHWC activations.
 
-Data layout in HBM
-  activations   bf16, NHWC ([N, H, W, C]; the (B, S, C) token view of the attention blocks is the
-                same memory), fp32 only for latents, UNet output (eps), VAE moments and images
-  conv weights  bf16 [Cout][ky][kx][Cin] (K-major rows of 9*Cin), linear weights bf16 [out][in]
+Data layout in HBM (DESIGN.md section 3)
+  activations   NHWC ([N, H, W, C]; the (B, S, C) token view of the attention blocks is the same memory). The
+                residual stream proper (block inputs / outputs, skips, VAE stream, latents, eps, moments, images)
+                is fp32; tensor-core operands are 16-bit - IEEE half at the UNet's full-resolution level (TOP_F16),
+                bf16 elsewhere; the resblock's hidden tensor (HID_F16) and the attention blocks' token stream
+                (TOK_F16) are IEEE half
+  conv weights  16-bit [Cout][ky][kx][Cin] (K-major rows of 9*Cin), linear weights 16-bit [out][in]
   attention     QK projection output [tokens, 2C]; V produced transposed [C, N, S] by a swapped GEMM
   biases/affine fp32
 
@@ -279,14 +282,14 @@ def pack_self_attention(att, dev):
 # ------------------------------------------------------------------------------------------------
 # residual stream
 class Stream:
-    """A residual-stream activation: fp32 NHWC master `f` plus an optional bf16 shadow `b`.
+    """A residual-stream activation: fp32 NHWC master `f` plus an optional 16-bit shadow `b`.
 
-    Everything that is added to again later (block inputs/outputs, the token stream inside an
-    attention block, UNet skips) stays fp32 so that rounding does not accumulate along the ~60
-    residual additions of a UNet evaluation; the bf16 shadow exists only where a tensor-core kernel
-    reads the stream directly as its A operand (skip 1x1 convs, down/up-sampling convs, conv_output,
-    the VAE attention projections). Branch tensors (GroupNorm/LayerNorm outputs, conv hidden, Q/K/V,
-    attention outputs) are bf16."""
+    What is added to again from block to block (block inputs/outputs, UNet skips, the VAE stream) stays fp32
+    so that rounding does not accumulate along the residual additions of a UNet evaluation; the 16-bit shadow
+    (bf16, or IEEE half at the full-resolution level) exists only where a tensor-core kernel reads the stream
+    directly as its A operand (skip 1x1 convs, down/up-sampling convs, the VAE attention projections). Branch
+    tensors (GroupNorm/LayerNorm outputs, Q/K/V, attention outputs) are 16-bit; the tensors that live inside one
+    block - the resblock's hidden tensor, the attention block's token stream - are IEEE half (HID_F16, TOK_F16)."""
     __slots__ = ("f", "b", "gp")
 
     def __init__(self, f, b=None, gp=None):
