@@ -391,3 +391,26 @@ def test_header_is_plain_c_and_matches_the_bindings(tmp_path):
     ver, gemm, attn = (int(t) for t in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split())
     assert gemm == ctypes.sizeof(_ext.GemmArgs) and attn == ctypes.sizeof(_ext.AttnArgs)
     assert ver == _ext.lib().sdb_abi_version()        # the library was built from this header
+
+
+def _build_c_example(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("no gcc / CUDA headers")
+    from pytorch_stable_diffusion_b200 import _ext
+    _ext.lib()                                   # raises if the library is not built
+    csrc = os.path.join(ROOT, "pytorch_stable_diffusion_b200", "csrc")
+    exe = tmp_path / "abi_linear"
+    r = subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", "/usr/local/cuda/include", os.path.join(ROOT, "examples", "abi_linear.c"), "-L", csrc,
+                        "-lsdb200", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{csrc}", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_host_program_builds_against_the_library(tmp_path):
+    """examples/abi_linear.c - a C99 program with no Python and no torch - compiles and links against include/sdb200.h,
+    libsdb200.so and the CUDA runtime alone (it runs in tests/test_kernels_gpu.py::test_c_host_program)."""
+    _build_c_example(tmp_path)

@@ -962,3 +962,15 @@ def test_conv_up2x_phases(N, H, W, Cin, Cout, dt):
     assert torch.equal(out, sep) and torch.equal(out2, sep2)
     if part is not None:
         assert torch.equal(part, part_sep)
+
+
+def test_c_host_program(tmp_path):
+    """The boundary from the other side: examples/abi_linear.c (C99, links libsdb200.so + cudart only, no Python in the
+    process) runs one nn.Linear through sdb_gemm_tc and checks it against a double-precision host loop."""
+    import subprocess
+    from test_host_cpu import _build_c_example
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    print(r.stdout.strip(), r.stderr.strip(), flush=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
